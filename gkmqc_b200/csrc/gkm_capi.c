@@ -1,0 +1,414 @@
+/* gkm_capi.c -- the exported entry points: the extended ABI (include/gkm_b200.h) and
+ * the reference's own ABI (include/gkm_abi.h == src/libgkm.h of the reference),
+ * including gkm_main_pywrapper, the operator gkmQC calls (gkmkern_pylib.c:92-246).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gkm_internal.h"
+#include "gkm_options.h"
+
+/* ================================================================== */
+/* extended ABI                                                        */
+/* ================================================================== */
+int gkmb200_problem_upload(gkmb200_problem *p)
+{
+    if (!p) { gkm_set_error("null problem"); return 1; }
+    return gkm_dev_upload(p);
+}
+
+int gkmb200_problem_sqnorm(gkmb200_problem *p, double *out)
+{
+    if (!p || !out) { gkm_set_error("null argument"); return 1; }
+    if (gkm_dev_upload(p)) return 1;
+    memcpy(out, p->sqnorm, sizeof(double) * (size_t) p->n);
+    return 0;
+}
+
+int gkmb200_kernel_lower(gkmb200_problem *p, double **rows, int copy_threads)
+{
+    if (!p || !rows) { gkm_set_error("null argument"); return 1; }
+    return gkm_dev_compute(p, 0, p->n, 0, p->n, 1, NULL, 0, rows, NULL, copy_threads);
+}
+
+int gkmb200_kernel_block(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower, double *out, long ld)
+{
+    if (!p || !out) { gkm_set_error("null argument"); return 1; }
+    if (ld < ncols) { gkm_set_error("ld < ncols"); return 1; }
+    return gkm_dev_compute(p, row0, nrows, col0, ncols, lower, out, ld, NULL, NULL, 4);
+}
+
+int gkmb200_hist_block(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower, int32_t *hist)
+{
+    if (!p || !hist) { gkm_set_error("null argument"); return 1; }
+    return gkm_dev_compute(p, row0, nrows, col0, ncols, lower, NULL, 0, NULL, hist, 1);
+}
+
+int gkmb200_decision_values(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
+                            const double *alpha, double bias, double *out)
+{
+    return gkm_dev_decision(p, row0, nrows, col0, ncols, alpha, bias, out);
+}
+
+static gkmb200_stats g_last_stats; /* of the most recent gkm_main_pywrapper call */
+static long long g_last_nk = 0;
+
+int gkmb200_get_stats(const gkmb200_problem *p, gkmb200_stats *out)
+{
+    if (!out) return 1;
+    if (!p) { /* the pywrapper's problem does not outlive the call (ownership) */
+        *out = g_last_stats;
+        out->lmer_pairs = out->entries * g_last_nk * 2 * g_last_nk;
+        return 0;
+    }
+    *out = p->stats;
+    /* L-mer pair comparisons behind the entries of the last call, for uniform-length problems:
+     * n_a * 2 n_b per entry; ragged problems report the maximum-length figure */
+    int maxlen = 0;
+    for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
+    long long nk = maxlen - p->param.L + 1;
+    out->lmer_pairs = out->entries * nk * 2 * nk;
+    return 0;
+}
+
+int gkmb200_bench_lower_resident(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each)
+{
+    return gkm_dev_bench_lower(p, steps, warmup, flush_l2, ms_each);
+}
+
+int gkmb200_microbench(const char *what, double *result) { return gkm_dev_microbench(what, result); }
+
+/* ================================================================== */
+/* the operator: gkm_main_pywrapper (gkmkern_pylib.c:92-246)           */
+/* ================================================================== */
+int gkm_main_pywrapper(gkmOpt *opts, double **kmat, int *kmat_size)
+{
+    if (!opts || !kmat || !kmat_size) { fprintf(stderr, "gkm_main_pywrapper: null argument\n"); return 1; }
+    if (opts->verbosity < 0 || opts->verbosity > 4) {
+        /* the reference prints this and calls exit(0), taking the Python host down with it
+         * (gkmkern_pylib.c:135-137); an error return reaches the same sys.exit() in gkmsvm.py:90-92 */
+        fprintf(stderr, "Unknown verbosity: %d\n", opts->verbosity);
+        return 1;
+    }
+    gkmb200_set_verbosity(opts->verbosity);
+
+    gkm_parameter param;
+    memset(&param, 0, sizeof(param));
+    param.kernel_type = opts->kernel_type;
+    param.L = opts->L;
+    param.k = opts->k;
+    param.d = opts->d;
+    param.M = opts->M;
+    param.H = opts->H;
+    param.gamma = opts->gamma;
+    param.nthreads = 1;
+
+    gkm_log(GKM_LOG_INFO, "Arguments:");
+    gkm_log(GKM_LOG_INFO, "  posfile = %s", opts->posfile);
+    gkm_log(GKM_LOG_INFO, "  negfile = %s", opts->negfile);
+    gkm_log(GKM_LOG_INFO, "Parameters:");
+    gkm_log(GKM_LOG_INFO, "  kernel-type = %d", param.kernel_type);
+    gkm_log(GKM_LOG_INFO, "  L = %d", param.L);
+    gkm_log(GKM_LOG_INFO, "  k = %d", param.k);
+    gkm_log(GKM_LOG_INFO, "  d = %d", param.d);
+    if (param.kernel_type == EST_TRUNC_RBF || param.kernel_type == EST_TRUNC_PW_RBF)
+        gkm_log(GKM_LOG_INFO, "  gamma = %g", param.gamma);
+    if (param.kernel_type == EST_TRUNC_PW || param.kernel_type == EST_TRUNC_PW_RBF) {
+        gkm_log(GKM_LOG_INFO, "  M = %d", param.M);
+        gkm_log(GKM_LOG_INFO, "  H = %g", param.H);
+    }
+
+    const char *bad = gkm_param_problem(&param, gkm_opt_max_L()); /* L <= 12 unless GKM_MAX_L=16 */
+    if (bad) { gkm_set_error("%s", bad); return 1; }
+    if (!opts->posfile || !opts->negfile) { gkm_set_error("can't open file"); return 1; }
+
+    gkmb200_problem *p = gkmb200_problem_new(&param);
+    if (!p) return 1;
+    int rc = 1;
+    int npos = gkmb200_problem_read(p, opts->posfile, opts->negfile);
+    if (npos >= 0 && p->n > 0) {
+        int nt = opts->nthreads;
+        if (nt < 1) nt = 1;
+        rc = gkmb200_kernel_lower(p, kmat, nt);
+        if (!rc) {
+            kmat_size[0] = npos;
+            kmat_size[1] = p->n - npos;
+            g_last_stats = p->stats;
+            g_last_nk = 0;
+            for (int i = 0; i < p->n; i++) if (p->len[i] - param.L + 1 > g_last_nk) g_last_nk = p->len[i] - param.L + 1;
+            gkm_log(GKM_LOG_INFO, "kernel matrix: %d sequences, %lld entries, %d GPU(s), kernel %.1f ms, total %.1f ms",
+                    p->n, p->stats.entries, p->stats.devices, p->stats.kernel_ms, p->stats.wall_ms);
+        }
+    } else if (npos >= 0) {
+        gkm_set_error("no sequences in %s / %s", opts->posfile, opts->negfile);
+    }
+    gkmb200_problem_free(p);
+    return rc;
+}
+
+/* ================================================================== */
+/* the rest of libgkm.h, on top of the same engine                     */
+/* ================================================================== */
+/* per-kernel engine state hangs off gkm_kernel.prob_kmertree (opaque to callers) */
+typedef struct gkm_shadow {
+    gkmb200_problem *prob; /* device-resident image of prob_svm_data */
+    int dirty;
+} gkm_shadow;
+
+static gkm_shadow *shadow_of(gkm_kernel *kernel) { return (gkm_shadow *) (void *) kernel->prob_kmertree; }
+
+void gkmkernel_set_num_threads(gkm_parameter *param)
+{
+    /* the reference picks a 1/4/16-thread DFS here (libgkm.c:1187-1205); the GPU engine has no
+     * such mode, but the observable side effect on the parameter is kept */
+    if (param->nthreads != 1 && param->nthreads != 4 && param->nthreads != 16) {
+        gkm_log(GKM_LOG_WARN, "Supported number of threads are 1, 4 and 16. nthread is set to 1");
+        param->nthreads = 1;
+    }
+}
+
+gkm_kernel *gkmkernel_init(gkm_parameter *param)
+{
+    if (!param) return NULL;
+    gkmkernel_set_num_threads(param);
+    const char *bad = gkm_param_problem(param, GKM_MAX_L);
+    if (bad) { gkm_set_error("%s", bad); return NULL; }
+    gkm_kernel *kernel = (gkm_kernel *) calloc(1, sizeof(gkm_kernel));
+    if (!kernel) return NULL;
+    kernel->param = param;
+    double w[GKM_MAX_L + 1];
+    gkm_calc_weights(param->kernel_type, param->L, param->k, w);
+    for (int i = 0; i <= MAX_MM && i <= param->L; i++) kernel->weights[i] = w[i];
+    gkm_log(GKM_LOG_DEBUG, "gkm-kernel weights:");
+    for (int i = 0; i <= param->d; i++) gkm_log(GKM_LOG_DEBUG, "  c[%d] = %.6f", i, w[i]);
+    gkm_shadow *sh = (gkm_shadow *) calloc(1, sizeof(gkm_shadow));
+    kernel->prob_kmertree = (KmerTree *) (void *) sh;
+    kernel->mmcnt_nlookups = (param->L <= MMCNT_LOOKUPTAB_WIDTH) ? 1 : 2;
+    kernel->mmcnt_lookuptab_mask = 0xFFFF;
+    return kernel;
+}
+
+void gkmkernel_destroy(gkm_kernel *kernel)
+{
+    if (!kernel) return;
+    gkm_shadow *sh = shadow_of(kernel);
+    if (sh) { gkmb200_problem_free(sh->prob); free(sh); }
+    free(kernel->prob_svm_data);
+    free(kernel->prob_gkmkernel_index);
+    free(kernel->prob_libsvm_index);
+    free(kernel);
+}
+
+static char *dup_string(const char *s)
+{
+    size_t n = strlen(s) + 1;
+    char *r = (char *) malloc(n);
+    if (r) memcpy(r, s, n);
+    return r;
+}
+
+/* a gkm_data laid out like the reference's (libgkm.c:841-938); sqnorm comes from the GPU */
+gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seqid)
+{
+    if (!kernel || !seq) return NULL;
+    const gkm_parameter *pa = kernel->param;
+    const int len = (int) strlen(seq);
+    const int nk = len - pa->L + 1;
+    if (nk < 1) { gkm_set_error("sequence %s is shorter than L", sid ? sid : "?"); return NULL; }
+    gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
+    if (!d) return NULL;
+    d->sid = sid ? dup_string(sid) : NULL;
+    d->seqid = seqid;
+    d->seqlen = len;
+    d->seq_string = dup_string(seq);
+    d->seq = (u_int8_t *) malloc((size_t) len);
+    d->seq_rc = (u_int8_t *) malloc((size_t) len);
+    d->wt = (u_int8_t *) malloc((size_t) nk);
+    d->wt_rc = (u_int8_t *) malloc((size_t) nk);
+    d->kmerids = (int *) malloc(sizeof(int) * (size_t) nk);
+    d->kmerids_rc = (int *) malloc(sizeof(int) * (size_t) nk);
+
+    /* one-sequence problem: coding, and sqnorm = sqrt(Kraw(x,x)) on the device */
+    gkmb200_problem *one = gkmb200_problem_new(pa);
+    if (!one || gkmb200_problem_add(one, seq, len) < 0 || gkmb200_problem_codes(one, 0, d->seq, d->seq_rc) ||
+        gkm_dev_upload(one)) {
+        gkmb200_problem_free(one);
+        gkmkernel_delete_object(d);
+        return NULL;
+    }
+    d->sqnorm = one->sqnorm[0];
+    gkmb200_problem_free(one);
+    gkm_calc_posweights(nk, pa->kernel_type, pa->M, pa->H, d->wt, d->wt_rc);
+    /* leaf index of each L-mer in the reference's 4-ary tree (libgkm.c:891-908): base-4 digits 0..3 */
+    u_int8_t *strands[2] = { d->seq, d->seq_rc };
+    int *ids[2] = { d->kmerids, d->kmerids_rc };
+    for (int s = 0; s < 2; s++)
+        for (int j = 0; j < nk; j++) {
+            int v = 0;
+            for (int i = 0; i < pa->L; i++) v = v * 4 + (strands[s][i + j] - 1);
+            ids[s][j] = v;
+        }
+    gkm_log(GKM_LOG_TRACE, "%d's sqnorm is %f", seqid, d->sqnorm);
+    return d;
+}
+
+void gkmkernel_free_object(gkm_data *d)
+{
+    if (!d) return;
+    free(d->kmerids); free(d->kmerids_rc); free(d->seq_string); free(d->wt); free(d->wt_rc);
+    free(d->seq); free(d->seq_rc); free(d->sid);
+    d->kmerids = d->kmerids_rc = NULL;
+    d->seq_string = NULL; d->sid = NULL;
+    d->wt = d->wt_rc = d->seq = d->seq_rc = NULL;
+}
+
+void gkmkernel_delete_object(gkm_data *d)
+{
+    if (!d) return;
+    gkmkernel_free_object(d);
+    free(d);
+}
+
+/* rebuild the device image from prob_svm_data (order = current gkmkernel index order) */
+static int shadow_sync(gkm_kernel *kernel)
+{
+    gkm_shadow *sh = shadow_of(kernel);
+    if (!sh) return 1;
+    if (sh->prob && !sh->dirty) return 0;
+    gkmb200_problem_free(sh->prob);
+    sh->prob = gkmb200_problem_new(kernel->param);
+    if (!sh->prob) return 1;
+    static const char letters[4] = { 'A', 'C', 'G', 'T' };
+    char *buf = (char *) malloc(MAX_SEQ_LENGTH);
+    if (!buf) return 1;
+    for (int i = 0; i < kernel->prob_num; i++) {
+        const gkm_data *x = kernel->prob_svm_data[i];
+        if (!x->seq) { gkm_set_error("object %d was freed with gkmkernel_free_object", i); free(buf); return 1; }
+        for (int j = 0; j < x->seqlen; j++) buf[j] = letters[(x->seq[j] - 1) & 3];
+        if (gkmb200_problem_add(sh->prob, buf, x->seqlen) < 0) { free(buf); return 1; }
+    }
+    free(buf);
+    sh->dirty = 0;
+    return gkm_dev_upload(sh->prob);
+}
+
+/* "build the tree" (libgkm.c:1035-1056): here, make the sequence set resident on the GPUs */
+void gkmkernel_build_tree(gkm_kernel *kernel, gkm_data **x, int n)
+{
+    if (!kernel || !x || n < 0) return;
+    free(kernel->prob_svm_data);
+    free(kernel->prob_gkmkernel_index);
+    free(kernel->prob_libsvm_index);
+    kernel->prob_svm_data = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
+    kernel->prob_gkmkernel_index = (int *) malloc(sizeof(int) * (size_t) (n ? n : 1));
+    kernel->prob_libsvm_index = (int *) malloc(sizeof(int) * (size_t) (n ? n : 1));
+    memcpy(kernel->prob_svm_data, x, sizeof(gkm_data *) * (size_t) n);
+    kernel->prob_num = n;
+    for (int i = 0; i < n; i++) { kernel->prob_gkmkernel_index[i] = i; kernel->prob_libsvm_index[i] = i; }
+    gkm_shadow *sh = shadow_of(kernel);
+    if (sh) sh->dirty = 1;
+    if (n > 0 && shadow_sync(kernel)) gkm_log(GKM_LOG_ERROR, "gkmkernel_build_tree: %s", gkmb200_last_error());
+}
+
+/* K(prob[a], prob[j]) for j in [start,end) (libgkm.c:1156-1185) */
+double *gkmkernel_kernelfunc_batch_all(gkm_kernel *kernel, const int a, const int start, const int end, double *res)
+{
+    if (!kernel || !res || end < start) return res;
+    for (int j = 0; j < end - start; j++) res[j] = 0;
+    if (end == start) return res;
+    if (shadow_sync(kernel) ||
+        gkm_dev_compute(shadow_of(kernel)->prob, a, 1, start, end - start, 0, res, end - start, NULL, NULL, 1))
+        gkm_log(GKM_LOG_ERROR, "gkmkernel_kernelfunc_batch_all: %s", gkmb200_last_error());
+    return res;
+}
+
+/* the intended meaning of libgkm.c:1115-1153 -- K(prob[a], db_array[i]), normalised (+RBF);
+ * see SURVEY.md 3.4 for why the reference's own body does not compute that */
+double *gkmkernel_kernelfunc_batch(gkm_kernel *kernel, int a, const gkm_data **db_array, const int n, double *res)
+{
+    if (!kernel || !res || n < 0) return res;
+    for (int i = 0; i < n; i++) res[i] = 0;
+    if (n == 0 || a < 0 || a >= kernel->prob_num) return res;
+    static const char letters[4] = { 'A', 'C', 'G', 'T' };
+    gkmb200_problem *tmp = gkmb200_problem_new(kernel->param);
+    char *buf = (char *) malloc(MAX_SEQ_LENGTH);
+    int ok = tmp && buf;
+    for (int i = 0; ok && i <= n; i++) { /* db_array[0..n-1] then the query */
+        const gkm_data *x = (i < n) ? db_array[i] : kernel->prob_svm_data[a];
+        for (int j = 0; j < x->seqlen; j++) buf[j] = letters[(x->seq[j] - 1) & 3];
+        ok = gkmb200_problem_add(tmp, buf, x->seqlen) >= 0;
+    }
+    if (!ok || gkm_dev_compute(tmp, n, 1, 0, n, 0, res, n, NULL, NULL, 1))
+        gkm_log(GKM_LOG_ERROR, "gkmkernel_kernelfunc_batch: %s", gkmb200_last_error());
+    free(buf);
+    gkmb200_problem_free(tmp);
+    return res;
+}
+
+/* single pair; declared in libgkm.h:140 but defined nowhere upstream */
+double gkmkernel_kernelfunc(const gkm_data *da, const gkm_data *db)
+{
+    (void) da; (void) db;
+    gkm_set_error("gkmkernel_kernelfunc needs a kernel handle; use gkmkernel_kernelfunc_batch");
+    return NAN;
+}
+
+int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *posfile, const char *negfile)
+{
+    if (!kernel || !prob) return -1;
+    gkmb200_problem *p = gkmb200_problem_new(kernel->param);
+    if (!p) return -1;
+    int npos = gkmb200_problem_read(p, posfile, negfile);
+    if (npos < 0 || gkm_dev_upload(p)) { gkmb200_problem_free(p); return -1; }
+    const int n = p->n, L = kernel->param->L;
+    prob->l = n;
+    prob->y = (double *) malloc(sizeof(double) * (size_t) (n ? n : 1));
+    prob->x = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
+    static const char letters[4] = { 'A', 'C', 'G', 'T' };
+    for (int i = 0; i < n; i++) {
+        const int len = p->len[i], nk = len - L + 1;
+        gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
+        d->seqid = i; d->seqlen = len;
+        d->label = (i < npos) ? 1 : -1;
+        d->seq = (u_int8_t *) malloc((size_t) len);
+        d->seq_rc = (u_int8_t *) malloc((size_t) len);
+        d->wt = (u_int8_t *) malloc((size_t) nk);
+        d->wt_rc = (u_int8_t *) malloc((size_t) nk);
+        d->seq_string = (char *) malloc((size_t) len + 1);
+        gkmb200_problem_codes(p, i, d->seq, d->seq_rc);
+        for (int j = 0; j < len; j++) d->seq_string[j] = letters[p->code[i][j]];
+        d->seq_string[len] = '\0';
+        gkm_calc_posweights(nk, kernel->param->kernel_type, kernel->param->M, kernel->param->H, d->wt, d->wt_rc);
+        d->sqnorm = p->sqnorm[i];
+        prob->y[i] = d->label;
+        prob->x[i] = d;
+    }
+    /* keep the uploaded image: build_tree on exactly these objects can reuse it */
+    gkm_shadow *sh = shadow_of(kernel);
+    if (sh) { gkmb200_problem_free(sh->prob); sh->prob = p; sh->dirty = 1; }
+    else gkmb200_problem_free(p);
+    return npos;
+}
+
+void gkmkernel_swap_index(gkm_kernel *kernel, int i, int j)
+{
+    int *gi = kernel->prob_gkmkernel_index, *li = kernel->prob_libsvm_index;
+    int t = li[gi[i]]; li[gi[i]] = li[gi[j]]; li[gi[j]] = t;
+    t = gi[i]; gi[i] = gi[j]; gi[j] = t;
+}
+
+/* apply the accumulated permutation (libgkm.c:1084-1109): afterwards id i means what
+ * libsvm calls i; the device image is rebuilt in the new order on next use */
+void gkmkernel_update_index(gkm_kernel *kernel)
+{
+    const int n = kernel->prob_num;
+    gkm_data **fresh = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
+    for (int i = 0; i < n; i++) fresh[i] = kernel->prob_svm_data[kernel->prob_gkmkernel_index[i]];
+    free(kernel->prob_svm_data);
+    kernel->prob_svm_data = fresh;
+    for (int i = 0; i < n; i++) { kernel->prob_gkmkernel_index[i] = i; kernel->prob_libsvm_index[i] = i; }
+    gkm_shadow *sh = shadow_of(kernel);
+    if (sh) sh->dirty = 1;
+}

@@ -1,0 +1,788 @@
+/* gkm_device.cu -- device layer of gkmkern_pylib.so: GPU selection, the resident
+ * problem image, kernel launches over chunks of row tiles, and the return path
+ * into caller memory.
+ *
+ * Stands where the reference has its pthread row scheduler and row loop
+ * (gkmkern_pylib.c:70-90,169-216 -> libgkm.c:1156): thread t there takes rows
+ * t, t+T, ...; here one host thread per GPU takes whole chunks of row tiles, the
+ * GPU computes chunk i+1 while chunk i is copied D2H (second stream, pinned
+ * staging) and scattered into the caller's rows by `copy_threads` host threads.
+ * The caller's matrix is neither pinned nor contiguous (numpy rows with a
+ * 120 000-byte stride, gkmsvm.py:75-77), hence the bounce buffer.
+ * There is no collective: every chunk depends only on the replicated sequence image.
+ */
+#include <cuda_runtime.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "gkm_internal.h"
+#include "gkm_options.h"
+#include "gkm_lmer_kernel.cuh"
+
+#define GKM_MAX_DEV 16
+#define GKM_FLUSH_BYTES ((size_t) 256 << 20) /* > 126 MB L2 */
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            gkm_set_error("CUDA: %s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+extern "C" {
+const void *gkm_diag_fn_L2(int, int);  const void *gkm_diag_fn_L3(int, int);  const void *gkm_diag_fn_L4(int, int);
+const void *gkm_diag_fn_L5(int, int);  const void *gkm_diag_fn_L6(int, int);  const void *gkm_diag_fn_L7(int, int);
+const void *gkm_diag_fn_L8(int, int);  const void *gkm_diag_fn_L9(int, int);  const void *gkm_diag_fn_L10(int, int);
+const void *gkm_diag_fn_L11(int, int); const void *gkm_diag_fn_L12(int, int); const void *gkm_diag_fn_L13(int, int);
+const void *gkm_diag_fn_L14(int, int); const void *gkm_diag_fn_L15(int, int); const void *gkm_diag_fn_L16(int, int);
+}
+
+static const void *diag_fn(int L, int nb, int weighted)
+{
+    switch (L) {
+        case 2: return gkm_diag_fn_L2(nb, weighted);   case 3: return gkm_diag_fn_L3(nb, weighted);
+        case 4: return gkm_diag_fn_L4(nb, weighted);   case 5: return gkm_diag_fn_L5(nb, weighted);
+        case 6: return gkm_diag_fn_L6(nb, weighted);   case 7: return gkm_diag_fn_L7(nb, weighted);
+        case 8: return gkm_diag_fn_L8(nb, weighted);   case 9: return gkm_diag_fn_L9(nb, weighted);
+        case 10: return gkm_diag_fn_L10(nb, weighted); case 11: return gkm_diag_fn_L11(nb, weighted);
+        case 12: return gkm_diag_fn_L12(nb, weighted); case 13: return gkm_diag_fn_L13(nb, weighted);
+        case 14: return gkm_diag_fn_L14(nb, weighted); case 15: return gkm_diag_fn_L15(nb, weighted);
+        case 16: return gkm_diag_fn_L16(nb, weighted);
+        default: return NULL;
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* per-GPU resources, created lazily and kept for the life of the process
+ * (the ABI has no handle that survives gkm_main_pywrapper) */
+/* ------------------------------------------------------------------ */
+struct gkm_gpu {
+    int id;
+    int ready;
+    cudaStream_t sc, sx;       /* compute, copy */
+    cudaEvent_t k0[2], k1[2];  /* kernel start / end per staging slot */
+    cudaEvent_t cdone[2];      /* D2H complete per staging slot */
+    void *d_band[2];
+    size_t band_cap;
+    void *h_stage[2];
+    size_t stage_cap;
+    void *d_flush;
+};
+
+static gkm_gpu g_gpu[GKM_MAX_DEV];
+static int g_sel[GKM_MAX_DEV];
+static int g_nsel = -1;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+
+struct gkm_image {
+    uint32_t *planes;
+    int32_t *lens;
+    uint8_t *wend;
+    double *sqnorm;
+    double *full;       /* resident N x ldfull result (bench) */
+    size_t full_ld;
+};
+
+struct gkm_devstate {
+    int ndev;
+    int dev[GKM_MAX_DEV];
+    gkm_image img[GKM_MAX_DEV];
+};
+
+static double now_ms(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * (double) t.tv_sec + 1e-6 * (double) t.tv_nsec;
+}
+
+extern "C" int gkm_dev_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n && i < GKM_MAX_DEV; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+extern "C" int gkmb200_device_count(void) { return gkm_dev_count(); }
+
+extern "C" int gkm_dev_select(const int *ids, int n)
+{
+    int total = 0;
+    if (cudaGetDeviceCount(&total) != cudaSuccess) { cudaGetLastError(); total = 0; }
+    if (n < 1 || n > GKM_MAX_DEV) { gkm_set_error("bad device list"); return 1; }
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (ids[i] < 0 || ids[i] >= total ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, ids[i]) != cudaSuccess || major != 10) {
+            gkm_set_error("device %d is not a visible sm_100 GPU", ids[i]);
+            return 1;
+        }
+    }
+    for (int i = 0; i < n; i++) g_sel[i] = ids[i];
+    g_nsel = n;
+    return 0;
+}
+
+extern "C" int gkmb200_set_devices(const int *ids, int n) { return gkm_dev_select(ids, n); }
+
+static int ensure_selected(void)
+{
+    if (g_nsel > 0) return 0;
+    const char *env = getenv("GKM_DEVICES");
+    if (env && *env) {
+        int ids[GKM_MAX_DEV], n = 0;
+        const char *s = env;
+        while (*s && n < GKM_MAX_DEV) {
+            ids[n++] = (int) strtol(s, (char **) &s, 10);
+            while (*s == ',' || *s == ' ') s++;
+        }
+        return gkm_dev_select(ids, n);
+    }
+    int total = 0, n = 0, ids[GKM_MAX_DEV];
+    if (cudaGetDeviceCount(&total) != cudaSuccess) { cudaGetLastError(); total = 0; }
+    for (int i = 0; i < total && n < GKM_MAX_DEV; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ids[n++] = i;
+    }
+    if (n == 0) {
+        gkm_set_error("no sm_100 (B200) GPU is visible: gkmkern_pylib.so has no CPU fallback");
+        return 1;
+    }
+    return gkm_dev_select(ids, n);
+}
+
+static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes)
+{
+    CK(cudaSetDevice(id));
+    if (!g->ready) {
+        g->id = id;
+        CK(cudaStreamCreateWithFlags(&g->sc, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g->sx, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreate(&g->k0[i]));
+            CK(cudaEventCreate(&g->k1[i]));
+            CK(cudaEventCreateWithFlags(&g->cdone[i], cudaEventDisableTiming));
+        }
+        g->ready = 1;
+    }
+    if (band_bytes > g->band_cap) {
+        for (int i = 0; i < 2; i++) { if (g->d_band[i]) cudaFree(g->d_band[i]); g->d_band[i] = NULL; }
+        g->band_cap = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMalloc(&g->d_band[i], band_bytes));
+        g->band_cap = band_bytes;
+    }
+    if (stage_bytes > g->stage_cap) {
+        for (int i = 0; i < 2; i++) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); g->h_stage[i] = NULL; }
+        g->stage_cap = 0;
+        for (int i = 0; i < 2; i++) CK(cudaMallocHost(&g->h_stage[i], stage_bytes));
+        g->stage_cap = stage_bytes;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* one launch of a histogram kernel over the block described by kp     */
+/* ------------------------------------------------------------------ */
+static int pick_variant(const gkmb200_problem *p)
+{
+    int v = gkm_opt_kernel();
+    if (v == GKM_KERNEL_LMER) return GKM_KERNEL_LMER;
+    return GKM_KERNEL_DIAG;
+}
+
+static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st, int *variant_out)
+{
+    const int variant = pick_variant(p);
+    const int rows = kp.row_end - kp.row_begin, cols = kp.col_end - kp.col_begin;
+    if (rows <= 0 || cols <= 0) return 0;
+    const int forced_ta = gkm_opt_tile_rows();
+    const void *fn = NULL;
+    unsigned smem = 0;
+    if (variant == GKM_KERNEL_DIAG) {
+        const int nb = (p->param.d < 4) ? 4 : (p->param.d < 8) ? 8 : 16;
+        fn = diag_fn(p->param.L, nb, p->weighted);
+        if (!fn) { gkm_set_error("no diag kernel for L=%d", p->param.L); return 1; }
+        static const int cand[][2] = { {8, 16}, {4, 16}, {4, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1} };
+        int chosen = -1;
+        for (int pass = 0; pass < 2 && chosen < 0; pass++)
+            for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); i++) {
+                if (forced_ta && cand[i][0] != forced_ta && pass == 0) continue;
+                unsigned s = gkm_diag_layout(p->Wmax, cand[i][0], cand[i][1], nb, p->weighted).total;
+                if (s <= (pass == 0 ? 72u * 1024u : 220u * 1024u)) { chosen = (int) i; smem = s; break; }
+            }
+        if (chosen < 0) { gkm_set_error("sequence too long for shared memory"); return 1; }
+        kp.TA = cand[chosen][0];
+        kp.TB = cand[chosen][1];
+    } else {
+        fn = p->weighted ? (const void *) gkm_lmer_kernel<true> : (const void *) gkm_lmer_kernel<false>;
+        static const int cand[][2] = { {8, 8}, {4, 4}, {2, 2}, {1, 1} };
+        int chosen = -1;
+        for (int pass = 0; pass < 2 && chosen < 0; pass++)
+            for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); i++) {
+                unsigned s = gkm_lmer_smem_bytes(p->Wmax, cand[i][0], cand[i][1], p->nbins, p->weighted);
+                if (s <= (pass == 0 ? 100u * 1024u : 220u * 1024u)) { chosen = (int) i; smem = s; break; }
+            }
+        if (chosen < 0) { gkm_set_error("sequence too long for shared memory"); return 1; }
+        kp.TA = cand[chosen][0];
+        kp.TB = cand[chosen][1];
+    }
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    dim3 grid((unsigned) ((cols + kp.TB - 1) / kp.TB), (unsigned) ((rows + kp.TA - 1) / kp.TA), 1);
+    if (grid.y > 65535u) { gkm_set_error("chunk has too many row tiles"); return 1; }
+    void *args[] = { &kp };
+    CK(cudaLaunchKernel(fn, grid, dim3(256, 1, 1), args, smem, st));
+    if (variant_out) *variant_out = variant;
+    return 0;
+}
+
+static void fill_kparams(const gkmb200_problem *p, const gkm_image *im, gkm_kparams *kp)
+{
+    memset(kp, 0, sizeof(*kp));
+    kp->planes = im->planes;
+    kp->lens = im->lens;
+    kp->wend = im->wend;
+    kp->sqnorm = im->sqnorm;
+    kp->W = p->Wmax;
+    kp->L = p->param.L;
+    kp->d = p->param.d;
+    kp->nbins = p->nbins;
+    kp->kernel_type = p->param.kernel_type;
+    kp->gamma = p->param.gamma;
+    for (int m = 0; m < 16; m++) kp->w[m] = (m < p->nbins) ? p->w[m] : 0.0;
+}
+
+/* ------------------------------------------------------------------ */
+/* upload: packed image to every selected GPU; sqnorm = diagonal of the kernel */
+/* ------------------------------------------------------------------ */
+extern "C" void gkm_dev_release(gkmb200_problem *p)
+{
+    if (!p || !p->dev) return;
+    gkm_devstate *ds = p->dev;
+    for (int i = 0; i < ds->ndev; i++) {
+        if (cudaSetDevice(ds->dev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaFree(ds->img[i].planes);
+        cudaFree(ds->img[i].lens);
+        cudaFree(ds->img[i].wend);
+        cudaFree(ds->img[i].sqnorm);
+        cudaFree(ds->img[i].full);
+    }
+    free(ds);
+    p->dev = NULL;
+}
+
+static int upload_locked(gkmb200_problem *p)
+{
+    if (p->dev && p->packed && p->have_sqnorm) return 0;
+    if (ensure_selected()) return 1;
+    const double t0 = now_ms();
+    gkm_dev_release(p);
+    if (gkm_pack_problem(p)) return 1;
+    gkm_devstate *ds = (gkm_devstate *) calloc(1, sizeof(gkm_devstate));
+    if (!ds) { gkm_set_error("out of memory"); return 1; }
+    p->dev = ds;
+    ds->ndev = g_nsel;
+    const size_t n = (size_t) p->n, W = (size_t) p->Wmax;
+    long long h2d = 0;
+    for (int i = 0; i < ds->ndev; i++) {
+        ds->dev[i] = g_sel[i];
+        gkm_gpu *g = &g_gpu[g_sel[i]];
+        if (gpu_prepare(g, g_sel[i], 0, 0)) return 1;
+        gkm_image *im = &ds->img[i];
+        CK(cudaMalloc(&im->planes, n * 4 * W * sizeof(uint32_t)));
+        CK(cudaMalloc(&im->lens, n * sizeof(int32_t)));
+        CK(cudaMalloc(&im->sqnorm, n * sizeof(double)));
+        CK(cudaMemcpyAsync(im->planes, p->planes, n * 4 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
+        CK(cudaMemcpyAsync(im->lens, p->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->sc));
+        h2d += (long long) (n * 4 * W * sizeof(uint32_t) + n * sizeof(int32_t));
+        if (p->weighted) {
+            CK(cudaMalloc(&im->wend, n * 64 * W));
+            CK(cudaMemcpyAsync(im->wend, p->wend, n * 64 * W, cudaMemcpyHostToDevice, g->sc));
+            h2d += (long long) (n * 64 * W);
+        }
+        /* sqnorm: Kraw(a,a) by the same kernel in diagonal mode, in blocks of 1024 rows */
+        gkm_kparams kp;
+        fill_kparams(p, im, &kp);
+        kp.mode = GKM_MODE_DIAG;
+        kp.sqnorm_out = im->sqnorm;
+        for (int r = 0; r < p->n; r += 1024) {
+            kp.row_begin = kp.col_begin = kp.row_base = kp.col_base = r;
+            kp.row_end = kp.col_end = (r + 1024 < p->n) ? r + 1024 : p->n;
+            if (launch_hist(p, kp, g->sc, NULL)) return 1;
+            p->stats.launches++;
+        }
+    }
+    for (int i = 0; i < ds->ndev; i++) {
+        gkm_gpu *g = &g_gpu[ds->dev[i]];
+        CK(cudaSetDevice(ds->dev[i]));
+        if (i == 0) CK(cudaMemcpyAsync(p->sqnorm, ds->img[0].sqnorm, n * sizeof(double), cudaMemcpyDeviceToHost, g->sc));
+        CK(cudaStreamSynchronize(g->sc));
+    }
+    p->have_sqnorm = 1;
+    p->stats.upload_ms = now_ms() - t0;
+    p->stats.h2d_bytes = h2d;
+    p->stats.devices = ds->ndev;
+    gkm_log(GKM_LOG_DEBUG, "uploaded %d sequences (%d words/plane) to %d GPU(s) in %.2f ms", p->n, p->Wmax, ds->ndev, p->stats.upload_ms);
+    return 0;
+}
+
+extern "C" int gkm_dev_upload(gkmb200_problem *p)
+{
+    pthread_mutex_lock(&g_lock);
+    p->stats.launches = 0;
+    int r = upload_locked(p);
+    pthread_mutex_unlock(&g_lock);
+    return r;
+}
+
+/* ------------------------------------------------------------------ */
+/* compute: chunks -> GPUs -> pinned staging -> caller memory           */
+/* ------------------------------------------------------------------ */
+struct gkm_job {
+    gkmb200_problem *p;
+    const gkm_chunk *chunks;
+    const int *owned;
+    int nowned;
+    int next;               /* atomic cursor into owned[] */
+    int row0, col0, ncols, lower;
+    double *out; long ld;   /* dense destination ... */
+    double **rows;          /* ... or row pointers (absolute column index) */
+    int32_t *hist;          /* dense histogram destination (tests) */
+    int copy_threads;
+    int failed;
+    char err[256];
+};
+
+struct gkm_scatter {
+    const gkm_job *job;
+    const gkm_chunk *c;
+    const double *src;
+    int t, nt;
+};
+
+static void *scatter_worker(void *arg)
+{
+    const gkm_scatter *s = (const gkm_scatter *) arg;
+    const gkm_job *job = s->job;
+    const gkm_chunk *c = s->c;
+    const int width = c->col_end - c->col_begin;
+    for (int r = c->row_begin + s->t; r < c->row_end; r += s->nt) {
+        int hi = c->col_end;
+        if (job->lower && hi > r) hi = r;
+        const int ncopy = hi - c->col_begin;
+        double *dst = job->rows ? job->rows[r] + c->col_begin
+                                : job->out + (size_t) (r - job->row0) * (size_t) job->ld + (size_t) (c->col_begin - job->col0);
+        if (ncopy > 0) memcpy(dst, s->src + (size_t) (r - c->row_begin) * (size_t) width, (size_t) ncopy * sizeof(double));
+        if (job->lower && r >= job->col0 && r < job->col0 + job->ncols) {
+            if (job->rows) job->rows[r][r] = 1.0;                 /* gkmkern_pylib.c:219-221 */
+            else job->out[(size_t) (r - job->row0) * (size_t) job->ld + (size_t) (r - job->col0)] = 1.0;
+        }
+    }
+    return NULL;
+}
+
+static void scatter_chunk(const gkm_job *job, const gkm_chunk *c, const double *src)
+{
+    int nt = job->copy_threads;
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if (nt > c->row_end - c->row_begin) nt = c->row_end - c->row_begin;
+    pthread_t th[64];
+    gkm_scatter sc[64];
+    int started[64];
+    for (int t = 0; t < nt; t++) {
+        sc[t].job = job; sc[t].c = c; sc[t].src = src; sc[t].t = t; sc[t].nt = nt;
+        started[t] = 0;
+        if (t > 0) started[t] = (pthread_create(&th[t], NULL, scatter_worker, &sc[t]) == 0);
+    }
+    scatter_worker(&sc[0]);
+    for (int t = 1; t < nt; t++) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else scatter_worker(&sc[t]); /* like the reference: run the share inline if the thread could not start */
+    }
+}
+
+struct gkm_devthread {
+    gkm_job *job;
+    int slot;          /* index into devstate */
+    double kernel_ms;
+    long long launches, d2h_bytes, entries;
+    int variant;
+};
+
+static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const gkm_chunk *c, int buf, int32_t *d_hist)
+{
+    gkm_job *job = dt->job;
+    gkm_kparams kp;
+    fill_kparams(job->p, im, &kp);
+    kp.mode = job->lower ? GKM_MODE_LOWER : GKM_MODE_RECT;
+    kp.row_begin = kp.row_base = c->row_begin;
+    kp.row_end = c->row_end;
+    kp.col_begin = kp.col_base = c->col_begin;
+    kp.col_end = c->col_end;
+    const int width = c->col_end - c->col_begin;
+    kp.out = (double *) g->d_band[buf];
+    kp.ld = width;
+    kp.hist = d_hist;
+    kp.hist_cols = width;
+    CK(cudaEventRecord(g->k0[buf], g->sc));
+    if (launch_hist(job->p, kp, g->sc, &dt->variant)) return 1;
+    CK(cudaEventRecord(g->k1[buf], g->sc));
+    CK(cudaStreamWaitEvent(g->sx, g->k1[buf], 0));
+    const size_t bytes = (size_t) (c->row_end - c->row_begin) * (size_t) width * sizeof(double);
+    if (bytes) CK(cudaMemcpyAsync(g->h_stage[buf], g->d_band[buf], bytes, cudaMemcpyDeviceToHost, g->sx));
+    CK(cudaEventRecord(g->cdone[buf], g->sx));
+    dt->launches++;
+    dt->d2h_bytes += (long long) bytes;
+    dt->entries += c->entries;
+    return 0;
+}
+
+static int dev_thread_body(gkm_devthread *dt)
+{
+    gkm_job *job = dt->job;
+    gkmb200_problem *p = job->p;
+    gkm_devstate *ds = p->dev;
+    gkm_gpu *g = &g_gpu[ds->dev[dt->slot]];
+    const gkm_image *im = &ds->img[dt->slot];
+    size_t maxbytes = 0, maxhist = 0;
+    for (int i = 0; i < job->nowned; i++) {
+        const gkm_chunk *c = &job->chunks[job->owned[i]];
+        size_t cells = (size_t) (c->row_end - c->row_begin) * (size_t) (c->col_end - c->col_begin);
+        if (cells * 8 > maxbytes) maxbytes = cells * 8;
+        if (cells * 4 * (size_t) p->nbins > maxhist) maxhist = cells * 4 * (size_t) p->nbins;
+    }
+    if (gpu_prepare(g, ds->dev[dt->slot], maxbytes, maxbytes)) return 1;
+    int32_t *d_hist = NULL, *h_hist = NULL;
+    if (job->hist) {
+        CK(cudaMalloc(&d_hist, maxhist ? maxhist : 4));
+        h_hist = (int32_t *) malloc(maxhist ? maxhist : 4);
+        if (!h_hist) { gkm_set_error("out of memory"); return 1; }
+    }
+    int cur = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+    int curbuf = 0;
+    int rc = 0;
+    if (cur < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[cur]], curbuf, d_hist);
+    while (!rc && cur < job->nowned) {
+        const gkm_chunk *c = &job->chunks[job->owned[cur]];
+        int nxt = job->nowned;
+        if (!job->hist) { /* histogram dumps run one chunk at a time (single device buffer) */
+            nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+            if (nxt < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], curbuf ^ 1, d_hist);
+            if (rc) break;
+        }
+        if (cudaEventSynchronize(g->cdone[curbuf]) != cudaSuccess) {
+            gkm_set_error("CUDA: kernel or copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = 1;
+            break;
+        }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g->k0[curbuf], g->k1[curbuf]) == cudaSuccess) dt->kernel_ms += ms;
+        if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[curbuf]);
+        if (job->hist) {
+            const int width = c->col_end - c->col_begin, nb = p->nbins;
+            const size_t cells = (size_t) (c->row_end - c->row_begin) * (size_t) width;
+            if (cudaMemcpy(h_hist, d_hist, cells * 4 * (size_t) nb, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                gkm_set_error("CUDA: histogram copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+                break;
+            }
+            for (int r = c->row_begin; r < c->row_end; r++) {
+                int hi = c->col_end;
+                if (job->lower && hi > r) hi = r;
+                for (int cc = c->col_begin; cc < hi; cc++)
+                    memcpy(job->hist + ((size_t) (r - job->row0) * (size_t) job->ncols + (size_t) (cc - job->col0)) * (size_t) nb,
+                           h_hist + ((size_t) (r - c->row_begin) * (size_t) width + (size_t) (cc - c->col_begin)) * (size_t) nb,
+                           (size_t) nb * 4);
+            }
+            nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+            if (nxt < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], curbuf ^ 1, d_hist);
+        }
+        cur = nxt;
+        curbuf ^= 1;
+    }
+    if (rc) cudaDeviceSynchronize();
+    if (d_hist) cudaFree(d_hist);
+    free(h_hist);
+    return rc;
+}
+
+static void *dev_thread(void *arg)
+{
+    gkm_devthread *dt = (gkm_devthread *) arg;
+    if (dev_thread_body(dt)) {
+        dt->job->failed = 1;
+        snprintf(dt->job->err, sizeof(dt->job->err), "%s", gkmb200_last_error());
+    }
+    return NULL;
+}
+
+static long long plan_budget(const gkmb200_problem *p, long long total_cells, int ndev)
+{
+    long long cap = (long long) gkm_opt_chunk_mb() << 20;
+    long long want = total_cells * 8 / (16LL * ndev * p->shard_world);
+    if (want < (4LL << 20)) want = 4LL << 20;
+    return want < cap ? want : cap;
+}
+
+extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower,
+                               double *out, long ld, double **rows, int32_t *hist, int copy_threads)
+{
+    if (!p) { gkm_set_error("null problem"); return 1; }
+    if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > p->n || col0 + ncols > p->n) {
+        gkm_set_error("block [%d,+%d) x [%d,+%d) outside the problem (n=%d)", row0, nrows, col0, ncols, p->n);
+        return 1;
+    }
+    pthread_mutex_lock(&g_lock);
+    const double t0 = now_ms();
+    p->stats.launches = 0;
+    int rc = upload_locked(p);
+    gkm_chunk *chunks = NULL;
+    int *owned = NULL;
+    if (!rc) {
+        gkm_devstate *ds = p->dev;
+        const long long total_cells = (long long) nrows * ncols / (lower ? 2 : 1);
+        const int tile_rows = 16;
+        const int maxc = nrows / tile_rows + 2;
+        chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
+        owned = (int *) malloc(sizeof(int) * (size_t) maxc);
+        int nchunks = (chunks && owned) ? gkm_plan_chunks(row0, nrows, col0, ncols, lower, tile_rows,
+                                                          plan_budget(p, total_cells, ds->ndev), chunks, maxc) : -1;
+        if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
+        if (!rc) {
+            gkm_job job;
+            memset(&job, 0, sizeof(job));
+            job.p = p; job.chunks = chunks; job.owned = owned;
+            for (int c = 0; c < nchunks; c++)
+                if (gkm_chunk_owner(c, nchunks, p->shard_world) == p->shard_rank) owned[job.nowned++] = c;
+            job.row0 = row0; job.col0 = col0; job.ncols = ncols; job.lower = lower;
+            job.out = out; job.ld = ld; job.rows = rows; job.hist = hist;
+            job.copy_threads = copy_threads;
+            gkm_devthread dts[GKM_MAX_DEV];
+            pthread_t th[GKM_MAX_DEV];
+            int started[GKM_MAX_DEV];
+            memset(dts, 0, sizeof(dts));
+            for (int i = 0; i < ds->ndev; i++) {
+                dts[i].job = &job; dts[i].slot = i;
+                started[i] = 0;
+                if (i > 0) started[i] = (pthread_create(&th[i], NULL, dev_thread, &dts[i]) == 0);
+            }
+            dev_thread(&dts[0]);
+            for (int i = 1; i < ds->ndev; i++) {
+                if (started[i]) pthread_join(th[i], NULL);
+                else dev_thread(&dts[i]);
+            }
+            p->stats.kernel_ms = 0; p->stats.d2h_bytes = 0; p->stats.entries = 0;
+            for (int i = 0; i < ds->ndev; i++) {
+                if (dts[i].kernel_ms > p->stats.kernel_ms) p->stats.kernel_ms = dts[i].kernel_ms;
+                p->stats.launches += dts[i].launches;
+                p->stats.d2h_bytes += dts[i].d2h_bytes;
+                p->stats.entries += dts[i].entries;
+                if (dts[i].variant) p->stats.kernel_variant = dts[i].variant;
+            }
+            p->stats.devices = ds->ndev;
+            if (job.failed) { gkm_set_error("%s", job.err); rc = 1; }
+        }
+    }
+    free(chunks);
+    free(owned);
+    p->stats.wall_ms = now_ms() - t0;
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* fused decision values                              */
+/* ------------------------------------------------------------------ */
+extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
+                                const double *alpha, double bias, double *out)
+{
+    if (!p || !alpha || !out) { gkm_set_error("null argument"); return 1; }
+    if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > p->n || col0 + ncols > p->n) {
+        gkm_set_error("block outside the problem");
+        return 1;
+    }
+    pthread_mutex_lock(&g_lock);
+    int rc = upload_locked(p);
+    double *d_alpha = NULL, *d_dec = NULL;
+    if (!rc) {
+        gkm_devstate *ds = p->dev;
+        gkm_gpu *g = &g_gpu[ds->dev[0]];
+        rc = (cudaSetDevice(ds->dev[0]) != cudaSuccess);
+        if (!rc) rc = (cudaMalloc(&d_alpha, sizeof(double) * (size_t) (ncols ? ncols : 1)) != cudaSuccess);
+        if (!rc) rc = (cudaMalloc(&d_dec, sizeof(double) * (size_t) (nrows ? nrows : 1)) != cudaSuccess);
+        if (!rc) rc = (cudaMemcpyAsync(d_alpha, alpha, sizeof(double) * (size_t) ncols, cudaMemcpyHostToDevice, g->sc) != cudaSuccess);
+        if (!rc) rc = (cudaMemsetAsync(d_dec, 0, sizeof(double) * (size_t) nrows, g->sc) != cudaSuccess);
+        if (rc) gkm_set_error("CUDA: decision-value buffers: %s", cudaGetErrorString(cudaGetLastError()));
+        gkm_kparams kp;
+        fill_kparams(p, &ds->img[0], &kp);
+        kp.mode = GKM_MODE_RECT;
+        kp.alpha = d_alpha; kp.decision = d_dec;
+        kp.col_begin = kp.col_base = col0; kp.col_end = col0 + ncols;
+        kp.row_base = row0;
+        for (int r = row0; !rc && r < row0 + nrows; r += 8192) {
+            kp.row_begin = r;
+            kp.row_end = (r + 8192 < row0 + nrows) ? r + 8192 : row0 + nrows;
+            rc = launch_hist(p, kp, g->sc, NULL);
+        }
+        if (!rc) {
+            rc = (cudaMemcpyAsync(out, d_dec, sizeof(double) * (size_t) nrows, cudaMemcpyDeviceToHost, g->sc) != cudaSuccess) ||
+                 (cudaStreamSynchronize(g->sc) != cudaSuccess);
+            if (rc) gkm_set_error("CUDA: decision values failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (!rc) for (int i = 0; i < nrows; i++) out[i] += bias;
+    }
+    cudaFree(d_alpha);
+    cudaFree(d_dec);
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
+/* measurement                                                          */
+/* ------------------------------------------------------------------ */
+extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each)
+{
+    if (!p || steps < 1 || !ms_each) { gkm_set_error("bad bench arguments"); return 1; }
+    pthread_mutex_lock(&g_lock);
+    int rc = upload_locked(p);
+    gkm_chunk *chunks = NULL;
+    if (!rc) {
+        gkm_devstate *ds = p->dev;
+        gkm_gpu *g = &g_gpu[ds->dev[0]];
+        gkm_image *im = &ds->img[0];
+        const int n = p->n;
+        do {
+            if (cudaSetDevice(ds->dev[0]) != cudaSuccess) { rc = 1; break; }
+            if (!im->full) {
+                im->full_ld = ((size_t) n + 15) & ~(size_t) 15;
+                if (cudaMalloc(&im->full, im->full_ld * (size_t) n * sizeof(double)) != cudaSuccess) { rc = 1; break; }
+            }
+            if (flush_l2 && !g->d_flush && cudaMalloc(&g->d_flush, GKM_FLUSH_BYTES) != cudaSuccess) { rc = 1; break; }
+        } while (0);
+        if (rc) gkm_set_error("CUDA: bench buffers: %s", cudaGetErrorString(cudaGetLastError()));
+        const int maxc = n / 16 + 2;
+        int nchunks = -1;
+        if (!rc) {
+            chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
+            nchunks = chunks ? gkm_plan_chunks(0, n, 0, n, 1, 16, plan_budget(p, (long long) n * n / 2, 1), chunks, maxc) : -1;
+            if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
+        }
+        cudaEvent_t e0 = NULL, e1 = NULL;
+        if (!rc) rc = (cudaEventCreate(&e0) != cudaSuccess) || (cudaEventCreate(&e1) != cudaSuccess);
+        long long launches = 0, entries = 0;
+        int variant = 0;
+        for (int it = 0; !rc && it < warmup + steps; it++) {
+            if (flush_l2) cudaMemsetAsync(g->d_flush, it & 0xff, GKM_FLUSH_BYTES, g->sc);
+            cudaEventRecord(e0, g->sc);
+            launches = 0; entries = 0;
+            for (int c = 0; !rc && c < nchunks; c++) {
+                if (gkm_chunk_owner(c, nchunks, p->shard_world) != p->shard_rank) continue;
+                gkm_kparams kp;
+                fill_kparams(p, im, &kp);
+                kp.mode = GKM_MODE_LOWER;
+                kp.row_begin = chunks[c].row_begin; kp.row_end = chunks[c].row_end;
+                kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
+                kp.row_base = 0; kp.col_base = 0;
+                kp.out = im->full; kp.ld = (long long) im->full_ld;
+                rc = launch_hist(p, kp, g->sc, &variant);
+                launches++;
+                entries += chunks[c].entries;
+            }
+            cudaEventRecord(e1, g->sc);
+            if (!rc && cudaEventSynchronize(e1) != cudaSuccess) {
+                gkm_set_error("CUDA: bench pass failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+            }
+            float ms = 0.f;
+            if (!rc) cudaEventElapsedTime(&ms, e0, e1);
+            if (it >= warmup) ms_each[it - warmup] = ms;
+        }
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        p->stats.launches = launches;
+        p->stats.entries = entries;
+        p->stats.kernel_variant = variant;
+        p->stats.devices = 1;
+        p->stats.d2h_bytes = 0;
+    }
+    free(chunks);
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+/* ---- issue-rate micro-benchmarks: the denominators of the integer roofline ---- */
+template <int OP>
+__global__ void __launch_bounds__(256) gkm_mb_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = seed * (uint32_t) (threadIdx.x + 1) + (uint32_t) i * 0x9E3779B9u;
+    uint32_t y = seed ^ 0x5bd1e995u, z = seed + (uint32_t) blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (OP == 0) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y), "r"(z));
+                if (OP == 1) asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(x[i]) : "r"(y));
+                if (OP == 2) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
+                if (OP == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y));
+                if (OP == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z));
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x[i];
+    if (s == 0x12345u) out[0] = s;
+}
+
+extern "C" int gkm_dev_microbench(const char *what, double *result)
+{
+    if (!what || !result) { gkm_set_error("null argument"); return 1; }
+    pthread_mutex_lock(&g_lock);
+    int rc = ensure_selected();
+    if (!rc) {
+        do {
+            gkm_gpu *g = &g_gpu[g_sel[0]];
+            if (gpu_prepare(g, g_sel[0], 0, 0)) { rc = 1; break; }
+            uint32_t *d = NULL;
+            if (cudaMalloc(&d, 64) != cudaSuccess) { rc = 1; break; }
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_sel[0]);
+            const int iters = 4096, blocks = sms * 8;
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            float best = 1e30f;
+            for (int rep = 0; rep < 4; rep++) {
+                cudaEventRecord(e0, g->sc);
+                if (!strcmp(what, "lop3")) gkm_mb_kernel<0><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "shf")) gkm_mb_kernel<1><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "popc")) gkm_mb_kernel<2><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "iadd3")) gkm_mb_kernel<3><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "imad")) gkm_mb_kernel<4><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else { gkm_set_error("unknown microbench %s", what); rc = 1; break; }
+                cudaEventRecord(e1, g->sc);
+                if (cudaEventSynchronize(e1) != cudaSuccess) { gkm_set_error("CUDA: microbench failed"); rc = 1; break; }
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (rep > 0 && ms < best) best = ms;
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            cudaFree(d);
+            if (!rc) *result = (double) blocks * 256.0 * (double) iters * 32.0 / ((double) best * 1e-3) / 1e9;
+        } while (0);
+    }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}

@@ -1,0 +1,93 @@
+/* gkm_internal.h -- host-side internals of gkmkern_pylib.so (C, shared with the .cu files) */
+#ifndef GKM_INTERNAL_H_INCLUDED
+#define GKM_INTERNAL_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/gkm_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKM_MAX_L 16       /* one L-mer fits a 32-bit word (2 bits per base) */
+#define GKM_MAX_BINS 16    /* d <= 15 */
+#define GKM_MAX_BASES 2047 /* MAX_SEQ_LENGTH - 1, libgkm.c:1294-1299 */
+
+/* ---- logging (gkm_log.c): same look as the reference's clog format "%l %d %t: %m\n" ---- */
+enum { GKM_LOG_TRACE = 0, GKM_LOG_DEBUG, GKM_LOG_INFO, GKM_LOG_WARN, GKM_LOG_ERROR };
+void gkm_log_set_level(int level);
+int gkm_log_get_level(void);
+void gkm_log(int level, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void gkm_set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+
+/* ---- parameters and weights (gkm_weights.c) ---- */
+const char *gkm_param_problem(const gkm_parameter *p, int max_L);
+int gkm_calc_weights(int kernel_type, int L, int k, double *w /* L+1 slots */);
+void gkm_calc_posweights(int nk, int kernel_type, int M, double H, uint8_t *wt, uint8_t *wt_rc);
+
+/* ---- the problem: sequences, their packed form, and (opaque) device state ---- */
+struct gkm_devstate; /* gkm_device.cu */
+
+struct gkmb200_problem {
+    gkm_parameter param;
+    double w[GKM_MAX_L + 1];
+    int nbins;     /* d + 1 */
+    int weighted;  /* kernel types 4, 5 */
+    int n, cap;
+    int npos;      /* set by read_problem */
+    int *len;      /* bases per sequence */
+    uint8_t **code;/* forward strand, base codes 0..3 (A,C,G,T) */
+    int nonacgt;   /* characters mapped to 'A' so far */
+
+    /* packed image (gkm_pack_problem) */
+    int packed;
+    int Wmax;        /* 32-bit words per bit plane = ceil(maxlen / 32) */
+    uint32_t *planes;/* [n][4][Wmax]: fwd bit0, fwd bit1, rc bit0, rc bit1 */
+    uint8_t *wend;   /* weighted only: [n][2][32*Wmax] weight by window END position */
+    double *sqnorm;  /* [n], filled by the device */
+    int have_sqnorm;
+
+    int shard_rank, shard_world;
+    struct gkm_devstate *dev;
+    gkmb200_stats stats;
+};
+
+int gkm_problem_reserve(gkmb200_problem *p, int extra);
+int gkm_pack_problem(gkmb200_problem *p);
+void gkm_unpack_problem(gkmb200_problem *p);
+
+/* ---- chunk planning (gkm_sched.c), pure host logic ---- */
+typedef struct gkm_chunk {
+    int row_begin, row_end; /* query rows [row_begin, row_end) */
+    int col_begin, col_end; /* target columns computed for these rows */
+    long long entries;      /* kernel entries this chunk produces */
+} gkm_chunk;
+
+/* split rows [row0,row0+nrows) x cols [col0,col0+ncols) into chunks of whole row tiles.
+ * lower != 0: only columns j < row are needed (triangular matrix path).
+ * Returns the number of chunks written (<= max_chunks) or -1. */
+int gkm_plan_chunks(int row0, int nrows, int col0, int ncols, int lower, int tile_rows,
+                    long long max_chunk_bytes, gkm_chunk *out, int max_chunks);
+/* which chunks belong to shard `rank` of `world` (round-robin by descending cost) */
+int gkm_chunk_owner(int chunk_index, int nchunks, int world);
+
+/* ---- device layer (gkm_device.cu) ---- */
+int gkm_dev_count(void);
+int gkm_dev_select(const int *ids, int n);
+int gkm_dev_upload(gkmb200_problem *p);            /* planes -> every selected GPU, sqnorm on GPU */
+void gkm_dev_release(gkmb200_problem *p);
+/* host destinations: either dense `out` (ld doubles per row) or row pointers `rows` (rows[r][c]) */
+int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower,
+                    double *out, long ld, double **rows, int32_t *hist, int copy_threads);
+int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
+                     const double *alpha, double bias, double *out);
+int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each);
+int gkm_dev_microbench(const char *what, double *result);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,74 @@
+/* gkm_options.c -- process-wide knobs.  The reference's whole configuration surface is
+ * the gkmOpt struct (libgkm.h:149-161), which cannot grow without breaking the ABI, so
+ * everything GPU-specific comes from gkmb200_set_option() or the environment:
+ *   GKM_KERNEL   = auto | lmer | diag      kernel variant
+ *   GKM_MAX_L    = 12 | 16                 ceiling of the parameter gate in gkm_main_pywrapper
+ *   GKM_CHUNK_MB = n                       upper bound of one chunk's dense output
+ *   GKM_DEVICES  = "0,1,.."                GPUs to use (gkm_device.cu)
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "gkm_internal.h"
+#include "gkm_options.h"
+
+static int g_loaded = 0;
+static int g_kernel = GKM_KERNEL_AUTO;
+static int g_max_L = 12;
+static int g_chunk_mb = 64;
+static int g_tile_rows = 0;
+
+static int parse_kernel(const char *v, int *out)
+{
+    if (!strcmp(v, "auto")) *out = GKM_KERNEL_AUTO;
+    else if (!strcmp(v, "lmer")) *out = GKM_KERNEL_LMER;
+    else if (!strcmp(v, "diag")) *out = GKM_KERNEL_DIAG;
+    else return 1;
+    return 0;
+}
+
+static void load_env(void)
+{
+    if (g_loaded) return;
+    g_loaded = 1;
+    const char *v;
+    if ((v = getenv("GKM_KERNEL")) != NULL) parse_kernel(v, &g_kernel);
+    if ((v = getenv("GKM_MAX_L")) != NULL) { int x = atoi(v); if (x == 12 || x == 16) g_max_L = x; }
+    if ((v = getenv("GKM_CHUNK_MB")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 4096) g_chunk_mb = x; }
+    if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
+}
+
+int gkm_opt_kernel(void) { load_env(); return g_kernel; }
+int gkm_opt_max_L(void) { load_env(); return g_max_L; }
+int gkm_opt_chunk_mb(void) { load_env(); return g_chunk_mb; }
+int gkm_opt_tile_rows(void) { load_env(); return g_tile_rows; }
+
+int gkmb200_set_option(const char *key, const char *value)
+{
+    load_env();
+    if (!key || !value) { gkm_set_error("null option"); return 1; }
+    if (!strcmp(key, "kernel")) {
+        if (parse_kernel(value, &g_kernel)) { gkm_set_error("kernel must be auto, lmer or diag"); return 1; }
+        return 0;
+    }
+    int x = atoi(value);
+    if (!strcmp(key, "max_L")) {
+        if (x != 12 && x != 16) { gkm_set_error("max_L must be 12 or 16"); return 1; }
+        g_max_L = x;
+        return 0;
+    }
+    if (!strcmp(key, "chunk_mb")) {
+        if (x < 1 || x > 4096) { gkm_set_error("chunk_mb out of range"); return 1; }
+        g_chunk_mb = x;
+        return 0;
+    }
+    if (!strcmp(key, "tile_rows")) {
+        if (x < 0 || x > 16) { gkm_set_error("tile_rows out of range"); return 1; }
+        g_tile_rows = x;
+        return 0;
+    }
+    gkm_set_error("unknown option %s", key);
+    return 1;
+}
+
+int gkmb200_abi_version(void) { return 1; }

@@ -1,0 +1,14 @@
+#ifndef GKM_OPTIONS_H_INCLUDED
+#define GKM_OPTIONS_H_INCLUDED
+#ifdef __cplusplus
+extern "C" {
+#endif
+enum { GKM_KERNEL_AUTO = 0, GKM_KERNEL_LMER = 1, GKM_KERNEL_DIAG = 2, GKM_KERNEL_MMA = 3 };
+int gkm_opt_kernel(void);
+int gkm_opt_max_L(void);
+int gkm_opt_chunk_mb(void);
+int gkm_opt_tile_rows(void);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,257 @@
+/* gkm_seq.c -- sequences of a problem: FASTA input, base coding, 2-bit plane packing.
+ *
+ * Host-side counterpart of gkmkernel_new_object (libgkm.c:841-938) and
+ * read_fasta_file (libgkm.c:1251-1314).  What the reference keeps per sequence as
+ * byte arrays (seq, seq_rc, wt, wt_rc) is packed here into the image the kernels
+ * read: two bit planes per strand (bit p of plane b = bit b of the base code at
+ * position p, A,C,G,T = 0,1,2,3) and, for the weighted kernel types, the positional
+ * weights re-indexed by window END position.  sqnorm is NOT computed here -- it is
+ * the diagonal of the kernel and comes from the GPU (gkm_device.cu).
+ */
+#include <ctype.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gkm_internal.h"
+
+gkmb200_problem *gkmb200_problem_new(const gkm_parameter *param)
+{
+    if (!param) { gkm_set_error("null parameter"); return NULL; }
+    const char *bad = gkm_param_problem(param, GKM_MAX_L);
+    if (bad) { gkm_set_error("%s", bad); return NULL; }
+    gkmb200_problem *p = (gkmb200_problem *) calloc(1, sizeof(*p));
+    if (!p) { gkm_set_error("out of memory"); return NULL; }
+    p->param = *param;
+    p->nbins = param->d + 1;
+    p->weighted = (param->kernel_type == EST_TRUNC_PW || param->kernel_type == EST_TRUNC_PW_RBF);
+    p->shard_rank = 0;
+    p->shard_world = 1;
+    { /* one process per GPU (torchrun-style launches): GKM_SHARD="rank/world" shards the chunk list */
+        const char *sh = getenv("GKM_SHARD");
+        int r = 0, w = 1;
+        if (sh && sscanf(sh, "%d/%d", &r, &w) == 2 && w >= 1 && r >= 0 && r < w) { p->shard_rank = r; p->shard_world = w; }
+    }
+    if (gkm_calc_weights(param->kernel_type, param->L, param->k, p->w)) {
+        gkm_set_error("cannot compute weights for L=%d k=%d", param->L, param->k);
+        free(p);
+        return NULL;
+    }
+    return p;
+}
+
+void gkmb200_problem_free(gkmb200_problem *p)
+{
+    if (!p) return;
+    gkm_dev_release(p);
+    gkm_unpack_problem(p);
+    for (int i = 0; i < p->n; i++) free(p->code[i]);
+    free(p->code);
+    free(p->len);
+    free(p);
+}
+
+int gkm_problem_reserve(gkmb200_problem *p, int extra)
+{
+    if (p->n + extra <= p->cap) return 0;
+    int cap = p->cap ? p->cap : 256;
+    while (cap < p->n + extra) cap *= 2;
+    int *len = (int *) realloc(p->len, sizeof(int) * (size_t) cap);
+    if (!len) return 1;
+    p->len = len;
+    uint8_t **code = (uint8_t **) realloc(p->code, sizeof(uint8_t *) * (size_t) cap);
+    if (!code) return 1;
+    p->code = code;
+    p->cap = cap;
+    return 0;
+}
+
+/* A,C,G,T (either case) -> 0..3; anything else counts as 'A' (libgkm.c:864-875) */
+static inline int base_code(int ch, int *bad)
+{
+    switch (ch) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: *bad = 1; return 0;
+    }
+}
+
+int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
+{
+    if (!p || !seq) { gkm_set_error("null argument"); return -1; }
+    if (len < 0) len = (int) strlen(seq);
+    if (len > GKM_MAX_BASES) len = GKM_MAX_BASES;
+    if (len < p->param.L) {
+        gkm_set_error("sequence %d has %d bases, fewer than L=%d", p->n, len, p->param.L);
+        return -1;
+    }
+    if (gkm_problem_reserve(p, 1)) { gkm_set_error("out of memory"); return -1; }
+    uint8_t *c = (uint8_t *) malloc((size_t) len);
+    if (!c) { gkm_set_error("out of memory"); return -1; }
+    for (int i = 0; i < len; i++) {
+        int bad = 0;
+        c[i] = (uint8_t) base_code((unsigned char) seq[i], &bad);
+        if (bad) {
+            if (p->nonacgt < 10)
+                gkm_log(GKM_LOG_WARN, "'%c' at sequence %d(%d) is not a valid nucleotide. Only ACGT are allowed", seq[i], p->n, i);
+            p->nonacgt++;
+        }
+    }
+    p->len[p->n] = len;
+    p->code[p->n] = c;
+    gkm_unpack_problem(p); /* packed image is stale now */
+    return p->n++;
+}
+
+/* one FASTA file; the line discipline of libgkm.c:1207-1225,1268-1304:
+ * a line ends at the first CR or LF, '>' in column 0 opens a record, all other
+ * lines extend the current record up to 2047 bases, text before the first
+ * record is ignored. */
+int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
+{
+    if (!p || !path) { gkm_set_error("null argument"); return -1; }
+    FILE *fp = fopen(path, "r");
+    if (!fp) { gkm_set_error("can't open file %s", path); return -1; }
+    char *line = NULL;
+    size_t cap = 0;
+    char *seq = (char *) malloc(GKM_MAX_BASES + 1);
+    int seqlen = 0, open_rec = 0, added = 0, warned = 0, fail = 0;
+    ssize_t got;
+    while (!fail && (got = getline(&line, &cap, fp)) >= 0) {
+        line[strcspn(line, "\r\n")] = '\0';
+        if (line[0] == '>') {
+            if (open_rec) {
+                if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
+            }
+            if ((added % 1000) == 0) gkm_log(GKM_LOG_INFO, "reading... %d", added);
+            open_rec = 1; seqlen = 0; warned = 0;
+        } else if (open_rec && seqlen < GKM_MAX_BASES) {
+            size_t ll = strlen(line);
+            if ((size_t) seqlen + ll > GKM_MAX_BASES) {
+                if (!warned)
+                    gkm_log(GKM_LOG_WARN, "maximum sequence length allowed is %d. The first %d nucleotides of record %d will only be used",
+                            GKM_MAX_BASES, GKM_MAX_BASES, added);
+                warned = 1;
+                ll = (size_t) (GKM_MAX_BASES - seqlen);
+            }
+            memcpy(seq + seqlen, line, ll);
+            seqlen += (int) ll;
+        }
+    }
+    if (!fail && open_rec) {
+        if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
+    }
+    gkm_log(GKM_LOG_INFO, "reading... done");
+    free(line);
+    free(seq);
+    fclose(fp);
+    return fail ? -1 : added;
+}
+
+/* positives get ids 0..n_pos-1, negatives follow (libgkm.c:1316-1333) */
+int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *negfile)
+{
+    gkm_log(GKM_LOG_INFO, "reading sequences from %s", posfile);
+    int np = gkmb200_problem_read_fasta(p, posfile);
+    if (np < 0) return -1;
+    gkm_log(GKM_LOG_INFO, "reading sequences from %s", negfile);
+    int nn = gkmb200_problem_read_fasta(p, negfile);
+    if (nn < 0) return -1;
+    p->npos = np;
+    return np;
+}
+
+int gkmb200_problem_size(const gkmb200_problem *p) { return p ? p->n : -1; }
+
+int gkmb200_problem_seqlen(const gkmb200_problem *p, int i)
+{
+    if (!p || i < 0 || i >= p->n) return -1;
+    return p->len[i];
+}
+
+/* the byte arrays the reference would hold in gkm_data.seq / seq_rc (codes 1..4) */
+int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t *rc)
+{
+    if (!p || i < 0 || i >= p->n) return 1;
+    const int n = p->len[i];
+    for (int j = 0; j < n; j++) {
+        if (fwd) fwd[j] = (uint8_t) (p->code[i][j] + 1);
+        if (rc) rc[j] = (uint8_t) (4 - p->code[i][n - 1 - j]);
+    }
+    return 0;
+}
+
+int gkmb200_problem_get_weights(const gkmb200_problem *p, double *w)
+{
+    if (!p || !w) return 1;
+    for (int m = 0; m < p->nbins; m++) w[m] = p->w[m];
+    return 0;
+}
+
+int gkmb200_problem_set_shard(gkmb200_problem *p, int rank, int world)
+{
+    if (!p || world < 1 || rank < 0 || rank >= world) { gkm_set_error("bad shard %d/%d", rank, world); return 1; }
+    p->shard_rank = rank;
+    p->shard_world = world;
+    return 0;
+}
+
+void gkm_unpack_problem(gkmb200_problem *p)
+{
+    if (!p->packed) return;
+    free(p->planes); p->planes = NULL;
+    free(p->wend); p->wend = NULL;
+    free(p->sqnorm); p->sqnorm = NULL;
+    p->packed = 0;
+    p->have_sqnorm = 0;
+}
+
+/* build the device image on the host */
+int gkm_pack_problem(gkmb200_problem *p)
+{
+    if (p->packed) return 0;
+    if (p->n == 0) { gkm_set_error("problem has no sequences"); return 1; }
+    const int L = p->param.L;
+    int maxlen = 0;
+    for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
+    const int W = (maxlen + 31) / 32;
+    p->Wmax = W;
+    p->planes = (uint32_t *) calloc((size_t) p->n * 4 * (size_t) W, sizeof(uint32_t));
+    p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
+    if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 2 * 32 * (size_t) W, 1);
+    if (!p->planes || !p->sqnorm || (p->weighted && !p->wend)) {
+        gkm_unpack_problem(p);
+        gkm_set_error("out of memory packing %d sequences", p->n);
+        return 1;
+    }
+    uint8_t wt[GKM_MAX_BASES + 1], wt_rc[GKM_MAX_BASES + 1];
+    for (int i = 0; i < p->n; i++) {
+        const int n = p->len[i];
+        const uint8_t *c = p->code[i];
+        uint32_t *pl = p->planes + (size_t) i * 4 * (size_t) W;
+        for (int pos = 0; pos < n; pos++) {
+            const uint32_t f = c[pos];
+            const uint32_t r = 3u - c[n - 1 - pos]; /* complement of the mirrored base */
+            const uint32_t bit = 1u << (pos & 31);
+            const int wi = pos >> 5;
+            if (f & 1u) pl[0 * W + wi] |= bit;
+            if (f & 2u) pl[1 * W + wi] |= bit;
+            if (r & 1u) pl[2 * W + wi] |= bit;
+            if (r & 2u) pl[3 * W + wi] |= bit;
+        }
+        if (p->weighted) {
+            const int nk = n - L + 1;
+            gkm_calc_posweights(nk, p->param.kernel_type, p->param.M, p->param.H, wt, wt_rc);
+            uint8_t *we = p->wend + (size_t) i * 2 * 32 * (size_t) W;
+            for (int s = 0; s < nk; s++) {
+                we[s + L - 1] = wt[s];
+                we[32 * W + s + L - 1] = wt_rc[s];
+            }
+        }
+    }
+    p->packed = 1;
+    p->have_sqnorm = 0;
+    return 0;
+}

@@ -1,0 +1,93 @@
+/* gkm_b200.h -- extended C-ABI of gkmkern_pylib.so (B200 / sm_100a gkm kernel engine).
+ *
+ * gkm_abi.h holds the entry points the reference exports (src/libgkm.h); this
+ * header adds what a GPU engine needs that the reference's ABI cannot express:
+ * in-memory sequences, the rectangular test x SV shape without
+ * abusing one row per call (libgkm.c:1156), raw integer histograms for parity
+ * checks (the reference keeps them private, libgkm.c:568-588), fused decision
+ * values (8f/f1, what gkmsvm.py:109,118 does with the slice), tile sharding over
+ * processes, device timing.  Plain pointers and sizes only.
+ *
+ * Every function returns 0 on success unless stated otherwise; on failure
+ * gkmb200_last_error() describes why.  Compute entry points FAIL when no
+ * sm_100 device is visible: there is no CPU fallback.
+ */
+#ifndef GKM_B200_H_INCLUDED
+#define GKM_B200_H_INCLUDED
+
+#include "gkm_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gkmb200_problem gkmb200_problem;
+
+typedef struct gkmb200_stats {
+    double kernel_ms;        /* device time of the histogram kernels of the last compute call (CUDA events) */
+    double wall_ms;          /* host wall time of the last compute call */
+    double upload_ms;        /* pack + H2D + sqnorm of the last upload */
+    long long launches;      /* kernel launches of the last compute call */
+    long long entries;       /* kernel entries produced by the last compute call */
+    long long lmer_pairs;    /* L-mer pair comparisons those entries stand for */
+    long long h2d_bytes;     /* bytes copied host->device by the last upload */
+    long long d2h_bytes;     /* bytes copied device->host by the last compute call */
+    int devices;             /* GPUs used */
+    int kernel_variant;      /* 1 = lmer (XOR/LOP3/POPC per pair), 2 = diag (bit-sliced diagonals), 3 = mma (tcgen05) */
+    int reserved[6];
+} gkmb200_stats;
+
+/* ---- process-wide ---- */
+const char *gkmb200_last_error(void);
+int gkmb200_abi_version(void);
+int gkmb200_device_count(void);                      /* visible CUDA devices of compute capability 10.x; 0 if none */
+int gkmb200_set_devices(const int *ids, int n);      /* default: env GKM_DEVICES ("0,1,.."), else all */
+int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag ; "max_L" = 12|16 ; "tile_rows", "chunk_mb" */
+void gkmb200_set_verbosity(int level);               /* 0..4 like gkmOpt.verbosity */
+
+/* ---- host-only arithmetic of the path (no GPU needed) ---- */
+const char *gkmb200_check_parameter(const gkm_parameter *param); /* NULL if ok; the gate of gkmkern_pylib.c:38-64 */
+int gkmb200_weights(int kernel_type, int L, int k, double *w);   /* w[0..L]; libgkm.c:107-217 */
+int gkmb200_posweights(int nk, int kernel_type, int M, double H, uint8_t *wt, uint8_t *wt_rc); /* libgkm.c:910-932 */
+
+/* ---- problem = parameter set + sequences (ids in insertion order) ---- */
+gkmb200_problem *gkmb200_problem_new(const gkm_parameter *param);
+void gkmb200_problem_free(gkmb200_problem *p);
+int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len);       /* len < 0: strlen. returns the id or -1 */
+int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path);        /* records appended, or -1 (libgkm.c:1251) */
+int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *negfile); /* n_pos, or -1 (libgkm.c:1316) */
+int gkmb200_problem_size(const gkmb200_problem *p);
+int gkmb200_problem_seqlen(const gkmb200_problem *p, int i);
+int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t *rc);   /* 1..4 like gkm_data.seq */
+int gkmb200_problem_get_weights(const gkmb200_problem *p, double *w);        /* d+1 values */
+int gkmb200_problem_set_shard(gkmb200_problem *p, int rank, int world);      /* this process computes chunk c iff owner(c) == rank */
+
+/* pack to 2-bit planes, copy to every selected GPU, compute sqnorm there (libgkm.c:723-759) */
+int gkmb200_problem_upload(gkmb200_problem *p);
+int gkmb200_problem_sqnorm(gkmb200_problem *p, double *out);                 /* n values */
+
+/* ---- the kernel ---- */
+/* triangular matrix into caller rows: rows[a][j] = K(a,j) for j<a, rows[a][a] = 1 (gkmkern_pylib.c:169-221) */
+int gkmb200_kernel_lower(gkmb200_problem *p, double **rows, int copy_threads);
+/* dense block: out[(r-row0)*ld + (c-col0)] = K(r,c).  lower != 0: only c < r is written (and r == c gets 1.0).
+ * With the SVs at ids [0,nSV) this is gkmkernel_kernelfunc_batch_all(a, 0, nSV) for a whole batch of rows. */
+int gkmb200_kernel_block(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower, double *out, long ld);
+/* raw truncated mismatch histograms: hist[((r-row0)*ncols + (c-col0))*(d+1) + m] = H_m(r,c), 32-bit */
+int gkmb200_hist_block(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower, int32_t *hist);
+/* out[r-row0] = bias + sum_c alpha[c-col0] * K(r,c), reduced on the device */
+int gkmb200_decision_values(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
+                            const double *alpha, double bias, double *out);
+
+/* ---- measurement ---- */
+int gkmb200_get_stats(const gkmb200_problem *p, gkmb200_stats *out);
+/* `steps` timed passes over the full lower triangle with inputs and outputs resident in HBM;
+ * ms_each[steps] = CUDA-event time of each pass; flush_l2 != 0 rewrites a >L2-sized buffer between passes */
+int gkmb200_bench_lower_resident(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each);
+/* issue-rate micro-benchmarks: what = "lop3" | "shf" | "popc" | "iadd3" | "imad"; result = 1e9 lane-ops per second */
+int gkmb200_microbench(const char *what, double *result);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GKM_B200_H_INCLUDED */

@@ -1,0 +1,286 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI of gkmkern_pylib.so, against
+(1) golden vectors from the unmodified reference, (2) the oracle on seeded inputs, and
+(3) size-independent properties at BASELINE.json sizes.
+
+Bars: integer mismatch histograms bit-exact; kernel values bit-identical for the non-RBF
+kernel types and within 1e-9 relative (north_star) for the RBF types (device exp())."""
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle
+from conftest import golden_names, load_golden, random_seqs, write_fasta
+from gkmqc_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+RTOL_RBF = 1e-9
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    capi.load()
+    if capi.device_count() < 1:
+        pytest.fail("no B200 visible; the product has no CPU fallback")
+
+
+@pytest.fixture(params=["diag", "lmer"])
+def variant(request):
+    capi.set_option("kernel", request.param)
+    yield request.param
+    capi.set_option("kernel", "auto")
+
+
+def check_kmat(K, Kref, kernel_type):
+    if kernel_type in (3, 5):
+        np.testing.assert_allclose(K, Kref, rtol=RTOL_RBF, atol=0)
+    else:
+        assert np.array_equal(K, Kref), "max abs diff %g" % np.max(np.abs(K - Kref))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_histograms_and_kernel(name, variant):
+    g, cfg, pos, neg = load_golden(name)
+    with capi.Problem(**cfg) as P:
+        assert P.read(pos, neg) == int(g["npos"])
+        n = P.n
+        assert np.array_equal(P.weights(), g["weights"])
+        assert np.array_equal(P.sqnorm(), g["sqnorm"]), "sqnorm (device diagonal)"
+        H = P.hist_block(0, n, 0, n, lower=True)
+        assert np.array_equal(H, g["hist"]), "integer mismatch histograms"
+        K = P.kernel_lower()
+        check_kmat(K, g["kmat"], cfg["kernel_type"])
+        st = P.stats()
+        assert st["launches"] > 0 and st["kernel_variant"] == {"lmer": 1, "diag": 2}[variant]
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if int(n.split("_L")[1].split("k")[0]) <= 12])
+def test_pywrapper_is_drop_in(name):
+    """gkm_main_pywrapper exactly as scripts/gkmsvm.py:75-88 calls it: padded kmat, row pointers, int[2]"""
+    g, cfg, pos, neg = load_golden(name)
+    n = len(g["lens"])
+    ret, kmat, npos, nneg = capi.main_pywrapper(pos, neg, nthreads=3, verbosity=0, nmax=n + 5, **cfg)
+    assert ret == 0, capi.last_error()
+    assert (npos, nneg) == (int(g["npos"]), n - int(g["npos"]))
+    check_kmat(kmat[:n, :n], g["kmat"], cfg["kernel_type"])
+    assert not kmat[n:].any() and not kmat[:, n:].any(), "wrote outside rows/cols 0..N-1"
+    assert not np.triu(kmat[:n, :n], 1).any(), "upper triangle must stay untouched"
+
+
+def test_pywrapper_parameter_gate_and_errors(tmp_path):
+    g, cfg, pos, neg = load_golden("uni_t2_L11k7d3")
+    for bad in (dict(L=13, k=7, d=3), dict(L=1, k=1, d=0), dict(L=10, k=11, d=0), dict(L=10, k=8, d=3), dict(kernel_type=6)):
+        c = dict(cfg)
+        c.update(bad)
+        ret, kmat, _, _ = capi.main_pywrapper(pos, neg, nmax=24, **c)
+        assert ret == 1 and not kmat.any()
+    ret, kmat, _, _ = capi.main_pywrapper(str(tmp_path / "missing.fa"), neg, nmax=24, **cfg)
+    assert ret == 1 and not kmat.any()
+
+
+def test_long_L_opt_in():
+    g, cfg, pos, neg = load_golden("mix_t2_L13k7d4")
+    n = len(g["lens"])
+    ret, _, _, _ = capi.main_pywrapper(pos, neg, nmax=n, **cfg)
+    assert ret == 1  # reference gate: L <= 12 (gkmkern_pylib.c:54)
+    capi.set_option("max_L", 16)
+    try:
+        ret, kmat, _, _ = capi.main_pywrapper(pos, neg, nmax=n, **cfg)
+        assert ret == 0
+        assert np.array_equal(kmat, g["kmat"])
+    finally:
+        capi.set_option("max_L", 12)
+
+
+@pytest.mark.parametrize("kernel_type,L,k,d,length,ragged", [
+    (2, 11, 7, 3, 300, False), (4, 10, 6, 3, 300, False), (2, 11, 7, 3, 600, True), (4, 12, 8, 4, 257, True),
+    (0, 8, 4, 4, 64, True), (5, 14, 8, 4, 320, False), (2, 16, 12, 4, 200, True), (1, 6, 3, 3, 96, False),
+])
+def test_seeded_against_oracle(kernel_type, L, k, d, length, ragged, variant):
+    n = 96 if length <= 320 else 40
+    seqs = random_seqs(n, length, seed=7 * L + d + kernel_type, ragged=ragged)
+    seqs[3] = seqs[2]                       # duplicate
+    seqs[5] = seqs[4][: max(L, length // 2)]  # prefix
+    o = pyoracle.Oracle(kernel_type, L, k, d, 50, 50.0, 0.7)
+    with capi.Problem(kernel_type, L, k, d, 50, 50.0, 0.7) as P:
+        for s in seqs:
+            o.add(s)
+            P.add(s)
+        Ko, Ho = o.matrix_lower()
+        assert np.array_equal(P.sqnorm(), o.sqnorm())
+        assert np.array_equal(P.hist_block(0, n, 0, n, lower=True), Ho)
+        check_kmat(P.kernel_lower(), Ko, kernel_type)
+        # rectangular "test x SV" shape: SVs at ids [0,nsv), tests after them
+        nsv = n // 3
+        Kr, Hr = o.rect(np.arange(nsv, n), nsv)
+        assert np.array_equal(P.hist_block(nsv, n - nsv, 0, nsv), Hr)
+        check_kmat(P.kernel_block(nsv, n - nsv, 0, nsv), Kr, kernel_type)
+        # fused decision values against the dense block
+        alpha = np.random.default_rng(1).standard_normal(nsv)
+        dv = P.decision_values(nsv, n - nsv, 0, nsv, alpha, bias=0.25)
+        np.testing.assert_allclose(dv, Kr @ alpha + 0.25, rtol=1e-9, atol=1e-12)
+
+
+def test_edge_cases(variant):
+    L, k, d = 11, 7, 3
+    seqs = ["ACGTACGTACG",               # exactly one L-mer
+            "A" * 40, "T" * 40,           # homopolymers, reverse complements of each other
+            "ACGTTGCAACGTTGCAACGT",       # short
+            random_seqs(1, 2047, 5)[0],   # maximum length (2047 bases, libgkm.c:1294-1299)
+            random_seqs(1, 33, 6)[0], random_seqs(1, 32, 7)[0], random_seqs(1, 31, 8)[0], random_seqs(1, 65, 9)[0]]
+    o = pyoracle.Oracle(4, L, k, d)
+    with capi.Problem(4, L, k, d) as P:
+        for s in seqs:
+            o.add(s)
+            P.add(s)
+        n = len(seqs)
+        Ko, Ho = o.matrix_lower()
+        assert np.array_equal(P.hist_block(0, n, 0, n, lower=True), Ho)
+        assert np.array_equal(P.kernel_lower(), Ko)
+        # single sequence problem and empty blocks
+        assert P.kernel_block(0, 0, 0, 0).shape == (0, 0)
+    with capi.Problem(2, L, k, d) as P1:
+        P1.add(seqs[4])
+        assert np.array_equal(P1.kernel_lower(), [[1.0]])
+    with capi.Problem(2, L, k, d) as P2:
+        with pytest.raises(capi.GkmError):
+            P2.add("ACGT")  # shorter than L
+
+
+def test_fasta_without_trailing_newline(tmp_path):
+    seqs = random_seqs(5, 80, 11)
+    p = tmp_path / "p.fa"
+    p.write_text("".join(">s%d x\n%s\n" % (i, s) for i, s in enumerate(seqs[:3])))
+    q = tmp_path / "q.fa"
+    q.write_text(">a\n" + seqs[3] + "\n>b\n" + seqs[4])  # the reference double-frees on this (libgkm.c:1207-1225)
+    ret, kmat, npos, nneg = capi.main_pywrapper(str(p), str(q), nmax=5)
+    assert ret == 0 and (npos, nneg) == (3, 2)
+    o = pyoracle.Oracle()
+    for s in seqs:
+        o.add(s)
+    assert np.array_equal(kmat, o.matrix_lower(False)[0])
+
+
+def test_reference_abi_functions(tmp_path):
+    """the lower-level libgkm.h surface: init / read_problems / build_tree / batch_all / swap / destroy"""
+    import ctypes
+    lib = capi.load()
+    g, cfg, pos, neg = load_golden("mix_t4_L11k7d3")
+    n = len(g["lens"])
+
+    class svm_problem(ctypes.Structure):
+        _fields_ = [("l", ctypes.c_int), ("y", capi.c_dbl_p), ("x", ctypes.POINTER(ctypes.c_void_p))]
+
+    lib.gkmkernel_init.restype = ctypes.c_void_p
+    lib.gkmkernel_init.argtypes = [ctypes.POINTER(capi.gkm_parameter)]
+    lib.gkmkernel_read_problems.argtypes = [ctypes.c_void_p, ctypes.POINTER(svm_problem), ctypes.c_char_p, ctypes.c_char_p]
+    lib.gkmkernel_build_tree.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+    lib.gkmkernel_kernelfunc_batch_all.restype = capi.c_dbl_p
+    lib.gkmkernel_kernelfunc_batch_all.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, capi.c_dbl_p]
+    lib.gkmkernel_swap_index.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    lib.gkmkernel_update_index.argtypes = [ctypes.c_void_p]
+    lib.gkmkernel_delete_object.argtypes = [ctypes.c_void_p]
+    lib.gkmkernel_destroy.argtypes = [ctypes.c_void_p]
+    lib.gkmkernel_new_object.restype = ctypes.c_void_p
+    lib.gkmkernel_new_object.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+
+    param = capi.make_param(**cfg)
+    kern = lib.gkmkernel_init(ctypes.byref(param))
+    assert kern
+    prob = svm_problem()
+    assert lib.gkmkernel_read_problems(kern, ctypes.byref(prob), os.fsencode(pos), os.fsencode(neg)) == int(g["npos"])
+    assert prob.l == n
+    sq = np.array([ctypes.cast(prob.x[i] + 80, capi.c_dbl_p)[0] for i in range(n)])  # gkm_data.sqnorm @80
+    assert np.array_equal(sq, g["sqnorm"])
+    lib.gkmkernel_build_tree(kern, prob.x, n)
+    res = np.zeros(n)
+    for a in (1, 7, n - 1):
+        lib.gkmkernel_kernelfunc_batch_all(kern, a, 0, a, res.ctypes.data_as(capi.c_dbl_p))
+        assert np.array_equal(res[:a], g["kmat"][a, :a])
+    lib.gkmkernel_kernelfunc_batch_all(kern, n - 1, 3, 9, res.ctypes.data_as(capi.c_dbl_p))
+    assert np.array_equal(res[:6], g["kmat"][n - 1, 3:9])
+    # permutation bookkeeping (libgkm.c:1071-1109): after swap+update id 2 and id 5 trade places
+    lib.gkmkernel_swap_index(kern, 2, 5)
+    lib.gkmkernel_update_index(kern)
+    lib.gkmkernel_kernelfunc_batch_all(kern, 7, 0, 7, res.ctypes.data_as(capi.c_dbl_p))
+    perm = list(range(n))
+    perm[2], perm[5] = perm[5], perm[2]
+    full = np.maximum(g["kmat"], g["kmat"].T)
+    assert np.array_equal(res[:7], full[7, perm[:7]])
+    # new_object fills sqnorm from the device
+    obj = lib.gkmkernel_new_object(kern, b"ACGTTGCAACGTTGCAACGTAAA", b"x", 99)
+    assert obj
+    o = pyoracle.Oracle(**cfg)
+    o.add("ACGTTGCAACGTTGCAACGTAAA")
+    assert ctypes.cast(obj + 80, capi.c_dbl_p)[0] == o.sqnorm()[0]
+    lib.gkmkernel_delete_object(obj)
+    for i in range(n):
+        lib.gkmkernel_delete_object(prob.x[i])
+    lib.gkmkernel_destroy(kern)
+
+
+def test_properties_at_scale():
+    """config-1 size (1 000 x 300 bp): things that must hold whatever the inputs are"""
+    n, L, k, d = 1000, 11, 7, 3
+    seqs = random_seqs(n, 300, seed=1234)
+    comp = str.maketrans("ACGT", "TGCA")
+    seqs[10] = seqs[9].translate(comp)[::-1]  # reverse complement of seq 9
+    with capi.Problem(2, L, k, d) as P:
+        P.add_many(seqs)
+        K = P.kernel_lower()
+        assert np.all(np.diag(K) == 1.0) and not np.triu(K, 1).any()
+        low = K[np.tril_indices(n, -1)]
+        assert np.all(np.isfinite(low)) and low.min() >= 0 and low.max() <= 1.0 + 1e-12
+        assert K[10, 9] == 1.0  # K(x, revcomp(x)) = 1: both strands of the target are scanned
+        # symmetry: the block above the diagonal computed the other way round
+        U = P.kernel_block(0, 200, 200, 300)
+        assert np.array_equal(U, K[200:500, 0:200].T)
+        H = P.hist_block(500, 40, 0, 500)
+        Hd4 = None
+        with capi.Problem(2, L, 7, 4) as P4:  # H for d=3 is a prefix of H for d=4; k never touches H
+            P4.add_many(seqs[:540])
+            Hd4 = P4.hist_block(500, 40, 0, 500)
+        assert np.array_equal(H, Hd4[..., :4])
+        # checksum against the oracle on a stated subsample of rows
+        o = pyoracle.Oracle(2, L, k, d)
+        for s in seqs:
+            o.add(s)
+        rows = np.array([1, 17, 333, 999])
+        for r in rows:
+            Kr, Hr = o.rect(np.array([r]), int(r))
+            assert np.array_equal(Kr[0], K[r, :r])
+
+
+def test_multi_gpu_in_one_process_if_available():
+    ndev = capi.device_count()
+    if ndev < 2:
+        pytest.skip("single GPU box")
+    seqs = random_seqs(700, 300, seed=77)
+    with capi.Problem(2, 11, 7, 3) as P:
+        P.add_many(seqs)
+        K = P.kernel_lower()
+        assert P.stats()["devices"] == ndev
+    ids = (capi.ctypes.c_int * 1)(0)
+    assert capi.load().gkmb200_set_devices(ids, 1) == 0
+    with capi.Problem(2, 11, 7, 3) as P:
+        P.add_many(seqs)
+        assert np.array_equal(P.kernel_lower(), K)
+
+
+def test_sharded_ranks_cover_the_matrix():
+    """two 'ranks' in one process: each computes only the chunks it owns; together = the full triangle"""
+    seqs = random_seqs(900, 300, seed=5)
+    parts = []
+    for rank in range(2):
+        with capi.Problem(2, 11, 7, 3) as P:
+            P.add_many(seqs)
+            P.set_shard(rank, 2)
+            parts.append(P.kernel_lower())
+    with capi.Problem(2, 11, 7, 3) as P:
+        P.add_many(seqs)
+        full = P.kernel_lower()
+    low = np.tril_indices(900, -1)
+    a, b = parts[0][low], parts[1][low]
+    assert not np.any((a != 0) & (b != 0)), "shards overlap"
+    assert np.array_equal(a + b, full[low])
