@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the number of sequences (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +257,7 @@ def main():
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 3))
     walls = []
     h2d = d2h = 0
-    for it in range(1 + e2e_steps):
+    for it in range(0 if args.no_e2e else 1 + e2e_steps):
         kmat = np.zeros((n, n))
         dist_barrier(dist)
         t0 = time.perf_counter()
@@ -270,6 +271,8 @@ def main():
         lib.gkmb200_get_stats(None, capi.ctypes.byref(pst))
         h2d, d2h = int(pst.h2d_bytes), int(pst.d2h_bytes)
         del kmat
+    if args.no_e2e:
+        walls = [float("nan")]
     e2e_value = total_entries / float(np.mean(walls))
     h2d = int(dist_sum(dist, h2d))
     d2h = int(dist_sum(dist, d2h))

@@ -284,3 +284,13 @@ def test_sharded_ranks_cover_the_matrix():
     a, b = parts[0][low], parts[1][low]
     assert not np.any((a != 0) & (b != 0)), "shards overlap"
     assert np.array_equal(a + b, full[low])
+
+
+def test_driver_mirror_returns_what_gkmsvm_would():
+    """computeGkmKernel(args_gkm) with gkmQC's default parameters (bin/gkmqc.py:169-199): wgkm, L=10 k=6 d=3"""
+    from gkmqc_b200 import driver
+    g, cfg, pos, neg = load_golden("uni_t4_L10k6d3")
+    kmat, npos, nneg = driver.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, pos, neg, 4, 0], max_seqs=64)
+    n = len(g["lens"])
+    assert (npos, nneg) == (int(g["npos"]), n - int(g["npos"])) and kmat.shape == (n, n)
+    assert np.array_equal(kmat, np.maximum(g["kmat"], g["kmat"].T))
