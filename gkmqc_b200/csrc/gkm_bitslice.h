@@ -8,25 +8,39 @@
  * loop (libgkm.c:738-751):  H_m(a,b) = sum over L-mer pairs at Hamming distance
  * m <= d of wt_a * wt_b.
  *
- * Formulation.  Fix query a, target strand s (forward or reverse complement of
- * b, circularly extended to P = 32*Wb positions) and a diagonal delta.  Let
- *     mm_delta[e] = [ a[e] != s[(e + delta) mod P] ]          (one bit)
- * The L-mer pair (window of a ENDING at e, window of s ending at j = e + delta)
- * has Hamming distance  sum_{t<L} mm_delta[e - t].  One 32-bit word holds 32
- * consecutive diagonals delta = 32q .. 32q+31 (one word per lane), and the kernel
- * walks e = 0, 1, 2, ...: the window sum is a sliding sum ACROSS successive words,
- * so it needs no shifts at all -- only bit-sliced adders (LOP3 xor3 / majority)
- * over a register ring of the last 16 words.  Per 32 L-mer pairs: 3 funnel shifts
- * (target planes and validity mask seen through a bit window that slides with e),
- * 2 LOP3 for the mismatch word, ~12 LOP3 for the sliding count (L = 11), ~6 for
- * thresholding into the d+1 bins, one POPC per bin.  The canonical XOR/POPC
- * formulation needs ~5 integer operations per PAIR.
+ * Formulation.  The target b is laid out as ONE circular string C of P = 32*Wc
+ * positions: forward strand at [0,len), reverse complement at [len,2len), zero
+ * padding after it.  Fix query a and a diagonal delta and let
+ *     mm_delta[e] = [ a[e] != C[(e + delta) mod P] ]            (one bit)
+ * The L-mer pair (window of a ENDING at e, window of C ending at j = e + delta)
+ * has Hamming distance  cnt[e] = sum_{t<L} mm_delta[e - t].  One 32-bit word holds
+ * 32 consecutive diagonals delta = 32q .. 32q+31 (one word per lane) and the kernel
+ * walks e = 0, 1, 2, ...  The count is kept as a bit-sliced RUNNING counter
+ * (plane i = bit i of 32 independent counters):
+ *     cnt[e] = cnt[e-1] + mm[e] - mm[e-L]
+ * i.e. one conditional +-1 per step: x = mm[e] ^ mm[e-L] says "changes",
+ * mm[e-L] says "down"; a ripple of  p_i ^= c ; c &= (p_i ^ down)  costs two LOP3
+ * per plane -- 8 for L <= 15 -- against a 16-word register ring of past mm words.
+ * No shifts are needed for the sum because it slides ACROSS successive words.
  *
- * Validity: windows that run off either sequence, wrap around the circular
- * extension or end before position L-1 are removed by AND-ing the hit word with
- *   Va[e]  (query side, warp-uniform word: all-ones iff L-1 <= e < len_a) and
- *   E[j]   (target side bit plane: 1 iff L-1 <= j < len_b),
+ * Each lane serves TWO queries at once: the three sliding bit windows of the
+ * target (two code planes and the validity plane E) are extracted once per step
+ * with funnel shifts and used for both.
+ *
+ * Validity: windows that run off either strand, straddle the strand junction or
+ * the wrap, or end before position L-1 are removed by AND-ing the hit word with
+ *   E[j]   target side bit plane: 1 iff j is a valid window end of either strand
+ *   Va[e]  query side, warp-uniform word: all-ones iff L-1 <= e < len_a (only the
+ *          first and the last chunks of a query can contain invalid ends, so only
+ *          those run the body variant that pays for the AND),
  * so garbage in padding bits can never be counted.
+ *
+ * Pipe balance (sm_100, measured): LOP3/SHF/IADD3 issue at 64
+ * lanes/clk/SM on the ALU pipe, IMAD at 64 on the FMA pipe, POPC at 16 on the XU
+ * pipe.  The counter is LOP3-only, so the ALU pipe is the bound; the XU pipe comes
+ * second.  FLAVOR bits: GKM_F_RARE_BINS takes the two rarest bins (count <= 1 when
+ * NB = 4) off the straight-line path (no POPC for them; a loop entered for ~1 % of
+ * the warp steps), GKM_F_IMAD_ACC accumulates the counters through IMAD.
  */
 #ifndef GKM_BITSLICE_H_INCLUDED
 #define GKM_BITSLICE_H_INCLUDED
@@ -41,20 +55,30 @@
 #define GKM_HDM inline
 #endif
 
-/* query-side record for one position e, read as one 16-byte broadcast load */
-struct alignas(16) gkm_apos {
-    uint32_t a0; /* all-ones iff low  bit of base code a[e] is 1 */
-    uint32_t a1; /* all-ones iff high bit of base code a[e] is 1 */
-    uint32_t va; /* all-ones iff a window may end at e           */
-    uint32_t wa; /* positional weight of the window ending at e  */
+enum { GKM_F_RARE_BINS = 2, GKM_F_IMAD_ACC = 4 };
+
+#if defined(__CUDACC__)
+/* the constant 1 behind a constant-bank load, so that ptxas keeps IMAD for the accumulation */
+static __constant__ uint32_t gkm_one_c[1] = { 1u };
+#endif
+
+/* query-side records of a PAIR of queries for one position e (two 16-byte broadcast loads) */
+struct alignas(16) gkm_apos2 {
+    uint32_t a0[2]; /* [q]: all-ones iff low  bit of base code a_q[e] is 1 */
+    uint32_t a1[2]; /* [q]: all-ones iff high bit of base code a_q[e] is 1 */
+};
+struct alignas(16) gkm_aaux2 {
+    uint32_t va[2]; /* [q]: all-ones iff a window of query q may end at e  */
+    uint32_t wa[2]; /* [q]: positional weight of the window ending at e    */
 };
 
-GKM_HD uint32_t gkm_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+/* bits [s, s+32) of the 64-bit value hi:lo, 0 <= s < 32 */
+GKM_HD uint32_t gkm_funnel(uint32_t lo, uint32_t hi, int s)
 {
 #if defined(__CUDA_ARCH__)
-    return __funnelshift_r(lo, hi, s);
+    return __funnelshift_r(lo, hi, (uint32_t) s);
 #else
-    return s ? ((lo >> s) | (hi << (32u - s))) : lo;
+    return s ? ((lo >> s) | (hi << (32 - s))) : lo;
 #endif
 }
 
@@ -76,226 +100,208 @@ GKM_HD int gkm_ffs0(uint32_t x) /* index of lowest set bit, x != 0 */
 #endif
 }
 
-GKM_HD uint32_t gkm_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }
-GKM_HD uint32_t gkm_maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
+template <int FLAVOR>
+GKM_HD void gkm_acc_add(int32_t &acc, int v)
+{
+#if defined(__CUDA_ARCH__)
+    if constexpr ((FLAVOR & GKM_F_IMAD_ACC) != 0) {
+        acc = (int32_t) ((uint32_t) v * gkm_one_c[0] + (uint32_t) acc);
+        return;
+    }
+#endif
+    acc += v;
+}
 
-/* ---- bit-sliced unsigned numbers: plane i holds bit i of 32 independent counters ---- */
 constexpr int gkm_nplanes(int maxv) { return maxv >= 16 ? 5 : maxv >= 8 ? 4 : maxv >= 4 ? 3 : maxv >= 2 ? 2 : 1; }
 
-template <int MAXV>
-struct gkm_bs {
-    static constexpr int NP = gkm_nplanes(MAXV);
-    uint32_t p[NP];
-    GKM_HDM uint32_t plane(int i) const { return i < NP ? p[i] : 0u; }
-};
-
-/* X + Y (+ carry-in plane) by ripple carry: one xor3 and one majority per plane */
-template <int MX, int MY, bool CIN>
-GKM_HD gkm_bs<MX + MY + (CIN ? 1 : 0)> gkm_bs_add(const gkm_bs<MX> &x, const gkm_bs<MY> &y, uint32_t cin)
-{
-    gkm_bs<MX + MY + (CIN ? 1 : 0)> r;
-    constexpr int NR = gkm_bs<MX + MY + (CIN ? 1 : 0)>::NP;
-    uint32_t c = CIN ? cin : 0u;
-#pragma unroll
-    for (int i = 0; i < NR; i++) {
-        const uint32_t xi = x.plane(i), yi = y.plane(i);
-        r.p[i] = gkm_xor3(xi, yi, c);
-        c = gkm_maj3(xi, yi, c);
-    }
-    return r;
-}
-
-/* X + one bit plane */
-template <int MX>
-GKM_HD gkm_bs<MX + 1> gkm_bs_inc(const gkm_bs<MX> &x, uint32_t bit)
-{
-    gkm_bs<MX + 1> r;
-    constexpr int NR = gkm_bs<MX + 1>::NP;
-    uint32_t c = bit;
-#pragma unroll
-    for (int i = 0; i < NR; i++) {
-        const uint32_t xi = x.plane(i);
-        r.p[i] = xi ^ c;
-        c = xi & c;
-    }
-    return r;
-}
-
-/* ---- per-lane sliding state: the last 16 mismatch words and the last RW 3-sums ---- */
-template <int L>
-struct gkm_win_state {
-    static constexpr int Q = L / 3;                   /* number of 3-sums in the window  */
-    static constexpr int R = L % 3;                   /* left-over single positions      */
-    static constexpr int RW = (Q >= 4) ? 16 : 8;      /* ring length for the 3-sums      */
-    uint32_t m[16];
-    uint32_t t0[RW], t1[RW];                          /* planes of w3[e] = m[e]+m[e-1]+m[e-2] */
-    GKM_HDM void clear()
-    {
-#pragma unroll
-        for (int i = 0; i < 16; i++) m[i] = 0u;
-#pragma unroll
-        for (int i = 0; i < RW; i++) { t0[i] = 0u; t1[i] = 0u; }
-    }
-};
-
-/* accumulate the remaining 3-sums (index I..Q-1) and single bits (index BI..R-1) */
-template <int L, int S, int I, int BI, int MV>
-GKM_HD auto gkm_win_accum(const gkm_bs<MV> &acc, const gkm_win_state<L> &st)
-{
-    constexpr int Q = gkm_win_state<L>::Q, R = gkm_win_state<L>::R, RW = gkm_win_state<L>::RW;
-    if constexpr (I < Q) {
-        gkm_bs<3> t;
-        t.p[0] = st.t0[(S - 3 * I) & (RW - 1)];
-        t.p[1] = st.t1[(S - 3 * I) & (RW - 1)];
-        if constexpr (BI < R) {
-            auto n = gkm_bs_add<MV, 3, true>(acc, t, st.m[(S - (3 * Q + BI)) & 15]);
-            return gkm_win_accum<L, S, I + 1, BI + 1>(n, st);
-        } else {
-            auto n = gkm_bs_add<MV, 3, false>(acc, t, 0u);
-            return gkm_win_accum<L, S, I + 1, BI>(n, st);
-        }
-    } else if constexpr (BI < R) {
-        auto n = gkm_bs_inc<MV>(acc, st.m[(S - (3 * Q + BI)) & 15]);
-        return gkm_win_accum<L, S, I, BI + 1>(n, st);
-    } else {
-        return acc;
-    }
-}
-
-/* push mismatch word `mm` of step S (compile-time ring slot) and return the bit-sliced
- * number of mismatches of the L-window ending here (value 0..L per bit lane) */
-template <int L, int S>
-GKM_HD gkm_bs<L> gkm_win_push(gkm_win_state<L> &st, uint32_t mm)
-{
-    constexpr int Q = gkm_win_state<L>::Q, RW = gkm_win_state<L>::RW;
-    st.m[S & 15] = mm;
-    if constexpr (Q == 0) {
-        gkm_bs<1> b; b.p[0] = mm;
-        if constexpr (L == 1) return b;
-        else return gkm_bs_inc<1>(b, st.m[(S - 1) & 15]);
-    } else {
-        const uint32_t m1 = st.m[(S - 1) & 15], m2 = st.m[(S - 2) & 15];
-        gkm_bs<3> t;
-        t.p[0] = gkm_xor3(mm, m1, m2);
-        t.p[1] = gkm_maj3(mm, m1, m2);
-        st.t0[S & (RW - 1)] = t.p[0];
-        st.t1[S & (RW - 1)] = t.p[1];
-        return gkm_win_accum<L, S, 1, 0>(t, st);
-    }
-}
-
-/* ---- binning: NB = 4, 8 or 16 histogram bins (count values 0..NB-1) ---- */
 template <int NB> struct gkm_log2nb;
 template <> struct gkm_log2nb<4> { static constexpr int v = 2; };
 template <> struct gkm_log2nb<8> { static constexpr int v = 3; };
 template <> struct gkm_log2nb<16> { static constexpr int v = 4; };
 
-/* word of bit lanes whose count is < NB, restricted to `valid` */
-template <int L, int NB>
-GKM_HD uint32_t gkm_hit_word(const gkm_bs<L> &cnt, uint32_t valid)
+/* ---- per-lane, per-query sliding state ---- */
+template <int L>
+struct gkm_win_state {
+    static constexpr int NP = gkm_nplanes(L);
+    uint32_t m[16];  /* ring of the last 16 mismatch words */
+    uint32_t p[NP];  /* bit-sliced count of mismatches in the current L-window */
+    GKM_HDM void clear()
+    {
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < NP; i++) p[i] = 0u;
+    }
+};
+
+/* push mismatch word `mm` of step S (compile-time ring slot): cnt += mm - mm[e-L] */
+template <int L, int S>
+GKM_HD void gkm_win_push(gkm_win_state<L> &st, uint32_t mm)
 {
-    constexpr int LB = gkm_log2nb<NB>::v;
+    constexpr int NP = gkm_win_state<L>::NP;
+    const uint32_t down = st.m[(S - L) & 15]; /* the position leaving the window (read before the slot is reused) */
+    st.m[S & 15] = mm;
+    uint32_t c = mm ^ down;                   /* lanes whose count changes */
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        const uint32_t t = st.p[i];
+        st.p[i] = t ^ c;
+        if (i + 1 < NP) c &= (t ^ down);      /* carry when counting up, borrow when counting down */
+    }
+}
+
+/* bit lanes whose count is < NB, restricted to `valid` */
+template <int L, int LB>
+GKM_HD uint32_t gkm_hit_word(const gkm_win_state<L> &st, uint32_t valid)
+{
     uint32_t high = 0u;
 #pragma unroll
-    for (int i = LB; i < gkm_bs<L>::NP; i++) high |= cnt.p[i];
+    for (int i = LB; i < gkm_win_state<L>::NP; i++) high |= st.p[i];
     return valid & ~high;
 }
 
+template <int L, int LB>
+GKM_HD uint32_t gkm_plane(const gkm_win_state<L> &st, int i) { return i < gkm_win_state<L>::NP ? st.p[i] : 0u; }
+
 /* mask of bit lanes (within hit) whose count equals V */
-template <int L, int NB, int V>
-GKM_HD uint32_t gkm_bin_mask(const gkm_bs<L> &cnt, uint32_t hit)
+template <int L, int LB, int V>
+GKM_HD uint32_t gkm_bin_mask(const gkm_win_state<L> &st, uint32_t hit)
 {
-    constexpr int LB = gkm_log2nb<NB>::v;
     uint32_t r = hit;
 #pragma unroll
-    for (int i = 0; i < LB; i++) r &= ((V >> i) & 1) ? cnt.plane(i) : ~cnt.plane(i);
+    for (int i = 0; i < LB; i++) r &= ((V >> i) & 1) ? gkm_plane<L, LB>(st, i) : ~gkm_plane<L, LB>(st, i);
     return r;
 }
 
-template <int L, int NB, int V>
-GKM_HD void gkm_bins_popc(const gkm_bs<L> &cnt, uint32_t hit, int32_t *acc)
+template <int L, int LB, int FLAVOR, int V0, int V1>
+GKM_HD void gkm_bins_popc(const gkm_win_state<L> &st, uint32_t hit, int32_t *acc)
 {
-    if constexpr (V < NB) {
-        if constexpr (V <= L) acc[V] += gkm_popc(gkm_bin_mask<L, NB, V>(cnt, hit));
-        gkm_bins_popc<L, NB, V + 1>(cnt, hit, acc);
+    if constexpr (V0 < V1) {
+        if constexpr (V0 <= L) gkm_acc_add<FLAVOR>(acc[V0], gkm_popc(gkm_bin_mask<L, LB, V0>(st, hit)));
+        gkm_bins_popc<L, LB, FLAVOR, V0 + 1, V1>(st, hit, acc);
     }
 }
 
 /* weighted bins: rare path, one (e, j) pair per set bit of `hit` */
-template <int L, int NB>
-GKM_HD void gkm_bins_weighted(const gkm_bs<L> &cnt, uint32_t hit, uint32_t wa, const uint8_t *wend,
-                              int jbase_lo, int jbase_hi, int s, int32_t *acc)
+template <int L, int LB>
+GKM_HD void gkm_bins_weighted(const gkm_win_state<L> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
+                              int jbase, int P, int32_t *acc)
 {
-    constexpr int LB = gkm_log2nb<NB>::v;
     while (hit) {
         const int bit = gkm_ffs0(hit);
         hit &= hit - 1u;
         int v = 0;
 #pragma unroll
-        for (int i = 0; i < LB; i++) v |= (int) ((cnt.plane(i) >> bit) & 1u) << i;
-        const int off = s + bit;
-        const int j = (off < 32) ? (jbase_lo + off) : (jbase_hi + off - 32);
+        for (int i = 0; i < LB; i++) v |= (int) ((gkm_plane<L, LB>(st, i) >> bit) & 1u) << i;
+        int j = jbase + bit;
+        while (j >= P) j -= P;
         const int w = (int) wa * (int) wend[j];
 #pragma unroll
-        for (int b = 0; b < NB; b++) acc[b] += (v == b) ? w : 0;
+        for (int b = 0; b < (1 << LB); b++) acc[b] += (v == b) ? w : 0;
     }
 }
 
-/* one step e = 32*c + S of one lane */
-template <int L, int NB, bool WEIGHTED, int S>
-GKM_HD void gkm_diag_step(gkm_win_state<L> &st, const gkm_apos &ap,
-                          uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1, uint32_t loE, uint32_t hiE,
-                          const uint8_t *wend, int jbase_lo, int jbase_hi, int32_t *acc)
+/* binning of one query at one step */
+template <int L, int NB, bool WEIGHTED, int FLAVOR>
+GKM_HD void gkm_bins(const gkm_win_state<L> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
+                     int jbase, int P, int32_t *acc)
 {
-    const uint32_t s0 = gkm_funnel_r(lo0, hi0, S);
-    const uint32_t s1 = gkm_funnel_r(lo1, hi1, S);
-    const uint32_t ev = gkm_funnel_r(loE, hiE, S) & ap.va;
-    const uint32_t mm = (s0 ^ ap.a0) | (s1 ^ ap.a1);
-    const gkm_bs<L> cnt = gkm_win_push<L, S>(st, mm);
-    const uint32_t hit = gkm_hit_word<L, NB>(cnt, ev);
+    constexpr int LB = gkm_log2nb<NB>::v;
     if constexpr (WEIGHTED) {
-        if (hit) gkm_bins_weighted<L, NB>(cnt, hit, ap.wa, wend, jbase_lo, jbase_hi, S, acc);
+        if (hit) gkm_bins_weighted<L, LB>(st, hit, wa, wend, jbase, P, acc);
+    } else if constexpr ((FLAVOR & GKM_F_RARE_BINS) != 0 && NB == 4) {
+        gkm_bins_popc<L, LB, FLAVOR, 2, 4>(st, hit, acc);   /* counts 2 and 3: ~99 % of all hits */
+        uint32_t rare = hit & ~gkm_plane<L, LB>(st, 1);      /* counts 0 and 1 */
+        if (rare) {
+            /* a loop, so that the compiler keeps this off the straight-line path (a real branch,
+             * not predication): entered for ~1 % of the warp steps on random sequences */
+            do {
+                const uint32_t low = rare & (0u - rare);
+                rare ^= low;
+                if (gkm_plane<L, LB>(st, 0) & low) acc[1] += 1; else acc[0] += 1;
+            } while (rare);
+        }
     } else {
-        gkm_bins_popc<L, NB, 0>(cnt, hit, acc);
+        gkm_bins_popc<L, LB, FLAVOR, 0, NB>(st, hit, acc);
     }
 }
 
-template <int L, int NB, bool WEIGHTED, int S0, int S1>
-GKM_HD void gkm_diag_steps(gkm_win_state<L> &st, const gkm_apos *ap,
+/* steps S0..S1-1 of one half chunk (16 positions) for the query pair */
+template <int L, int NB, bool WEIGHTED, int FLAVOR, bool USE_VA, int S0, int S1>
+GKM_HD void gkm_diag_steps(gkm_win_state<L> &st0, gkm_win_state<L> &st1,
+                           const gkm_apos2 *ap, const gkm_aaux2 *ax,
                            uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1, uint32_t loE, uint32_t hiE,
-                           const uint8_t *wend, int jbase_lo, int jbase_hi, int32_t *acc)
+                           const uint8_t *wend, int jbase, int P, int32_t *acc0, int32_t *acc1)
 {
     if constexpr (S0 < S1) {
-        gkm_diag_step<L, NB, WEIGHTED, S0>(st, ap[S0], lo0, hi0, lo1, hi1, loE, hiE, wend, jbase_lo, jbase_hi, acc);
-        gkm_diag_steps<L, NB, WEIGHTED, S0 + 1, S1>(st, ap, lo0, hi0, lo1, hi1, loE, hiE, wend, jbase_lo, jbase_hi, acc);
+        constexpr int LB = gkm_log2nb<NB>::v;
+        const gkm_apos2 a = ap[S0];
+        const uint32_t s0 = gkm_funnel(lo0, hi0, S0);
+        const uint32_t s1 = gkm_funnel(lo1, hi1, S0);
+        const uint32_t ev = gkm_funnel(loE, hiE, S0);
+        gkm_win_push<L, S0>(st0, (s0 ^ a.a0[0]) | (s1 ^ a.a1[0]));
+        gkm_win_push<L, S0>(st1, (s0 ^ a.a0[1]) | (s1 ^ a.a1[1]));
+        uint32_t v0 = ev, v1 = ev, w0 = 1u, w1 = 1u;
+        if constexpr (USE_VA || WEIGHTED) {
+            const gkm_aaux2 x = ax[S0];
+            if constexpr (USE_VA) { v0 &= x.va[0]; v1 &= x.va[1]; }
+            w0 = x.wa[0]; w1 = x.wa[1];
+        }
+        gkm_bins<L, NB, WEIGHTED, FLAVOR>(st0, gkm_hit_word<L, LB>(st0, v0), w0, wend, jbase + S0, P, acc0);
+        gkm_bins<L, NB, WEIGHTED, FLAVOR>(st1, gkm_hit_word<L, LB>(st1, v1), w1, wend, jbase + S0, P, acc1);
+        gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, USE_VA, S0 + 1, S1>(st0, st1, ap, ax, lo0, hi0, lo1, hi1, loE, hiE,
+                                                                     wend, jbase, P, acc0, acc1);
     }
 }
 
-/* One lane = one (target strand, block of 32 diagonals q) against one query.
- *   apos      query records, 32*Wa of them (positions >= len_a have va = 0)
- *   len_a     query length
- *   S0,S1,E   target strand bit planes and valid-window-end plane, Wb words each (circular)
- *   wend      WEIGHTED: target weights by window end position, 32*Wb bytes
- *   acc       NB counters, added to                                                     */
-template <int L, int NB, bool WEIGHTED>
-GKM_HD void gkm_diag_lane(const gkm_apos *apos, int len_a,
-                          const uint32_t *S0, const uint32_t *S1, const uint32_t *E, int Wb, int q,
-                          const uint8_t *wend, int32_t *acc)
+/* One lane = one block of 32 diagonals q of one target against a PAIR of queries.
+ *   apos/aaux  records of the pair, 32*ceil(max(len0,len1)/32) of each (va = 0 beyond a query's end;
+ *              a query of length 0 is a dummy)
+ *   C0,C1,E    target bit planes (both strands, circular) and valid-window-end plane, Wc words each
+ *   wend       WEIGHTED: target weights by window end position, 32*Wc bytes
+ *   acc0/acc1  NB counters per query, added to                                              */
+template <int L, int NB, bool WEIGHTED, int FLAVOR>
+GKM_HD void gkm_diag_lane(const gkm_apos2 *apos, const gkm_aaux2 *aaux, int len0, int len1,
+                          const uint32_t *C0, const uint32_t *C1, const uint32_t *E, int Wc, int q,
+                          const uint8_t *wend, int32_t *acc0, int32_t *acc1)
 {
-    gkm_win_state<L> st;
-    st.clear();
-    int k = q;
-    uint32_t lo0 = S0[k], lo1 = S1[k], loE = E[k];
-    const int Wa = (len_a + 31) >> 5;
-    for (int c = 0; c < Wa; c++) {
-        const int kn = (k + 1 == Wb) ? 0 : k + 1;
-        const uint32_t hi0 = S0[kn], hi1 = S1[kn], hiE = E[kn];
-        const gkm_apos *ap = apos + 32 * c;
-        gkm_diag_steps<L, NB, WEIGHTED, 0, 16>(st, ap, lo0, hi0, lo1, hi1, loE, hiE, wend, 32 * k, 32 * kn, acc);
-        if (32 * c + 16 < len_a)
-            gkm_diag_steps<L, NB, WEIGHTED, 16, 32>(st, ap, lo0, hi0, lo1, hi1, loE, hiE, wend, 32 * k, 32 * kn, acc);
-        lo0 = hi0; lo1 = hi1; loE = hiE;
-        k = kn;
+    gkm_win_state<L> st0, st1;
+    st0.clear();
+    st1.clear();
+    const int lmax = len0 > len1 ? len0 : len1;
+    const int lmin = (len0 > 0 && len1 > 0) ? (len0 < len1 ? len0 : len1) : 0; /* a dummy needs va everywhere */
+    const int P = 32 * Wc;
+    int k = q;                                   /* word holding stream bits [32(q+c), 32(q+c)+32) */
+    int k1 = (k + 1 == Wc) ? 0 : k + 1;
+    uint32_t a0 = C0[k], a1 = C1[k], aE = E[k];  /* word k */
+    uint32_t b0 = C0[k1], b1 = C1[k1], bE = E[k1];
+    const int nhalf = (lmax + 15) >> 4;          /* half chunks of 16 positions */
+    int jbase = 32 * q;
+#pragma unroll 1
+    for (int h = 0; h < nhalf; h += 2) {
+        const int k2 = (k1 + 1 == Wc) ? 0 : k1 + 1;
+        const uint32_t c0 = C0[k2], c1 = C1[k2], cE = E[k2];
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            if (h + half >= nhalf) break;
+            const int e0 = 16 * (h + half);
+            /* stream bits [e0', e0'+64) seen from this lane: aligned words, or words shifted by 16 */
+            const uint32_t lo0 = half ? gkm_funnel(a0, b0, 16) : a0, hi0 = half ? gkm_funnel(b0, c0, 16) : b0;
+            const uint32_t lo1 = half ? gkm_funnel(a1, b1, 16) : a1, hi1 = half ? gkm_funnel(b1, c1, 16) : b1;
+            const uint32_t loE = half ? gkm_funnel(aE, bE, 16) : aE, hiE = half ? gkm_funnel(bE, cE, 16) : bE;
+            const bool need_va = (e0 < L - 1) || (e0 + 16 > lmin);
+            if (need_va)
+                gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, true, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
+                                                                      wend, jbase, P, acc0, acc1);
+            else
+                gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, false, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
+                                                                       wend, jbase, P, acc0, acc1);
+            jbase += 16;
+            if (jbase >= P) jbase -= P;
+        }
+        a0 = b0; a1 = b1; aE = bE;
+        b0 = c0; b1 = c1; bE = cE;
+        k1 = k2;
     }
 }
 

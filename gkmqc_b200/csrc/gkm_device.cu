@@ -35,24 +35,24 @@
     } while (0)
 
 extern "C" {
-const void *gkm_diag_fn_L2(int, int);  const void *gkm_diag_fn_L3(int, int);  const void *gkm_diag_fn_L4(int, int);
-const void *gkm_diag_fn_L5(int, int);  const void *gkm_diag_fn_L6(int, int);  const void *gkm_diag_fn_L7(int, int);
-const void *gkm_diag_fn_L8(int, int);  const void *gkm_diag_fn_L9(int, int);  const void *gkm_diag_fn_L10(int, int);
-const void *gkm_diag_fn_L11(int, int); const void *gkm_diag_fn_L12(int, int); const void *gkm_diag_fn_L13(int, int);
-const void *gkm_diag_fn_L14(int, int); const void *gkm_diag_fn_L15(int, int); const void *gkm_diag_fn_L16(int, int);
+const void *gkm_diag_fn_L2(int, int, int);  const void *gkm_diag_fn_L3(int, int, int);  const void *gkm_diag_fn_L4(int, int, int);
+const void *gkm_diag_fn_L5(int, int, int);  const void *gkm_diag_fn_L6(int, int, int);  const void *gkm_diag_fn_L7(int, int, int);
+const void *gkm_diag_fn_L8(int, int, int);  const void *gkm_diag_fn_L9(int, int, int);  const void *gkm_diag_fn_L10(int, int, int);
+const void *gkm_diag_fn_L11(int, int, int); const void *gkm_diag_fn_L12(int, int, int); const void *gkm_diag_fn_L13(int, int, int);
+const void *gkm_diag_fn_L14(int, int, int); const void *gkm_diag_fn_L15(int, int, int); const void *gkm_diag_fn_L16(int, int, int);
 }
 
-static const void *diag_fn(int L, int nb, int weighted)
+static const void *diag_fn(int L, int nb, int weighted, int flavor)
 {
     switch (L) {
-        case 2: return gkm_diag_fn_L2(nb, weighted);   case 3: return gkm_diag_fn_L3(nb, weighted);
-        case 4: return gkm_diag_fn_L4(nb, weighted);   case 5: return gkm_diag_fn_L5(nb, weighted);
-        case 6: return gkm_diag_fn_L6(nb, weighted);   case 7: return gkm_diag_fn_L7(nb, weighted);
-        case 8: return gkm_diag_fn_L8(nb, weighted);   case 9: return gkm_diag_fn_L9(nb, weighted);
-        case 10: return gkm_diag_fn_L10(nb, weighted); case 11: return gkm_diag_fn_L11(nb, weighted);
-        case 12: return gkm_diag_fn_L12(nb, weighted); case 13: return gkm_diag_fn_L13(nb, weighted);
-        case 14: return gkm_diag_fn_L14(nb, weighted); case 15: return gkm_diag_fn_L15(nb, weighted);
-        case 16: return gkm_diag_fn_L16(nb, weighted);
+        case 2: return gkm_diag_fn_L2(nb, weighted, flavor);   case 3: return gkm_diag_fn_L3(nb, weighted, flavor);
+        case 4: return gkm_diag_fn_L4(nb, weighted, flavor);   case 5: return gkm_diag_fn_L5(nb, weighted, flavor);
+        case 6: return gkm_diag_fn_L6(nb, weighted, flavor);   case 7: return gkm_diag_fn_L7(nb, weighted, flavor);
+        case 8: return gkm_diag_fn_L8(nb, weighted, flavor);   case 9: return gkm_diag_fn_L9(nb, weighted, flavor);
+        case 10: return gkm_diag_fn_L10(nb, weighted, flavor); case 11: return gkm_diag_fn_L11(nb, weighted, flavor);
+        case 12: return gkm_diag_fn_L12(nb, weighted, flavor); case 13: return gkm_diag_fn_L13(nb, weighted, flavor);
+        case 14: return gkm_diag_fn_L14(nb, weighted, flavor); case 15: return gkm_diag_fn_L15(nb, weighted, flavor);
+        case 16: return gkm_diag_fn_L16(nb, weighted, flavor);
         default: return NULL;
     }
 }
@@ -210,15 +210,16 @@ static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st
     unsigned smem = 0;
     if (variant == GKM_KERNEL_DIAG) {
         const int nb = (p->param.d < 4) ? 4 : (p->param.d < 8) ? 8 : 16;
-        fn = diag_fn(p->param.L, nb, p->weighted);
+        fn = diag_fn(p->param.L, nb, p->weighted, gkm_opt_diag_flavor());
         if (!fn) { gkm_set_error("no diag kernel for L=%d", p->param.L); return 1; }
-        static const int cand[][2] = { {8, 16}, {4, 16}, {4, 8}, {2, 8}, {1, 8}, {1, 4}, {1, 2}, {1, 1} };
+        /* TB = 32 makes the lane-task count of a uniform-length tile a multiple of the warp size */
+        static const int cand[][2] = { {8, 32}, {4, 32}, {4, 16}, {2, 16}, {2, 8}, {2, 4}, {2, 2}, {2, 1} }; /* TA even: queries go in pairs */
         int chosen = -1;
         for (int pass = 0; pass < 2 && chosen < 0; pass++)
             for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); i++) {
                 if (forced_ta && cand[i][0] != forced_ta && pass == 0) continue;
-                unsigned s = gkm_diag_layout(p->Wmax, cand[i][0], cand[i][1], nb, p->weighted).total;
-                if (s <= (pass == 0 ? 72u * 1024u : 220u * 1024u)) { chosen = (int) i; smem = s; break; }
+                unsigned s = gkm_diag_layout(p->Wmax, p->Wa, cand[i][0], cand[i][1], nb, p->weighted).total;
+                if (s <= (pass == 0 ? 74u * 1024u : 220u * 1024u)) { chosen = (int) i; smem = s; break; }
             }
         if (chosen < 0) { gkm_set_error("sequence too long for shared memory"); return 1; }
         kp.TA = cand[chosen][0];
@@ -229,7 +230,7 @@ static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st
         int chosen = -1;
         for (int pass = 0; pass < 2 && chosen < 0; pass++)
             for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); i++) {
-                unsigned s = gkm_lmer_smem_bytes(p->Wmax, cand[i][0], cand[i][1], p->nbins, p->weighted);
+                unsigned s = gkm_lmer_smem_bytes(p->Wa, cand[i][0], cand[i][1], p->nbins, p->weighted);
                 if (s <= (pass == 0 ? 100u * 1024u : 220u * 1024u)) { chosen = (int) i; smem = s; break; }
             }
         if (chosen < 0) { gkm_set_error("sequence too long for shared memory"); return 1; }
@@ -253,6 +254,7 @@ static void fill_kparams(const gkmb200_problem *p, const gkm_image *im, gkm_kpar
     kp->wend = im->wend;
     kp->sqnorm = im->sqnorm;
     kp->W = p->Wmax;
+    kp->WA = p->Wa;
     kp->L = p->param.L;
     kp->d = p->param.d;
     kp->nbins = p->nbins;
@@ -298,16 +300,16 @@ static int upload_locked(gkmb200_problem *p)
         gkm_gpu *g = &g_gpu[g_sel[i]];
         if (gpu_prepare(g, g_sel[i], 0, 0)) return 1;
         gkm_image *im = &ds->img[i];
-        CK(cudaMalloc(&im->planes, n * 4 * W * sizeof(uint32_t)));
+        CK(cudaMalloc(&im->planes, n * 3 * W * sizeof(uint32_t)));
         CK(cudaMalloc(&im->lens, n * sizeof(int32_t)));
         CK(cudaMalloc(&im->sqnorm, n * sizeof(double)));
-        CK(cudaMemcpyAsync(im->planes, p->planes, n * 4 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
+        CK(cudaMemcpyAsync(im->planes, p->planes, n * 3 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
         CK(cudaMemcpyAsync(im->lens, p->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->sc));
-        h2d += (long long) (n * 4 * W * sizeof(uint32_t) + n * sizeof(int32_t));
+        h2d += (long long) (n * 3 * W * sizeof(uint32_t) + n * sizeof(int32_t));
         if (p->weighted) {
-            CK(cudaMalloc(&im->wend, n * 64 * W));
-            CK(cudaMemcpyAsync(im->wend, p->wend, n * 64 * W, cudaMemcpyHostToDevice, g->sc));
-            h2d += (long long) (n * 64 * W);
+            CK(cudaMalloc(&im->wend, n * 32 * W));
+            CK(cudaMemcpyAsync(im->wend, p->wend, n * 32 * W, cudaMemcpyHostToDevice, g->sc));
+            h2d += (long long) (n * 32 * W);
         }
         /* sqnorm: Kraw(a,a) by the same kernel in diagonal mode, in blocks of 1024 rows */
         gkm_kparams kp;
@@ -738,6 +740,15 @@ __global__ void __launch_bounds__(256) gkm_mb_kernel(uint32_t *out, int iters, u
                 if (OP == 2) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
                 if (OP == 3) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y));
                 if (OP == 4) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z));
+                if (OP == 5) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z));
+                /* mixes: do the pipes run side by side?  (ops counted: all of them) */
+                if (OP == 6) { if (i & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y), "r"(z));
+                               else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z)); }
+                if (OP == 7) { if (i & 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y), "r"(z));
+                               else asm volatile("popc.b32 %0, %0;" : "+r"(x[i])); }
+                if (OP == 8) { if (i == 0) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));
+                               else if (i < 5) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y), "r"(z));
+                               else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y), "r"(z)); }
             }
         }
     }
@@ -771,6 +782,10 @@ extern "C" int gkm_dev_microbench(const char *what, double *result)
                 else if (!strcmp(what, "popc")) gkm_mb_kernel<2><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
                 else if (!strcmp(what, "iadd3")) gkm_mb_kernel<3><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
                 else if (!strcmp(what, "imad")) gkm_mb_kernel<4><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "imadhi")) gkm_mb_kernel<5><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "lop3+imad")) gkm_mb_kernel<6><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "lop3+popc")) gkm_mb_kernel<7><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
+                else if (!strcmp(what, "lop3+imad+popc")) gkm_mb_kernel<8><<<blocks, 256, 0, g->sc>>>(d, iters, 12345u + rep);
                 else { gkm_set_error("unknown microbench %s", what); rc = 1; break; }
                 cudaEventRecord(e1, g->sc);
                 if (cudaEventSynchronize(e1) != cudaSuccess) { gkm_set_error("CUDA: microbench failed"); rc = 1; break; }

@@ -1,6 +1,6 @@
 /* gkm_diag_inst.cu -- instantiates the bit-sliced kernel for ONE word length.
  * Compiled once per L = 2..16 with -DGKM_INST_L=<L> (see Makefile) so that the
- * 90 specialisations (15 L x {4,8,16} bins x {plain, weighted}) build in parallel. */
+ * specialisations (15 L x {4,8,16} bins x {plain, weighted}) build in parallel. */
 #include "gkm_diag_kernel.cuh"
 
 #ifndef GKM_INST_L
@@ -10,11 +10,35 @@
 #define GKM_CAT2(a, b) a##b
 #define GKM_CAT(a, b) GKM_CAT2(a, b)
 
-extern "C" const void *GKM_CAT(gkm_diag_fn_L, GKM_INST_L)(int nb, int weighted)
+#ifndef GKM_DIAG_DEFAULT_FLAVOR
+#define GKM_DIAG_DEFAULT_FLAVOR 0
+#endif
+
+template <int L, int F>
+static const void *pick(int nb, int weighted)
+{
+    constexpr int FW = F & ~GKM_F_RARE_BINS; /* the rare-bin path exists for the plain 4-bin kernel only */
+    if (nb == 4) return weighted ? (const void *) gkm_diag_kernel<L, 4, true, FW> : (const void *) gkm_diag_kernel<L, 4, false, F>;
+    if (nb == 8) return weighted ? (const void *) gkm_diag_kernel<L, 8, true, FW> : (const void *) gkm_diag_kernel<L, 8, false, FW>;
+    if (nb == 16) return weighted ? (const void *) gkm_diag_kernel<L, 16, true, FW> : (const void *) gkm_diag_kernel<L, 16, false, FW>;
+    return nullptr;
+}
+
+/* flavor < 0: the default for this build.  Other flavors exist only where GKM_INST_FLAVORS is set
+ * (the benchmark word length), for A/B measurements on the device. */
+extern "C" const void *GKM_CAT(gkm_diag_fn_L, GKM_INST_L)(int nb, int weighted, int flavor)
 {
     constexpr int L = GKM_INST_L;
-    if (nb == 4) return weighted ? (const void *) gkm_diag_kernel<L, 4, true> : (const void *) gkm_diag_kernel<L, 4, false>;
-    if (nb == 8) return weighted ? (const void *) gkm_diag_kernel<L, 8, true> : (const void *) gkm_diag_kernel<L, 8, false>;
-    if (nb == 16) return weighted ? (const void *) gkm_diag_kernel<L, 16, true> : (const void *) gkm_diag_kernel<L, 16, false>;
-    return nullptr;
+#ifdef GKM_INST_FLAVORS
+    if (flavor >= 0 && nb == 4 && !weighted) {
+        switch (flavor & 6) {
+            case 0: return (const void *) gkm_diag_kernel<L, 4, false, 0>;
+            case 2: return (const void *) gkm_diag_kernel<L, 4, false, 2>;
+            case 4: return (const void *) gkm_diag_kernel<L, 4, false, 4>;
+            case 6: return (const void *) gkm_diag_kernel<L, 4, false, 6>;
+        }
+    }
+#endif
+    (void) flavor;
+    return pick<L, GKM_DIAG_DEFAULT_FLAVOR>(nb, weighted);
 }

@@ -5,13 +5,15 @@
  * TA x TB tile of (query, target) sequence pairs per CTA.
  *
  * CTA = 256 threads.  Shared memory holds, for the tile,
- *   sA    [TA][32W]  gkm_apos   query records (broadcast-read, one LDS.128 per step)
- *   sS    [TB][2 strands][2 planes][W] target bit planes, sE [TB][W] valid-window-end plane
- *   sW    [TB][2][32W] bytes    target weights by window end (weighted types)
- *   sTask [<= TB*2*W]           lane tasks (target, strand, block of 32 diagonals)
- *   sH    [TA][TB][NB] int32    the tile's histograms
- * A warp takes (query, group of 32 tasks) combos round-robin; every lane runs
- * gkm_diag_lane over the whole query, then adds its NB counters into sH with shared
+ *   sAp   [TA/2][32WA] gkm_apos2   records of query PAIRS (one broadcast LDS.128 per step)
+ *   sAx   [TA/2][32WA] gkm_aaux2   validity / weight words of the pairs (read by the edge chunks
+ *                                   and by the weighted kernel types only)
+ *   sS    [TB][3][W]   target bit planes of the circular both-strand string + valid-window-end plane
+ *   sW    [TB][32W] bytes          target weights by window end (weighted types)
+ *   sTask [<= TB*W]                lane tasks (target, block of 32 diagonals)
+ *   sH    [TA][TB][NB] int32       the tile's histograms
+ * A warp takes (query pair, group of 32 tasks) combos round-robin; every lane runs
+ * gkm_diag_lane over the two queries, then adds its 2*NB counters into sH with shared
  * atomics (a few per ~10^4 instructions).  The epilogue turns each histogram into
  * the normalised double exactly like the reference does: ascending-m sum from 0.0,
  * one division by sqnorm_a*sqnorm_b, no FMA contraction (libgkm.c:576-582,:1169-1179).
@@ -26,21 +28,23 @@
 #define GKM_DIAG_THREADS 256
 
 struct gkm_diag_layout_t {
-    unsigned offA, offS, offE, offZ, offW, offTask, offH, offLenA, offLenB, offPre, total;
+    unsigned offA, offX, offS, offZ, offW, offTask, offH, offLenA, offLenB, offPre, total;
 };
 
-__host__ __device__ inline gkm_diag_layout_t gkm_diag_layout(int W, int TA, int TB, int NB, int weighted)
+/* W = words per target plane (both strands), WA = 32-position chunks of the longest query, TA even */
+__host__ __device__ inline gkm_diag_layout_t gkm_diag_layout(int W, int WA, int TA, int TB, int NB, int weighted)
 {
     gkm_diag_layout_t l;
+    const unsigned npair = (unsigned) (TA + 1) / 2u;
     unsigned o = 0;
-    l.offA = o;    o += (unsigned) TA * 32u * (unsigned) W * 16u;
-    l.offS = o;    o += (unsigned) TB * 4u * (unsigned) W * 4u;
-    l.offE = o;    o += (unsigned) TB * (unsigned) W * 4u;
+    l.offA = o;    o += npair * 32u * (unsigned) WA * 16u;
+    l.offX = o;    o += npair * 32u * (unsigned) WA * 16u;
+    l.offS = o;    o += (unsigned) TB * 3u * (unsigned) W * 4u;
     l.offZ = o;    o += (unsigned) W * 4u;
-    l.offW = o;    o += weighted ? (unsigned) TB * 2u * 32u * (unsigned) W : 0u;
-    l.offTask = o; o += (unsigned) TB * 2u * (unsigned) W * 4u;
-    l.offH = o;    o += (unsigned) TA * (unsigned) TB * (unsigned) NB * 4u;
-    l.offLenA = o; o += (unsigned) TA * 4u;
+    l.offW = o;    o += weighted ? (unsigned) TB * 32u * (unsigned) W : 0u;
+    l.offTask = o; o += (unsigned) TB * (unsigned) W * 4u;
+    l.offH = o;    o += 2u * npair * (unsigned) TB * (unsigned) NB * 4u;
+    l.offLenA = o; o += 2u * npair * 4u;
     l.offLenB = o; o += (unsigned) TB * 4u;
     l.offPre = o;  o += ((unsigned) TB + 1u) * 4u;
     l.total = (o + 15u) & ~15u;
@@ -73,16 +77,17 @@ __device__ __forceinline__ void gkm_emit_entry(const gkm_kparams &p, int a_g, in
     if (p.decision) atomicAdd(p.decision + (a_g - p.row_base), p.alpha[b_g - p.col_base] * v);
 }
 
-template <int L, int NB, bool WEIGHTED>
+template <int L, int NB, bool WEIGHTED, int FLAVOR>
 __global__ void __launch_bounds__(GKM_DIAG_THREADS)
 gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int W = p.W, TA = p.TA, TB = p.TB;
-    const gkm_diag_layout_t lay = gkm_diag_layout(W, TA, TB, NB, WEIGHTED ? 1 : 0);
-    gkm_apos *sA = reinterpret_cast<gkm_apos *>(smem + lay.offA);
+    const int W = p.W, WA = p.WA, TA = p.TA, TB = p.TB;
+    const int NPAIR = (TA + 1) >> 1;
+    const gkm_diag_layout_t lay = gkm_diag_layout(W, WA, TA, TB, NB, WEIGHTED ? 1 : 0);
+    gkm_apos2 *sAp = reinterpret_cast<gkm_apos2 *>(smem + lay.offA);
+    gkm_aaux2 *sAx = reinterpret_cast<gkm_aaux2 *>(smem + lay.offX);
     uint32_t *sS = reinterpret_cast<uint32_t *>(smem + lay.offS);
-    uint32_t *sE = reinterpret_cast<uint32_t *>(smem + lay.offE);
     uint32_t *sZ = reinterpret_cast<uint32_t *>(smem + lay.offZ);
     uint8_t *sW = smem + lay.offW;
     uint32_t *sTask = reinterpret_cast<uint32_t *>(smem + lay.offTask);
@@ -100,16 +105,16 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
     if (p.mode == GKM_MODE_DIAG && (col0 > row_last || col_last < row0)) return;
 
     /* ---- stage the tile ---- */
-    if (tid < TA) sLenA[tid] = (row0 + tid < p.row_end) ? p.lens[row0 + tid] : 0;
+    if (tid < 2 * NPAIR) sLenA[tid] = (tid < TA && row0 + tid < p.row_end) ? p.lens[row0 + tid] : 0;
     if (tid < TB) sLenB[tid] = (col0 + tid < p.col_end) ? p.lens[col0 + tid] : 0;
     for (int i = tid; i < W; i += GKM_DIAG_THREADS) sZ[i] = 0u;
-    for (int i = tid; i < TA * TB * NB; i += GKM_DIAG_THREADS) sH[i] = 0;
-    for (int i = tid; i < TB * 4 * W; i += GKM_DIAG_THREADS) {
-        const int b = i / (4 * W);
-        sS[i] = (col0 + b < p.col_end) ? p.planes[(size_t) (col0 + b) * 4 * W + (i - b * 4 * W)] : 0u;
+    for (int i = tid; i < 2 * NPAIR * TB * NB; i += GKM_DIAG_THREADS) sH[i] = 0;
+    for (int i = tid; i < TB * 3 * W; i += GKM_DIAG_THREADS) {
+        const int b = i / (3 * W);
+        sS[i] = (col0 + b < p.col_end) ? p.planes[(size_t) (col0 + b) * 3 * W + (i - b * 3 * W)] : 0u;
     }
     if (WEIGHTED) {
-        const int wordsPerB = 16 * W; /* 2 strands * 32W bytes */
+        const int wordsPerB = 8 * W; /* 32W bytes */
         const uint32_t *src = reinterpret_cast<const uint32_t *>(p.wend);
         uint32_t *dst = reinterpret_cast<uint32_t *>(sW);
         for (int i = tid; i < TB * wordsPerB; i += GKM_DIAG_THREADS) {
@@ -118,32 +123,27 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
         }
     }
     __syncthreads();
-    /* valid-window-end plane of each target: bits L-1 .. len-1 */
-    for (int i = tid; i < TB * W; i += GKM_DIAG_THREADS) {
-        const int b = i / W, wi = i - b * W;
-        const int lo = max(L - 1, 32 * wi) - 32 * wi, hi = min(sLenB[b], 32 * wi + 32) - 32 * wi;
-        uint32_t m = 0u;
-        if (hi > lo) m = ((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-        sE[i] = m;
-    }
-    /* query records */
-    for (int i = tid; i < TA * 32 * W; i += GKM_DIAG_THREADS) {
-        const int a = i / (32 * W), e = i - a * 32 * W;
-        gkm_apos r;
-        r.a0 = 0u; r.a1 = 0u; r.va = 0u; r.wa = 1u;
-        if (row0 + a < p.row_end) {
-            const uint32_t *pl = p.planes + (size_t) (row0 + a) * 4 * W;
-            r.a0 = ((pl[e >> 5] >> (e & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
-            r.a1 = ((pl[W + (e >> 5)] >> (e & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
-            r.va = (e >= L - 1 && e < sLenA[a]) ? 0xFFFFFFFFu : 0u;
-            if (WEIGHTED) r.wa = p.wend[(size_t) (row0 + a) * 64 * W + e];
+    /* query records, two queries interleaved: the forward strand is the first len bits of the circular string */
+    for (int i = tid; i < 2 * NPAIR * 32 * WA; i += GKM_DIAG_THREADS) {
+        const int a = i / (32 * WA), e = i - a * 32 * WA;
+        const int pi = a >> 1, qi = a & 1;
+        uint32_t a0 = 0u, a1 = 0u, va = 0u, wa = 1u;
+        if (e < sLenA[a]) {
+            const uint32_t *pl = p.planes + (size_t) (row0 + a) * 3 * W;
+            a0 = ((pl[e >> 5] >> (e & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
+            a1 = ((pl[W + (e >> 5)] >> (e & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
+            va = (e >= L - 1) ? 0xFFFFFFFFu : 0u;
+            if (WEIGHTED) wa = p.wend[(size_t) (row0 + a) * 32 * W + e];
         }
-        sA[i] = r;
+        gkm_apos2 *rp = sAp + (size_t) pi * 32 * WA + e;
+        gkm_aaux2 *rx = sAx + (size_t) pi * 32 * WA + e;
+        rp->a0[qi] = a0; rp->a1[qi] = a1;
+        rx->va[qi] = va; rx->wa[qi] = wa;
     }
-    /* lane tasks: target b contributes 2 strands x ceil(len_b/32) blocks of 32 diagonals */
+    /* lane tasks: target b contributes ceil(2*len_b/32) blocks of 32 diagonals */
     if (tid == 0) {
         int acc = 0;
-        for (int b = 0; b < TB; b++) { sPre[b] = acc; acc += 2 * ((sLenB[b] + 31) >> 5); }
+        for (int b = 0; b < TB; b++) { sPre[b] = acc; acc += (2 * sLenB[b] + 31) >> 5; }
         sPre[TB] = acc;
     }
     __syncthreads();
@@ -151,45 +151,48 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
     for (int t = tid; t < ntasks; t += GKM_DIAG_THREADS) {
         int b = 0;
         while (sPre[b + 1] <= t) b++;
-        const int wb = (sLenB[b] + 31) >> 5;
-        const int r = t - sPre[b];
-        const int strand = r / wb, q = r - strand * wb;
-        sTask[t] = ((uint32_t) b << 16) | ((uint32_t) strand << 15) | (uint32_t) q;
+        sTask[t] = ((uint32_t) b << 16) | (uint32_t) (t - sPre[b]);
     }
     __syncthreads();
 
-    /* ---- main loop: (query, task group) combos ---- */
+    /* ---- main loop: (query pair, task group) combos ---- */
     const int lane = tid & 31, warp = tid >> 5;
     const int ngroups = (ntasks + 31) >> 5;
-    const int ncombos = TA * ngroups;
+    const int ncombos = NPAIR * ngroups;
     for (int combo = warp; combo < ncombos; combo += GKM_DIAG_THREADS / 32) {
-        const int a_l = combo / ngroups, g = combo - a_l * ngroups;
-        const int a_g = row0 + a_l;
-        if (a_g >= p.row_end) break;
+        const int pi = combo / ngroups, g = combo - pi * ngroups;
+        const int a0_g = row0 + 2 * pi;
+        const int len0 = sLenA[2 * pi], len1 = sLenA[2 * pi + 1];
+        if (len0 == 0) break;                                     /* past the last row of the block */
+        const int a_hi = (len1 > 0) ? a0_g + 1 : a0_g;            /* largest valid row of the pair */
         const int t = 32 * g + lane;
         bool active = t < ntasks;
         const uint32_t task = active ? sTask[t] : 0u;
-        const int b_l = (int) (task >> 16), strand = (int) ((task >> 15) & 1u), q = (int) (task & 0x7FFFu);
+        const int b_l = (int) (task >> 16), q = (int) (task & 0xFFFFu);
         const int b_g = col0 + b_l;
-        if (p.mode == GKM_MODE_LOWER) active = active && (b_g < a_g);
-        if (p.mode == GKM_MODE_DIAG) active = active && (b_g == a_g);
+        if (p.mode == GKM_MODE_LOWER) active = active && (b_g < a_hi);
+        if (p.mode == GKM_MODE_DIAG) active = active && (b_g == a0_g || (len1 > 0 && b_g == a0_g + 1));
         if (!__any_sync(0xFFFFFFFFu, active)) continue;
 
-        const uint32_t *S0 = sS + ((b_l * 2 + strand) * 2 + 0) * W;
-        const uint32_t *S1 = sS + ((b_l * 2 + strand) * 2 + 1) * W;
-        const uint32_t *E = active ? (sE + b_l * W) : sZ;
-        const int Wb = active ? ((sLenB[b_l] + 31) >> 5) : 1;
-        const uint8_t *wendp = WEIGHTED ? (sW + (size_t) (b_l * 2 + strand) * 32 * W) : nullptr;
+        const uint32_t *C0 = sS + (b_l * 3 + 0) * W;
+        const uint32_t *C1 = sS + (b_l * 3 + 1) * W;
+        const uint32_t *E = active ? (sS + (b_l * 3 + 2) * W) : sZ;
+        const int Wc = active ? ((2 * sLenB[b_l] + 31) >> 5) : 1;
+        const uint8_t *wendp = WEIGHTED ? (sW + (size_t) b_l * 32 * W) : nullptr;
 
-        int32_t acc[NB];
+        int32_t acc0[NB], acc1[NB];
 #pragma unroll
-        for (int m = 0; m < NB; m++) acc[m] = 0;
-        gkm_diag_lane<L, NB, WEIGHTED>(sA + (size_t) a_l * 32 * W, sLenA[a_l], S0, S1, E, Wb, active ? q : 0, wendp, acc);
+        for (int m = 0; m < NB; m++) { acc0[m] = 0; acc1[m] = 0; }
+        gkm_diag_lane<L, NB, WEIGHTED, FLAVOR>(sAp + (size_t) pi * 32 * WA, sAx + (size_t) pi * 32 * WA, len0, len1,
+                                               C0, C1, E, Wc, active ? q : 0, wendp, acc0, acc1);
         if (active) {
-            int32_t *h = sH + (a_l * TB + b_l) * NB;
+            int32_t *h0 = sH + ((2 * pi) * TB + b_l) * NB;
+            int32_t *h1 = sH + ((2 * pi + 1) * TB + b_l) * NB;
 #pragma unroll
-            for (int m = 0; m < NB; m++)
-                if (acc[m]) atomicAdd(h + m, acc[m]);
+            for (int m = 0; m < NB; m++) {
+                if (acc0[m]) atomicAdd(h0 + m, acc0[m]);
+                if (acc1[m]) atomicAdd(h1 + m, acc1[m]);
+            }
         }
     }
     __syncthreads();

@@ -43,9 +43,10 @@ struct gkmb200_problem {
 
     /* packed image (gkm_pack_problem) */
     int packed;
-    int Wmax;        /* 32-bit words per bit plane = ceil(maxlen / 32) */
-    uint32_t *planes;/* [n][4][Wmax]: fwd bit0, fwd bit1, rc bit0, rc bit1 */
-    uint8_t *wend;   /* weighted only: [n][2][32*Wmax] weight by window END position */
+    int Wmax;        /* 32-bit words per bit plane = ceil(2*maxlen / 32): both strands in one circular string */
+    int Wa;          /* ceil(maxlen / 32): 32-position chunks of a query */
+    uint32_t *planes;/* [n][3][Wmax]: code bit 0, code bit 1, valid-window-end plane E */
+    uint8_t *wend;   /* weighted only: [n][32*Wmax] weight by window END position */
     double *sqnorm;  /* [n], filled by the device */
     int have_sqnorm;
 

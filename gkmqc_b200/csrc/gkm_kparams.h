@@ -8,9 +8,9 @@ enum { GKM_MODE_RECT = 0, GKM_MODE_LOWER = 1, GKM_MODE_DIAG = 2 };
 
 struct gkm_kparams {
     /* device-resident problem image (gkm_seq.c: gkm_pack_problem) */
-    const uint32_t *planes; /* [n][4][W] */
+    const uint32_t *planes; /* [n][3][W]: code bit 0, code bit 1, valid-window-end plane; both strands, circular */
     const int32_t *lens;    /* [n] */
-    const uint8_t *wend;    /* [n][2][32W], weighted kernel types only */
+    const uint8_t *wend;    /* [n][32W], weighted kernel types only */
     const double *sqnorm;   /* [n] */
     /* outputs (any may be null) */
     double *out;            /* out[(row-row_base)*ld + (col-col_base)] = K(row,col) */
@@ -25,7 +25,8 @@ struct gkm_kparams {
     int row_base, col_base;
     int mode;
     /* shapes */
-    int W;      /* words per bit plane */
+    int W;      /* words per bit plane (2*maxlen bits) */
+    int WA;     /* 32-position chunks of the longest query */
     int TA, TB; /* query rows / target columns per CTA */
     int L, d, nbins, kernel_type;
     double gamma;

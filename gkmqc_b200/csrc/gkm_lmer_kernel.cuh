@@ -9,6 +9,8 @@
  *
  * L-mer word: bits 0..L-1 = low code bit of the L bases, bits 16..16+L-1 = high
  * code bit.  mismatches(x,y) = popc(((x^y) | (x^y)>>16) & 0xFFFF).
+ * Words are cut out of the same circular both-strand bit planes the diag kernel
+ * reads: forward L-mer j starts at bit j, reverse-complement L-mer j at bit len+j.
  *
  * CTA = 256 threads, tile TA x TB sequence pairs.  A warp owns one (a,b) pair at a
  * time: lanes stride over the 2*nk_b target L-mers (both strands) holding 4 of them
@@ -23,9 +25,10 @@
 #define GKM_LMER_THREADS 256
 #define GKM_LMER_RJ 4
 
-__host__ __device__ inline unsigned gkm_lmer_smem_bytes(int W, int TA, int TB, int nbins, int weighted)
+/* WA = 32-position chunks of the longest sequence: at most 32*WA L-mers per strand */
+__host__ __device__ inline unsigned gkm_lmer_smem_bytes(int WA, int TA, int TB, int nbins, int weighted)
 {
-    unsigned nk = 32u * (unsigned) W;
+    unsigned nk = 32u * (unsigned) WA;
     unsigned o = ((unsigned) TA + 2u * (unsigned) TB) * nk * 4u;     /* L-mer words */
     if (weighted) o += ((unsigned) TA + 2u * (unsigned) TB) * nk;    /* weights by L-mer start */
     o += (unsigned) TA * (unsigned) TB * (unsigned) nbins * 4u;      /* histograms */
@@ -33,9 +36,10 @@ __host__ __device__ inline unsigned gkm_lmer_smem_bytes(int W, int TA, int TB, i
     return (o + 15u) & ~15u;
 }
 
-__device__ __forceinline__ uint32_t gkm_lmer_word(const uint32_t *pl0, const uint32_t *pl1, int W, int j, uint32_t maskL)
+/* L bases starting at bit position `o` of the circular string */
+__device__ __forceinline__ uint32_t gkm_lmer_word(const uint32_t *pl0, const uint32_t *pl1, int W, int o, uint32_t maskL)
 {
-    const int wi = j >> 5, sh = j & 31;
+    const int wi = o >> 5, sh = o & 31;
     const uint32_t n0 = (wi + 1 < W) ? pl0[wi + 1] : 0u, n1 = (wi + 1 < W) ? pl1[wi + 1] : 0u;
     const uint32_t p0 = __funnelshift_r(pl0[wi], n0, sh) & maskL;
     const uint32_t p1 = __funnelshift_r(pl1[wi], n1, sh) & maskL;
@@ -48,7 +52,7 @@ gkm_lmer_kernel(const __grid_constant__ gkm_kparams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int W = p.W, TA = p.TA, TB = p.TB, L = p.L, d = p.d, NBN = p.nbins;
-    const int NK = 32 * W;
+    const int NK = 32 * p.WA;
     uint32_t *sIdA = reinterpret_cast<uint32_t *>(smem);           /* [TA][NK] */
     uint32_t *sIdB = sIdA + (size_t) TA * NK;                       /* [TB][2][NK] */
     uint8_t *sWtA = reinterpret_cast<uint8_t *>(sIdB + (size_t) TB * 2 * NK);
@@ -76,9 +80,9 @@ gkm_lmer_kernel(const __grid_constant__ gkm_kparams p)
         const int a = i / NK, j = i - a * NK;
         uint32_t v = 0u; uint8_t wt = 0;
         if (j + L <= sLenA[a]) {
-            const uint32_t *pl = p.planes + (size_t) (row0 + a) * 4 * W;
+            const uint32_t *pl = p.planes + (size_t) (row0 + a) * 3 * W;
             v = gkm_lmer_word(pl, pl + W, W, j, maskL);
-            if (WEIGHTED) wt = p.wend[(size_t) (row0 + a) * 64 * W + j + L - 1];
+            if (WEIGHTED) wt = p.wend[(size_t) (row0 + a) * 32 * W + j + L - 1];
         }
         sIdA[i] = v;
         if (WEIGHTED) sWtA[i] = wt;
@@ -88,9 +92,10 @@ gkm_lmer_kernel(const __grid_constant__ gkm_kparams p)
         const int b = i / (2 * NK), r = i - b * 2 * NK, strand = r / NK, j = r - strand * NK;
         uint32_t v = 0u; uint8_t wt = 0;
         if (j + L <= sLenB[b]) {
-            const uint32_t *pl = p.planes + (size_t) (col0 + b) * 4 * W + (size_t) (2 * strand) * W;
-            v = gkm_lmer_word(pl, pl + W, W, j, maskL);
-            if (WEIGHTED) wt = p.wend[((size_t) (col0 + b) * 2 + strand) * 32 * W + j + L - 1];
+            const uint32_t *pl = p.planes + (size_t) (col0 + b) * 3 * W;
+            const int o = strand * sLenB[b] + j;
+            v = gkm_lmer_word(pl, pl + W, W, o, maskL);
+            if (WEIGHTED) wt = p.wend[(size_t) (col0 + b) * 32 * W + o + L - 1];
         }
         sIdB[i] = v;
         if (WEIGHTED) sWtB[i] = wt;

@@ -17,6 +17,7 @@ static int g_kernel = GKM_KERNEL_AUTO;
 static int g_max_L = 12;
 static int g_chunk_mb = 64;
 static int g_tile_rows = 0;
+static int g_diag_flavor = -1;
 
 static int parse_kernel(const char *v, int *out)
 {
@@ -35,6 +36,7 @@ static void load_env(void)
     if ((v = getenv("GKM_KERNEL")) != NULL) parse_kernel(v, &g_kernel);
     if ((v = getenv("GKM_MAX_L")) != NULL) { int x = atoi(v); if (x == 12 || x == 16) g_max_L = x; }
     if ((v = getenv("GKM_CHUNK_MB")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 4096) g_chunk_mb = x; }
+    if ((v = getenv("GKM_DIAG_FLAVOR")) != NULL) { int x = atoi(v); if (x >= -1 && x <= 7) g_diag_flavor = x; }
     if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
 }
 
@@ -42,6 +44,7 @@ int gkm_opt_kernel(void) { load_env(); return g_kernel; }
 int gkm_opt_max_L(void) { load_env(); return g_max_L; }
 int gkm_opt_chunk_mb(void) { load_env(); return g_chunk_mb; }
 int gkm_opt_tile_rows(void) { load_env(); return g_tile_rows; }
+int gkm_opt_diag_flavor(void) { load_env(); return g_diag_flavor; }
 
 int gkmb200_set_option(const char *key, const char *value)
 {
@@ -60,6 +63,11 @@ int gkmb200_set_option(const char *key, const char *value)
     if (!strcmp(key, "chunk_mb")) {
         if (x < 1 || x > 4096) { gkm_set_error("chunk_mb out of range"); return 1; }
         g_chunk_mb = x;
+        return 0;
+    }
+    if (!strcmp(key, "diag_flavor")) { /* A/B switch for the pipe-balancing variants of the diag kernel */
+        if (x < -1 || x > 7) { gkm_set_error("diag_flavor out of range"); return 1; }
+        g_diag_flavor = x;
         return 0;
     }
     if (!strcmp(key, "tile_rows")) {

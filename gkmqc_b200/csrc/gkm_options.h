@@ -8,6 +8,7 @@ int gkm_opt_kernel(void);
 int gkm_opt_max_L(void);
 int gkm_opt_chunk_mb(void);
 int gkm_opt_tile_rows(void);
+int gkm_opt_diag_flavor(void);
 #ifdef __cplusplus
 }
 #endif

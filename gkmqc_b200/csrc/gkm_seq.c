@@ -208,7 +208,11 @@ void gkm_unpack_problem(gkmb200_problem *p)
     p->have_sqnorm = 0;
 }
 
-/* build the device image on the host */
+/* build the device image on the host.
+ * Per sequence one circular string of 32*Wc positions: forward strand at [0,len), reverse
+ * complement at [len,2len), zero padding behind.  planes[i][0..1][Wc] = the two code bit planes,
+ * planes[i][2][Wc] = E, the positions at which an L-mer of either strand may END
+ * (L-1 <= j < len and len+L-1 <= j < 2len).  wend[i][32*Wc] = weight of the L-mer ending at j. */
 int gkm_pack_problem(gkmb200_problem *p)
 {
     if (p->packed) return 0;
@@ -216,11 +220,12 @@ int gkm_pack_problem(gkmb200_problem *p)
     const int L = p->param.L;
     int maxlen = 0;
     for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
-    const int W = (maxlen + 31) / 32;
+    const int W = (2 * maxlen + 31) / 32;
     p->Wmax = W;
-    p->planes = (uint32_t *) calloc((size_t) p->n * 4 * (size_t) W, sizeof(uint32_t));
+    p->Wa = (maxlen + 31) / 32;
+    p->planes = (uint32_t *) calloc((size_t) p->n * 3 * (size_t) W, sizeof(uint32_t));
     p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
-    if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 2 * 32 * (size_t) W, 1);
+    if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 32 * (size_t) W, 1);
     if (!p->planes || !p->sqnorm || (p->weighted && !p->wend)) {
         gkm_unpack_problem(p);
         gkm_set_error("out of memory packing %d sequences", p->n);
@@ -230,24 +235,23 @@ int gkm_pack_problem(gkmb200_problem *p)
     for (int i = 0; i < p->n; i++) {
         const int n = p->len[i];
         const uint8_t *c = p->code[i];
-        uint32_t *pl = p->planes + (size_t) i * 4 * (size_t) W;
-        for (int pos = 0; pos < n; pos++) {
-            const uint32_t f = c[pos];
-            const uint32_t r = 3u - c[n - 1 - pos]; /* complement of the mirrored base */
+        uint32_t *pl = p->planes + (size_t) i * 3 * (size_t) W;
+        for (int pos = 0; pos < 2 * n; pos++) {
+            /* second half: complement of the mirrored base (libgkm.c:878-888) */
+            const uint32_t code = (pos < n) ? c[pos] : 3u - c[2 * n - 1 - pos];
             const uint32_t bit = 1u << (pos & 31);
             const int wi = pos >> 5;
-            if (f & 1u) pl[0 * W + wi] |= bit;
-            if (f & 2u) pl[1 * W + wi] |= bit;
-            if (r & 1u) pl[2 * W + wi] |= bit;
-            if (r & 2u) pl[3 * W + wi] |= bit;
+            if (code & 1u) pl[0 * W + wi] |= bit;
+            if (code & 2u) pl[1 * W + wi] |= bit;
+            if ((pos < n ? pos : pos - n) >= L - 1) pl[2 * W + wi] |= bit;
         }
         if (p->weighted) {
             const int nk = n - L + 1;
             gkm_calc_posweights(nk, p->param.kernel_type, p->param.M, p->param.H, wt, wt_rc);
-            uint8_t *we = p->wend + (size_t) i * 2 * 32 * (size_t) W;
+            uint8_t *we = p->wend + (size_t) i * 32 * (size_t) W;
             for (int s = 0; s < nk; s++) {
                 we[s + L - 1] = wt[s];
-                we[32 * W + s + L - 1] = wt_rc[s];
+                we[n + s + L - 1] = wt_rc[s];
             }
         }
     }
