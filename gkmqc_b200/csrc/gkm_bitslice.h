@@ -55,7 +55,7 @@
 #define GKM_HDM inline
 #endif
 
-enum { GKM_F_RARE_BINS = 2, GKM_F_IMAD_ACC = 4 };
+enum { GKM_F_ONE_BODY = 1, GKM_F_RARE_BINS = 2, GKM_F_IMAD_ACC = 4 };
 
 #if defined(__CUDACC__)
 /* the constant 1 behind a constant-bank load, so that ptxas keeps IMAD for the accumulation */
@@ -120,9 +120,13 @@ template <> struct gkm_log2nb<8> { static constexpr int v = 3; };
 template <> struct gkm_log2nb<16> { static constexpr int v = 4; };
 
 /* ---- per-lane, per-query sliding state ---- */
-template <int L>
+/* INV = index of a plane that is stored COMPLEMENTED (-1: none).  The rare-bin test needs
+ * hit & ~p1; with plane 1 kept inverted that is a plain AND and every other use absorbs the
+ * complement into its LOP3 truth table for free. */
+template <int L, int INV = -1>
 struct gkm_win_state {
     static constexpr int NP = gkm_nplanes(L);
+    static constexpr int INVP = INV;
     uint32_t m[16];  /* ring of the last 16 mismatch words */
     uint32_t p[NP];  /* bit-sliced count of mismatches in the current L-window */
     GKM_HDM void clear()
@@ -130,61 +134,59 @@ struct gkm_win_state {
 #pragma unroll
         for (int i = 0; i < 16; i++) m[i] = 0u;
 #pragma unroll
-        for (int i = 0; i < NP; i++) p[i] = 0u;
+        for (int i = 0; i < NP; i++) p[i] = (i == INV) ? 0xFFFFFFFFu : 0u;
     }
+    GKM_HDM uint32_t plane(int i) const { return i < NP ? (i == INV ? ~p[i] : p[i]) : 0u; }
 };
 
 /* push mismatch word `mm` of step S (compile-time ring slot): cnt += mm - mm[e-L] */
-template <int L, int S>
-GKM_HD void gkm_win_push(gkm_win_state<L> &st, uint32_t mm)
+template <int L, int INV, int S>
+GKM_HD void gkm_win_push(gkm_win_state<L, INV> &st, uint32_t mm)
 {
-    constexpr int NP = gkm_win_state<L>::NP;
+    constexpr int NP = gkm_win_state<L, INV>::NP;
     const uint32_t down = st.m[(S - L) & 15]; /* the position leaving the window (read before the slot is reused) */
     st.m[S & 15] = mm;
     uint32_t c = mm ^ down;                   /* lanes whose count changes */
 #pragma unroll
     for (int i = 0; i < NP; i++) {
         const uint32_t t = st.p[i];
-        st.p[i] = t ^ c;
-        if (i + 1 < NP) c &= (t ^ down);      /* carry when counting up, borrow when counting down */
+        st.p[i] = t ^ c;                      /* same for a complemented plane: ~(x ^ c) = ~x ^ c */
+        if (i + 1 < NP) c &= ((i == INV ? ~t : t) ^ down); /* carry when counting up, borrow when counting down */
     }
 }
 
 /* bit lanes whose count is < NB, restricted to `valid` */
-template <int L, int LB>
-GKM_HD uint32_t gkm_hit_word(const gkm_win_state<L> &st, uint32_t valid)
+template <int L, int INV, int LB>
+GKM_HD uint32_t gkm_hit_word(const gkm_win_state<L, INV> &st, uint32_t valid)
 {
     uint32_t high = 0u;
 #pragma unroll
-    for (int i = LB; i < gkm_win_state<L>::NP; i++) high |= st.p[i];
+    for (int i = LB; i < gkm_win_state<L, INV>::NP; i++) high |= st.plane(i);
     return valid & ~high;
 }
 
-template <int L, int LB>
-GKM_HD uint32_t gkm_plane(const gkm_win_state<L> &st, int i) { return i < gkm_win_state<L>::NP ? st.p[i] : 0u; }
-
 /* mask of bit lanes (within hit) whose count equals V */
-template <int L, int LB, int V>
-GKM_HD uint32_t gkm_bin_mask(const gkm_win_state<L> &st, uint32_t hit)
+template <int L, int INV, int LB, int V>
+GKM_HD uint32_t gkm_bin_mask(const gkm_win_state<L, INV> &st, uint32_t hit)
 {
     uint32_t r = hit;
 #pragma unroll
-    for (int i = 0; i < LB; i++) r &= ((V >> i) & 1) ? gkm_plane<L, LB>(st, i) : ~gkm_plane<L, LB>(st, i);
+    for (int i = 0; i < LB; i++) r &= ((V >> i) & 1) ? st.plane(i) : ~st.plane(i);
     return r;
 }
 
-template <int L, int LB, int FLAVOR, int V0, int V1>
-GKM_HD void gkm_bins_popc(const gkm_win_state<L> &st, uint32_t hit, int32_t *acc)
+template <int L, int INV, int LB, int FLAVOR, int V0, int V1>
+GKM_HD void gkm_bins_popc(const gkm_win_state<L, INV> &st, uint32_t hit, int32_t *acc)
 {
     if constexpr (V0 < V1) {
-        if constexpr (V0 <= L) gkm_acc_add<FLAVOR>(acc[V0], gkm_popc(gkm_bin_mask<L, LB, V0>(st, hit)));
-        gkm_bins_popc<L, LB, FLAVOR, V0 + 1, V1>(st, hit, acc);
+        if constexpr (V0 <= L) gkm_acc_add<FLAVOR>(acc[V0], gkm_popc(gkm_bin_mask<L, INV, LB, V0>(st, hit)));
+        gkm_bins_popc<L, INV, LB, FLAVOR, V0 + 1, V1>(st, hit, acc);
     }
 }
 
 /* weighted bins: rare path, one (e, j) pair per set bit of `hit` */
-template <int L, int LB>
-GKM_HD void gkm_bins_weighted(const gkm_win_state<L> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
+template <int L, int INV, int LB>
+GKM_HD void gkm_bins_weighted(const gkm_win_state<L, INV> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
                               int jbase, int P, int32_t *acc)
 {
     while (hit) {
@@ -192,7 +194,7 @@ GKM_HD void gkm_bins_weighted(const gkm_win_state<L> &st, uint32_t hit, uint32_t
         hit &= hit - 1u;
         int v = 0;
 #pragma unroll
-        for (int i = 0; i < LB; i++) v |= (int) ((gkm_plane<L, LB>(st, i) >> bit) & 1u) << i;
+        for (int i = 0; i < LB; i++) v |= (int) ((st.plane(i) >> bit) & 1u) << i;
         int j = jbase + bit;
         while (j >= P) j -= P;
         const int w = (int) wa * (int) wend[j];
@@ -202,33 +204,37 @@ GKM_HD void gkm_bins_weighted(const gkm_win_state<L> &st, uint32_t hit, uint32_t
 }
 
 /* binning of one query at one step */
-template <int L, int NB, bool WEIGHTED, int FLAVOR>
-GKM_HD void gkm_bins(const gkm_win_state<L> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
+template <int L, int INV, int NB, bool WEIGHTED, int FLAVOR>
+GKM_HD void gkm_bins(const gkm_win_state<L, INV> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
                      int jbase, int P, int32_t *acc)
 {
     constexpr int LB = gkm_log2nb<NB>::v;
     if constexpr (WEIGHTED) {
-        if (hit) gkm_bins_weighted<L, LB>(st, hit, wa, wend, jbase, P, acc);
+        if (hit) gkm_bins_weighted<L, INV, LB>(st, hit, wa, wend, jbase, P, acc);
     } else if constexpr ((FLAVOR & GKM_F_RARE_BINS) != 0 && NB == 4) {
-        gkm_bins_popc<L, LB, FLAVOR, 2, 4>(st, hit, acc);   /* counts 2 and 3: ~99 % of all hits */
-        uint32_t rare = hit & ~gkm_plane<L, LB>(st, 1);      /* counts 0 and 1 */
+        gkm_bins_popc<L, INV, LB, FLAVOR, 2, 4>(st, hit, acc); /* counts 2 and 3: ~99 % of all hits */
+        uint32_t rare = hit & ~st.plane(1);                   /* counts 0 and 1 (plane 1 is stored inverted) */
         if (rare) {
             /* a loop, so that the compiler keeps this off the straight-line path (a real branch,
              * not predication): entered for ~1 % of the warp steps on random sequences */
             do {
                 const uint32_t low = rare & (0u - rare);
                 rare ^= low;
-                if (gkm_plane<L, LB>(st, 0) & low) acc[1] += 1; else acc[0] += 1;
+                if (st.plane(0) & low) acc[1] += 1; else acc[0] += 1;
             } while (rare);
         }
     } else {
-        gkm_bins_popc<L, LB, FLAVOR, 0, NB>(st, hit, acc);
+        gkm_bins_popc<L, INV, LB, FLAVOR, 0, NB>(st, hit, acc);
     }
 }
 
+/* which plane to keep complemented for a given kernel flavour */
+template <int NB, bool WEIGHTED, int FLAVOR>
+struct gkm_inv_plane { static constexpr int v = (!WEIGHTED && NB == 4 && (FLAVOR & GKM_F_RARE_BINS) != 0) ? 1 : -1; };
+
 /* steps S0..S1-1 of one half chunk (16 positions) for the query pair */
-template <int L, int NB, bool WEIGHTED, int FLAVOR, bool USE_VA, int S0, int S1>
-GKM_HD void gkm_diag_steps(gkm_win_state<L> &st0, gkm_win_state<L> &st1,
+template <int L, int INV, int NB, bool WEIGHTED, int FLAVOR, bool USE_VA, int S0, int S1>
+GKM_HD void gkm_diag_steps(gkm_win_state<L, INV> &st0, gkm_win_state<L, INV> &st1,
                            const gkm_apos2 *ap, const gkm_aaux2 *ax,
                            uint32_t lo0, uint32_t hi0, uint32_t lo1, uint32_t hi1, uint32_t loE, uint32_t hiE,
                            const uint8_t *wend, int jbase, int P, int32_t *acc0, int32_t *acc1)
@@ -239,17 +245,17 @@ GKM_HD void gkm_diag_steps(gkm_win_state<L> &st0, gkm_win_state<L> &st1,
         const uint32_t s0 = gkm_funnel(lo0, hi0, S0);
         const uint32_t s1 = gkm_funnel(lo1, hi1, S0);
         const uint32_t ev = gkm_funnel(loE, hiE, S0);
-        gkm_win_push<L, S0>(st0, (s0 ^ a.a0[0]) | (s1 ^ a.a1[0]));
-        gkm_win_push<L, S0>(st1, (s0 ^ a.a0[1]) | (s1 ^ a.a1[1]));
+        gkm_win_push<L, INV, S0>(st0, (s0 ^ a.a0[0]) | (s1 ^ a.a1[0]));
+        gkm_win_push<L, INV, S0>(st1, (s0 ^ a.a0[1]) | (s1 ^ a.a1[1]));
         uint32_t v0 = ev, v1 = ev, w0 = 1u, w1 = 1u;
         if constexpr (USE_VA || WEIGHTED) {
             const gkm_aaux2 x = ax[S0];
             if constexpr (USE_VA) { v0 &= x.va[0]; v1 &= x.va[1]; }
             w0 = x.wa[0]; w1 = x.wa[1];
         }
-        gkm_bins<L, NB, WEIGHTED, FLAVOR>(st0, gkm_hit_word<L, LB>(st0, v0), w0, wend, jbase + S0, P, acc0);
-        gkm_bins<L, NB, WEIGHTED, FLAVOR>(st1, gkm_hit_word<L, LB>(st1, v1), w1, wend, jbase + S0, P, acc1);
-        gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, USE_VA, S0 + 1, S1>(st0, st1, ap, ax, lo0, hi0, lo1, hi1, loE, hiE,
+        gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st0, gkm_hit_word<L, INV, LB>(st0, v0), w0, wend, jbase + S0, P, acc0);
+        gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st1, gkm_hit_word<L, INV, LB>(st1, v1), w1, wend, jbase + S0, P, acc1);
+        gkm_diag_steps<L, INV, NB, WEIGHTED, FLAVOR, USE_VA, S0 + 1, S1>(st0, st1, ap, ax, lo0, hi0, lo1, hi1, loE, hiE,
                                                                      wend, jbase, P, acc0, acc1);
     }
 }
@@ -265,7 +271,8 @@ GKM_HD void gkm_diag_lane(const gkm_apos2 *apos, const gkm_aaux2 *aaux, int len0
                           const uint32_t *C0, const uint32_t *C1, const uint32_t *E, int Wc, int q,
                           const uint8_t *wend, int32_t *acc0, int32_t *acc1)
 {
-    gkm_win_state<L> st0, st1;
+    constexpr int INV = gkm_inv_plane<NB, WEIGHTED, FLAVOR>::v;
+    gkm_win_state<L, INV> st0, st1;
     st0.clear();
     st1.clear();
     const int lmax = len0 > len1 ? len0 : len1;
@@ -289,12 +296,13 @@ GKM_HD void gkm_diag_lane(const gkm_apos2 *apos, const gkm_aaux2 *aaux, int len0
             const uint32_t lo0 = half ? gkm_funnel(a0, b0, 16) : a0, hi0 = half ? gkm_funnel(b0, c0, 16) : b0;
             const uint32_t lo1 = half ? gkm_funnel(a1, b1, 16) : a1, hi1 = half ? gkm_funnel(b1, c1, 16) : b1;
             const uint32_t loE = half ? gkm_funnel(aE, bE, 16) : aE, hiE = half ? gkm_funnel(bE, cE, 16) : bE;
-            const bool need_va = (e0 < L - 1) || (e0 + 16 > lmin);
+            /* GKM_F_ONE_BODY: a single body that always pays for the AND (half the code, for the I-cache) */
+            const bool need_va = ((FLAVOR & GKM_F_ONE_BODY) != 0) || (e0 < L - 1) || (e0 + 16 > lmin);
             if (need_va)
-                gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, true, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
+                gkm_diag_steps<L, INV, NB, WEIGHTED, FLAVOR, true, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
                                                                       wend, jbase, P, acc0, acc1);
             else
-                gkm_diag_steps<L, NB, WEIGHTED, FLAVOR, false, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
+                gkm_diag_steps<L, INV, NB, WEIGHTED, FLAVOR, false, 0, 16>(st0, st1, apos + e0, aaux + e0, lo0, hi0, lo1, hi1, loE, hiE,
                                                                        wend, jbase, P, acc0, acc1);
             jbase += 16;
             if (jbase >= P) jbase -= P;

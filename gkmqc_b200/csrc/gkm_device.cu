@@ -64,7 +64,8 @@ static const void *diag_fn(int L, int nb, int weighted, int flavor)
 struct gkm_gpu {
     int id;
     int ready;
-    cudaStream_t sc, sx;       /* compute, copy */
+    cudaStream_t sc, sc2, sx;  /* compute (two, so that the tail of one chunk overlaps the head of the next), copy */
+    cudaEvent_t join;
     cudaEvent_t k0[2], k1[2];  /* kernel start / end per staging slot */
     cudaEvent_t cdone[2];      /* D2H complete per staging slot */
     void *d_band[2];
@@ -167,6 +168,8 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
     if (!g->ready) {
         g->id = id;
         CK(cudaStreamCreateWithFlags(&g->sc, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&g->sc2, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&g->join, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&g->sx, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
             CK(cudaEventCreate(&g->k0[i]));
@@ -436,9 +439,10 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     kp.ld = width;
     kp.hist = d_hist;
     kp.hist_cols = width;
-    CK(cudaEventRecord(g->k0[buf], g->sc));
-    if (launch_hist(job->p, kp, g->sc, &dt->variant)) return 1;
-    CK(cudaEventRecord(g->k1[buf], g->sc));
+    cudaStream_t st = buf ? g->sc2 : g->sc;
+    CK(cudaEventRecord(g->k0[buf], st));
+    if (launch_hist(job->p, kp, st, &dt->variant)) return 1;
+    CK(cudaEventRecord(g->k1[buf], st));
     CK(cudaStreamWaitEvent(g->sx, g->k1[buf], 0));
     const size_t bytes = (size_t) (c->row_end - c->row_begin) * (size_t) width * sizeof(double);
     if (bytes) CK(cudaMemcpyAsync(g->h_stage[buf], g->d_band[buf], bytes, cudaMemcpyDeviceToHost, g->sx));
@@ -686,6 +690,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
         for (int it = 0; !rc && it < warmup + steps; it++) {
             if (flush_l2) cudaMemsetAsync(g->d_flush, it & 0xff, GKM_FLUSH_BYTES, g->sc);
             cudaEventRecord(e0, g->sc);
+            cudaStreamWaitEvent(g->sc2, e0, 0);
             launches = 0; entries = 0;
             for (int c = 0; !rc && c < nchunks; c++) {
                 if (gkm_chunk_owner(c, nchunks, p->shard_world) != p->shard_rank) continue;
@@ -696,10 +701,12 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
                 kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
                 kp.row_base = 0; kp.col_base = 0;
                 kp.out = im->full; kp.ld = (long long) im->full_ld;
-                rc = launch_hist(p, kp, g->sc, &variant);
+                rc = launch_hist(p, kp, (launches & 1) ? g->sc2 : g->sc, &variant);
                 launches++;
                 entries += chunks[c].entries;
             }
+            cudaEventRecord(g->join, g->sc2);
+            cudaStreamWaitEvent(g->sc, g->join, 0);
             cudaEventRecord(e1, g->sc);
             if (!rc && cudaEventSynchronize(e1) != cudaSuccess) {
                 gkm_set_error("CUDA: bench pass failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -31,11 +31,13 @@ extern "C" const void *GKM_CAT(gkm_diag_fn_L, GKM_INST_L)(int nb, int weighted, 
     constexpr int L = GKM_INST_L;
 #ifdef GKM_INST_FLAVORS
     if (flavor >= 0 && nb == 4 && !weighted) {
-        switch (flavor & 6) {
+        switch (flavor & 7) {
             case 0: return (const void *) gkm_diag_kernel<L, 4, false, 0>;
+            case 1: return (const void *) gkm_diag_kernel<L, 4, false, 1>;
             case 2: return (const void *) gkm_diag_kernel<L, 4, false, 2>;
-            case 4: return (const void *) gkm_diag_kernel<L, 4, false, 4>;
+            case 3: return (const void *) gkm_diag_kernel<L, 4, false, 3>;
             case 6: return (const void *) gkm_diag_kernel<L, 4, false, 6>;
+            case 7: return (const void *) gkm_diag_kernel<L, 4, false, 7>;
         }
     }
 #endif
