@@ -189,17 +189,20 @@ template <int L, int INV, int LB>
 GKM_HD void gkm_bins_weighted(const gkm_win_state<L, INV> &st, uint32_t hit, uint32_t wa, const uint8_t *wend,
                               int jbase, int P, int32_t *acc)
 {
+    /* `wend` carries a wrap-around copy of its first 32 bytes behind position P-1, so that
+     * jbase + bit (< P + 32) needs no modulo */
+    (void) P;
+    constexpr int NB = 1 << LB;
+    const uint8_t *wj = wend + jbase;
     while (hit) {
         const int bit = gkm_ffs0(hit);
         hit &= hit - 1u;
         int v = 0;
 #pragma unroll
         for (int i = 0; i < LB; i++) v |= (int) ((st.plane(i) >> bit) & 1u) << i;
-        int j = jbase + bit;
-        while (j >= P) j -= P;
-        const int w = (int) wa * (int) wend[j];
+        const int w = (int) wa * (int) wj[bit];
 #pragma unroll
-        for (int b = 0; b < (1 << LB); b++) acc[b] += (v == b) ? w : 0;
+        for (int b = 0; b < NB; b++) acc[b] += (v == b) ? w : 0;
     }
 }
 
@@ -210,7 +213,7 @@ GKM_HD void gkm_bins(const gkm_win_state<L, INV> &st, uint32_t hit, uint32_t wa,
 {
     constexpr int LB = gkm_log2nb<NB>::v;
     if constexpr (WEIGHTED) {
-        if (hit) gkm_bins_weighted<L, INV, LB>(st, hit, wa, wend, jbase, P, acc);
+        gkm_bins_weighted<L, INV, LB>(st, hit, wa, wend, jbase, P, acc);
     } else if constexpr ((FLAVOR & GKM_F_RARE_BINS) != 0 && NB == 4) {
         gkm_bins_popc<L, INV, LB, FLAVOR, 2, 4>(st, hit, acc); /* counts 2 and 3: ~99 % of all hits */
         uint32_t rare = hit & ~st.plane(1);                   /* counts 0 and 1 (plane 1 is stored inverted) */
@@ -253,8 +256,11 @@ GKM_HD void gkm_diag_steps(gkm_win_state<L, INV> &st0, gkm_win_state<L, INV> &st
             if constexpr (USE_VA) { v0 &= x.va[0]; v1 &= x.va[1]; }
             w0 = x.wa[0]; w1 = x.wa[1];
         }
-        gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st0, gkm_hit_word<L, INV, LB>(st0, v0), w0, wend, jbase + S0, P, acc0);
-        gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st1, gkm_hit_word<L, INV, LB>(st1, v1), w1, wend, jbase + S0, P, acc1);
+        const uint32_t h0 = gkm_hit_word<L, INV, LB>(st0, v0), h1 = gkm_hit_word<L, INV, LB>(st1, v1);
+        if (!WEIGHTED || (h0 | h1) != 0u) { /* weighted: ONE divergent region per step for both queries */
+            gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st0, h0, w0, wend, jbase + S0, P, acc0);
+            gkm_bins<L, INV, NB, WEIGHTED, FLAVOR>(st1, h1, w1, wend, jbase + S0, P, acc1);
+        }
         gkm_diag_steps<L, INV, NB, WEIGHTED, FLAVOR, USE_VA, S0 + 1, S1>(st0, st1, ap, ax, lo0, hi0, lo1, hi1, loE, hiE,
                                                                      wend, jbase, P, acc0, acc1);
     }

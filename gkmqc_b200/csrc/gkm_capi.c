@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "gkm_internal.h"
 #include "gkm_options.h"
@@ -127,7 +128,11 @@ int gkm_main_pywrapper(gkmOpt *opts, double **kmat, int *kmat_size)
     gkmb200_problem *p = gkmb200_problem_new(&param);
     if (!p) return 1;
     int rc = 1;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     int npos = gkmb200_problem_read(p, opts->posfile, opts->negfile);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double read_ms = 1e3 * (double) (t1.tv_sec - t0.tv_sec) + 1e-6 * (double) (t1.tv_nsec - t0.tv_nsec);
     if (npos >= 0 && p->n > 0) {
         int nt = opts->nthreads;
         if (nt < 1) nt = 1;
@@ -138,8 +143,9 @@ int gkm_main_pywrapper(gkmOpt *opts, double **kmat, int *kmat_size)
             g_last_stats = p->stats;
             g_last_nk = 0;
             for (int i = 0; i < p->n; i++) if (p->len[i] - param.L + 1 > g_last_nk) g_last_nk = p->len[i] - param.L + 1;
-            gkm_log(GKM_LOG_INFO, "kernel matrix: %d sequences, %lld entries, %d GPU(s), kernel %.1f ms, total %.1f ms",
-                    p->n, p->stats.entries, p->stats.devices, p->stats.kernel_ms, p->stats.wall_ms);
+            gkm_log(GKM_LOG_INFO, "kernel matrix: %d sequences, %lld entries, %d GPU(s): read %.1f ms, pack+upload+sqnorm %.1f ms, "
+                    "kernels %.1f ms (device), compute+copy-out %.1f ms (wall)",
+                    p->n, p->stats.entries, p->stats.devices, read_ms, p->stats.upload_ms, p->stats.kernel_ms, p->stats.wall_ms);
         }
     } else if (npos >= 0) {
         gkm_set_error("no sequences in %s / %s", opts->posfile, opts->negfile);

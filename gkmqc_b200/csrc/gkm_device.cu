@@ -285,9 +285,23 @@ extern "C" void gkm_dev_release(gkmb200_problem *p)
     p->dev = NULL;
 }
 
-static int upload_locked(gkmb200_problem *p)
+/* bring sqnorm back to the host (only the ABI functions that expose it need that) */
+static int fetch_sqnorm(gkmb200_problem *p)
 {
-    if (p->dev && p->packed && p->have_sqnorm) return 0;
+    if (p->host_sqnorm) return 0;
+    gkm_devstate *ds = p->dev;
+    gkm_gpu *g = &g_gpu[ds->dev[0]];
+    CK(cudaSetDevice(ds->dev[0]));
+    CK(cudaMemcpyAsync(p->sqnorm, ds->img[0].sqnorm, (size_t) p->n * sizeof(double), cudaMemcpyDeviceToHost, g->sc));
+    CK(cudaStreamSynchronize(g->sc));
+    p->host_sqnorm = 1;
+    return 0;
+}
+
+/* need_host = 0: everything is only queued; later kernels are stream-ordered behind it */
+static int upload_locked(gkmb200_problem *p, int need_host)
+{
+    if (p->dev && p->packed && p->have_sqnorm) return need_host ? fetch_sqnorm(p) : 0;
     if (ensure_selected()) return 1;
     const double t0 = now_ms();
     gkm_dev_release(p);
@@ -325,14 +339,12 @@ static int upload_locked(gkmb200_problem *p)
             if (launch_hist(p, kp, g->sc, NULL)) return 1;
             p->stats.launches++;
         }
-    }
-    for (int i = 0; i < ds->ndev; i++) {
-        gkm_gpu *g = &g_gpu[ds->dev[i]];
-        CK(cudaSetDevice(ds->dev[i]));
-        if (i == 0) CK(cudaMemcpyAsync(p->sqnorm, ds->img[0].sqnorm, n * sizeof(double), cudaMemcpyDeviceToHost, g->sc));
-        CK(cudaStreamSynchronize(g->sc));
+        CK(cudaEventRecord(g->join, g->sc));            /* the second compute stream starts behind sqnorm too */
+        CK(cudaStreamWaitEvent(g->sc2, g->join, 0));
     }
     p->have_sqnorm = 1;
+    p->host_sqnorm = 0;
+    if (need_host && fetch_sqnorm(p)) return 1;
     p->stats.upload_ms = now_ms() - t0;
     p->stats.h2d_bytes = h2d;
     p->stats.devices = ds->ndev;
@@ -344,7 +356,7 @@ extern "C" int gkm_dev_upload(gkmb200_problem *p)
 {
     pthread_mutex_lock(&g_lock);
     p->stats.launches = 0;
-    int r = upload_locked(p);
+    int r = upload_locked(p, 1);
     pthread_mutex_unlock(&g_lock);
     return r;
 }
@@ -551,7 +563,7 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
     pthread_mutex_lock(&g_lock);
     const double t0 = now_ms();
     p->stats.launches = 0;
-    int rc = upload_locked(p);
+    int rc = upload_locked(p, 0);
     gkm_chunk *chunks = NULL;
     int *owned = NULL;
     if (!rc) {
@@ -618,7 +630,7 @@ extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col
         return 1;
     }
     pthread_mutex_lock(&g_lock);
-    int rc = upload_locked(p);
+    int rc = upload_locked(p, 0);
     double *d_alpha = NULL, *d_dec = NULL;
     if (!rc) {
         gkm_devstate *ds = p->dev;
@@ -660,7 +672,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
 {
     if (!p || steps < 1 || !ms_each) { gkm_set_error("bad bench arguments"); return 1; }
     pthread_mutex_lock(&g_lock);
-    int rc = upload_locked(p);
+    int rc = upload_locked(p, 0);
     gkm_chunk *chunks = NULL;
     if (!rc) {
         gkm_devstate *ds = p->dev;

@@ -9,7 +9,7 @@
  *   sAx   [TA/2][32WA] gkm_aaux2   validity / weight words of the pairs (read by the edge chunks
  *                                   and by the weighted kernel types only)
  *   sS    [TB][3][W]   target bit planes of the circular both-strand string + valid-window-end plane
- *   sW    [TB][32W] bytes          target weights by window end (weighted types)
+ *   sW    [TB][32W+32] bytes       target weights by window end + wrap-around copy (weighted types)
  *   sTask [<= TB*W]                lane tasks (target, block of 32 diagonals)
  *   sH    [TA][TB][NB] int32       the tile's histograms
  * A warp takes (query pair, group of 32 tasks) combos round-robin; every lane runs
@@ -41,7 +41,7 @@ __host__ __device__ inline gkm_diag_layout_t gkm_diag_layout(int W, int WA, int 
     l.offX = o;    o += npair * 32u * (unsigned) WA * 16u;
     l.offS = o;    o += (unsigned) TB * 3u * (unsigned) W * 4u;
     l.offZ = o;    o += (unsigned) W * 4u;
-    l.offW = o;    o += weighted ? (unsigned) TB * 32u * (unsigned) W : 0u;
+    l.offW = o;    o += weighted ? (unsigned) TB * (32u * (unsigned) W + 32u) : 0u; /* + wrap-around copy of 32 bytes */
     l.offTask = o; o += (unsigned) TB * (unsigned) W * 4u;
     l.offH = o;    o += 2u * npair * (unsigned) TB * (unsigned) NB * 4u;
     l.offLenA = o; o += 2u * npair * 4u;
@@ -119,10 +119,20 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
         uint32_t *dst = reinterpret_cast<uint32_t *>(sW);
         for (int i = tid; i < TB * wordsPerB; i += GKM_DIAG_THREADS) {
             const int b = i / wordsPerB;
-            dst[i] = (col0 + b < p.col_end) ? src[(size_t) (col0 + b) * wordsPerB + (i - b * wordsPerB)] : 0u;
+            dst[b * (wordsPerB + 8) + (i - b * wordsPerB)] =
+                (col0 + b < p.col_end) ? src[(size_t) (col0 + b) * wordsPerB + (i - b * wordsPerB)] : 0u;
         }
     }
     __syncthreads();
+    if (WEIGHTED) {
+        /* wrap-around copy: bytes [P_b, P_b + 32) repeat bytes [0, 32) of target b */
+        uint32_t *dst = reinterpret_cast<uint32_t *>(sW);
+        for (int i = tid; i < TB * 8; i += GKM_DIAG_THREADS) {
+            const int b = i >> 3, k = i & 7;
+            const int pw = ((2 * sLenB[b] + 31) >> 5) * 8; /* P_b / 4 words */
+            dst[b * (8 * W + 8) + pw + k] = dst[b * (8 * W + 8) + k];
+        }
+    }
     /* query records, two queries interleaved: the forward strand is the first len bits of the circular string */
     for (int i = tid; i < 2 * NPAIR * 32 * WA; i += GKM_DIAG_THREADS) {
         const int a = i / (32 * WA), e = i - a * 32 * WA;
@@ -178,7 +188,7 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
         const uint32_t *C1 = sS + (b_l * 3 + 1) * W;
         const uint32_t *E = active ? (sS + (b_l * 3 + 2) * W) : sZ;
         const int Wc = active ? ((2 * sLenB[b_l] + 31) >> 5) : 1;
-        const uint8_t *wendp = WEIGHTED ? (sW + (size_t) b_l * 32 * W) : nullptr;
+        const uint8_t *wendp = WEIGHTED ? (sW + (size_t) b_l * (32 * W + 32)) : nullptr;
 
         int32_t acc0[NB], acc1[NB];
 #pragma unroll

@@ -48,7 +48,8 @@ struct gkmb200_problem {
     uint32_t *planes;/* [n][3][Wmax]: code bit 0, code bit 1, valid-window-end plane E */
     uint8_t *wend;   /* weighted only: [n][32*Wmax] weight by window END position */
     double *sqnorm;  /* [n], filled by the device */
-    int have_sqnorm;
+    int have_sqnorm;   /* computed (or queued) on the devices */
+    int host_sqnorm;   /* copied back into sqnorm[] */
 
     int shard_rank, shard_world;
     struct gkm_devstate *dev;

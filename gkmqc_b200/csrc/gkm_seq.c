@@ -206,6 +206,7 @@ void gkm_unpack_problem(gkmb200_problem *p)
     free(p->sqnorm); p->sqnorm = NULL;
     p->packed = 0;
     p->have_sqnorm = 0;
+    p->host_sqnorm = 0;
 }
 
 /* build the device image on the host.
@@ -236,14 +237,22 @@ int gkm_pack_problem(gkmb200_problem *p)
         const int n = p->len[i];
         const uint8_t *c = p->code[i];
         uint32_t *pl = p->planes + (size_t) i * 3 * (size_t) W;
-        for (int pos = 0; pos < 2 * n; pos++) {
-            /* second half: complement of the mirrored base (libgkm.c:878-888) */
-            const uint32_t code = (pos < n) ? c[pos] : 3u - c[2 * n - 1 - pos];
-            const uint32_t bit = 1u << (pos & 31);
-            const int wi = pos >> 5;
-            if (code & 1u) pl[0 * W + wi] |= bit;
-            if (code & 2u) pl[1 * W + wi] |= bit;
-            if ((pos < n ? pos : pos - n) >= L - 1) pl[2 * W + wi] |= bit;
+        /* one word (32 positions) at a time, branch-free */
+        for (int wi = 0; wi * 32 < 2 * n; wi++) {
+            uint32_t w0 = 0, w1 = 0, we = 0;
+            const int top = (wi * 32 + 32 < 2 * n) ? 32 : 2 * n - wi * 32;
+            for (int b = 0; b < top; b++) {
+                const int pos = wi * 32 + b;
+                /* second half: complement of the mirrored base (libgkm.c:878-888) */
+                const uint32_t code = (pos < n) ? c[pos] : 3u - c[2 * n - 1 - pos];
+                const int rel = (pos < n) ? pos : pos - n;
+                w0 |= (code & 1u) << b;
+                w1 |= ((code >> 1) & 1u) << b;
+                we |= (uint32_t) (rel >= L - 1) << b;
+            }
+            pl[0 * W + wi] = w0;
+            pl[1 * W + wi] = w1;
+            pl[2 * W + wi] = we;
         }
         if (p->weighted) {
             const int nk = n - L + 1;

@@ -57,7 +57,14 @@ static void emu_pair(const gkmb200_problem *p, int a0, int a1, int b, int32_t *H
     int32_t acc0[NB], acc1[NB];
     for (int m = 0; m < NB; m++) acc0[m] = acc1[m] = 0;
     const uint32_t *pb = p->planes + (size_t) b * 3 * W;
-    const uint8_t *we = p->weighted ? p->wend + (size_t) b * 32 * W : NULL;
+    std::vector<uint8_t> wext; /* target weights with the wrap-around copy of 32 bytes the kernel keeps in smem */
+    const uint8_t *we = NULL;
+    if (p->weighted) {
+        const uint8_t *src = p->wend + (size_t) b * 32 * W;
+        wext.assign(src, src + 32 * Wc);
+        wext.insert(wext.end(), src, src + 32);
+        we = wext.data();
+    }
     for (int q = 0; q < Wc; q++)
         gkm_diag_lane<L, NB, WEIGHTED, FLAVOR>(apos.data(), aaux.data(), len[0], len[1], pb, pb + W, pb + 2 * W, Wc, q, we, acc0, acc1);
     for (int m = 0; m <= p->param.d; m++) { H0[m] = acc0[m]; if (H1) H1[m] = acc1[m]; }
