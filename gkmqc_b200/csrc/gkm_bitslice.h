@@ -226,6 +226,23 @@ GKM_HD void gkm_bins(const gkm_win_state<L, INV> &st, uint32_t hit, uint32_t wa,
                 if (st.plane(0) & low) acc[1] += 1; else acc[0] += 1;
             } while (rare);
         }
+    } else if constexpr ((FLAVOR & GKM_F_RARE_BINS) != 0 && NB == 8 && ((FLAVOR >> 8) & 15) == 4) {
+        /* d = 4 known at compile time: counts 5..7 are not wanted at all, 4 and 3 hold ~99 % of the
+         * wanted hits, 0..2 take the rare path.  2 POPC per step instead of 8. */
+        const uint32_t p0 = st.plane(0), p1 = st.plane(1), p2 = st.plane(2);
+        const uint32_t b4 = hit & p2 & ~(p1 | p0);
+        const uint32_t low = hit & ~p2;
+        const uint32_t b3 = low & p1 & p0;
+        uint32_t rare = low & ~(p1 & p0);
+        gkm_acc_add<FLAVOR>(acc[4], gkm_popc(b4));
+        gkm_acc_add<FLAVOR>(acc[3], gkm_popc(b3));
+        if (rare) {
+            do {
+                const uint32_t lowbit = rare & (0u - rare);
+                rare ^= lowbit;
+                if (p1 & lowbit) acc[2] += 1; else if (p0 & lowbit) acc[1] += 1; else acc[0] += 1;
+            } while (rare);
+        }
     } else {
         gkm_bins_popc<L, INV, LB, FLAVOR, 0, NB>(st, hit, acc);
     }

@@ -35,24 +35,24 @@
     } while (0)
 
 extern "C" {
-const void *gkm_diag_fn_L2(int, int, int);  const void *gkm_diag_fn_L3(int, int, int);  const void *gkm_diag_fn_L4(int, int, int);
-const void *gkm_diag_fn_L5(int, int, int);  const void *gkm_diag_fn_L6(int, int, int);  const void *gkm_diag_fn_L7(int, int, int);
-const void *gkm_diag_fn_L8(int, int, int);  const void *gkm_diag_fn_L9(int, int, int);  const void *gkm_diag_fn_L10(int, int, int);
-const void *gkm_diag_fn_L11(int, int, int); const void *gkm_diag_fn_L12(int, int, int); const void *gkm_diag_fn_L13(int, int, int);
-const void *gkm_diag_fn_L14(int, int, int); const void *gkm_diag_fn_L15(int, int, int); const void *gkm_diag_fn_L16(int, int, int);
+const void *gkm_diag_fn_L2(int, int, int, int);  const void *gkm_diag_fn_L3(int, int, int, int);  const void *gkm_diag_fn_L4(int, int, int, int);
+const void *gkm_diag_fn_L5(int, int, int, int);  const void *gkm_diag_fn_L6(int, int, int, int);  const void *gkm_diag_fn_L7(int, int, int, int);
+const void *gkm_diag_fn_L8(int, int, int, int);  const void *gkm_diag_fn_L9(int, int, int, int);  const void *gkm_diag_fn_L10(int, int, int, int);
+const void *gkm_diag_fn_L11(int, int, int, int); const void *gkm_diag_fn_L12(int, int, int, int); const void *gkm_diag_fn_L13(int, int, int, int);
+const void *gkm_diag_fn_L14(int, int, int, int); const void *gkm_diag_fn_L15(int, int, int, int); const void *gkm_diag_fn_L16(int, int, int, int);
 }
 
-static const void *diag_fn(int L, int nb, int weighted, int flavor)
+static const void *diag_fn(int L, int nb, int weighted, int d, int flavor)
 {
     switch (L) {
-        case 2: return gkm_diag_fn_L2(nb, weighted, flavor);   case 3: return gkm_diag_fn_L3(nb, weighted, flavor);
-        case 4: return gkm_diag_fn_L4(nb, weighted, flavor);   case 5: return gkm_diag_fn_L5(nb, weighted, flavor);
-        case 6: return gkm_diag_fn_L6(nb, weighted, flavor);   case 7: return gkm_diag_fn_L7(nb, weighted, flavor);
-        case 8: return gkm_diag_fn_L8(nb, weighted, flavor);   case 9: return gkm_diag_fn_L9(nb, weighted, flavor);
-        case 10: return gkm_diag_fn_L10(nb, weighted, flavor); case 11: return gkm_diag_fn_L11(nb, weighted, flavor);
-        case 12: return gkm_diag_fn_L12(nb, weighted, flavor); case 13: return gkm_diag_fn_L13(nb, weighted, flavor);
-        case 14: return gkm_diag_fn_L14(nb, weighted, flavor); case 15: return gkm_diag_fn_L15(nb, weighted, flavor);
-        case 16: return gkm_diag_fn_L16(nb, weighted, flavor);
+        case 2: return gkm_diag_fn_L2(nb, weighted, d, flavor);   case 3: return gkm_diag_fn_L3(nb, weighted, d, flavor);
+        case 4: return gkm_diag_fn_L4(nb, weighted, d, flavor);   case 5: return gkm_diag_fn_L5(nb, weighted, d, flavor);
+        case 6: return gkm_diag_fn_L6(nb, weighted, d, flavor);   case 7: return gkm_diag_fn_L7(nb, weighted, d, flavor);
+        case 8: return gkm_diag_fn_L8(nb, weighted, d, flavor);   case 9: return gkm_diag_fn_L9(nb, weighted, d, flavor);
+        case 10: return gkm_diag_fn_L10(nb, weighted, d, flavor); case 11: return gkm_diag_fn_L11(nb, weighted, d, flavor);
+        case 12: return gkm_diag_fn_L12(nb, weighted, d, flavor); case 13: return gkm_diag_fn_L13(nb, weighted, d, flavor);
+        case 14: return gkm_diag_fn_L14(nb, weighted, d, flavor); case 15: return gkm_diag_fn_L15(nb, weighted, d, flavor);
+        case 16: return gkm_diag_fn_L16(nb, weighted, d, flavor);
         default: return NULL;
     }
 }
@@ -213,7 +213,7 @@ static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st
     unsigned smem = 0;
     if (variant == GKM_KERNEL_DIAG) {
         const int nb = (p->param.d < 4) ? 4 : (p->param.d < 8) ? 8 : 16;
-        fn = diag_fn(p->param.L, nb, p->weighted, gkm_opt_diag_flavor());
+        fn = diag_fn(p->param.L, nb, p->weighted, p->param.d, gkm_opt_diag_flavor());
         if (!fn) { gkm_set_error("no diag kernel for L=%d", p->param.L); return 1; }
         /* TB = 32 makes the lane-task count of a uniform-length tile a multiple of the warp size */
         static const int cand[][2] = { {8, 32}, {4, 32}, {4, 16}, {2, 16}, {2, 8}, {2, 4}, {2, 2}, {2, 1} }; /* TA even: queries go in pairs */

@@ -15,32 +15,34 @@
 #endif
 
 template <int L, int F>
-static const void *pick(int nb, int weighted)
+static const void *pick(int nb, int weighted, int d)
 {
-    constexpr int FW = F & ~GKM_F_RARE_BINS; /* the rare-bin path exists for the plain 4-bin kernel only */
+    constexpr int FW = F & ~GKM_F_RARE_BINS; /* the rare-bin path exists for the plain kernels only */
     if (nb == 4) return weighted ? (const void *) gkm_diag_kernel<L, 4, true, FW> : (const void *) gkm_diag_kernel<L, 4, false, F>;
-    if (nb == 8) return weighted ? (const void *) gkm_diag_kernel<L, 8, true, FW> : (const void *) gkm_diag_kernel<L, 8, false, FW>;
+    if (nb == 8) {
+        if (weighted) return (const void *) gkm_diag_kernel<L, 8, true, FW>;
+        /* d = 4 (the top of the BASELINE sweep) has its own specialisation: flavor bits 8..11 carry d */
+        if (d == 4 && (F & GKM_F_RARE_BINS) != 0 && L >= 4) return (const void *) gkm_diag_kernel<L, 8, false, (F | (4 << 8))>;
+        return (const void *) gkm_diag_kernel<L, 8, false, FW>;
+    }
     if (nb == 16) return weighted ? (const void *) gkm_diag_kernel<L, 16, true, FW> : (const void *) gkm_diag_kernel<L, 16, false, FW>;
     return nullptr;
 }
 
 /* flavor < 0: the default for this build.  Other flavors exist only where GKM_INST_FLAVORS is set
  * (the benchmark word length), for A/B measurements on the device. */
-extern "C" const void *GKM_CAT(gkm_diag_fn_L, GKM_INST_L)(int nb, int weighted, int flavor)
+extern "C" const void *GKM_CAT(gkm_diag_fn_L, GKM_INST_L)(int nb, int weighted, int d, int flavor)
 {
     constexpr int L = GKM_INST_L;
 #ifdef GKM_INST_FLAVORS
     if (flavor >= 0 && nb == 4 && !weighted) {
         switch (flavor & 7) {
             case 0: return (const void *) gkm_diag_kernel<L, 4, false, 0>;
-            case 1: return (const void *) gkm_diag_kernel<L, 4, false, 1>;
             case 2: return (const void *) gkm_diag_kernel<L, 4, false, 2>;
-            case 3: return (const void *) gkm_diag_kernel<L, 4, false, 3>;
             case 6: return (const void *) gkm_diag_kernel<L, 4, false, 6>;
-            case 7: return (const void *) gkm_diag_kernel<L, 4, false, 7>;
         }
     }
 #endif
     (void) flavor;
-    return pick<L, GKM_DIAG_DEFAULT_FLAVOR>(nb, weighted);
+    return pick<L, GKM_DIAG_DEFAULT_FLAVOR>(nb, weighted, d);
 }

@@ -42,9 +42,14 @@ def test_cli_lossless_and_reference_format(tmp_path):
 
 
 def test_cli_defaults_are_the_reference_cli_defaults(tmp_path):
-    g, cfg, pos, neg = load_golden("mix_t2_L10k6d3") if os.path.exists(os.path.join(ROOT, "tests/golden/mix_t2_L10k6d3.npz")) else (None, None, None, None)
-    if g is None:
-        pytest.skip("no L=10,k=6,d=3 type-2 golden set")
+    # no options = EST_TRUNC, L=10 k=6 d=3 (src/gkmkern_main.c:99-107); expected values from the oracle
+    import pyoracle
+    g, cfg, pos, neg = load_golden("uni_t2_L11k7d3")
+    o = pyoracle.Oracle(2, 10, 6, 3)
+    n = o.read_problem(pos, neg)
+    out = tmp_path / "k.tsv"
+    subprocess.check_call([CLI, "-v", "0", "-p", "17", pos, neg, str(out)])
+    assert np.array_equal(parse_tsv(out, n), o.matrix_lower(False)[0])
 
 
 def test_cli_errors(tmp_path):
