@@ -621,6 +621,67 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
 /* ------------------------------------------------------------------ */
 /* fused decision values                              */
 /* ------------------------------------------------------------------ */
+struct gkm_decjob {
+    gkmb200_problem *p;
+    int slot, row0, nrows, col0, ncols;
+    const double *alpha;
+    double bias;
+    double *out;     /* out[0] = first row of this slice */
+    int rc;
+    char err[256];
+};
+
+/* one GPU's slice of the test rows: out[r] = bias + sum_c alpha[c] K(row0 + r, col0 + c) */
+static int decision_slice(gkm_decjob *j)
+{
+    gkmb200_problem *p = j->p;
+    gkm_devstate *ds = p->dev;
+    gkm_gpu *g = &g_gpu[ds->dev[j->slot]];
+    double *d_alpha = NULL, *d_dec = NULL;
+    int rc = 0;
+    do {
+        if (cudaSetDevice(ds->dev[j->slot]) != cudaSuccess) { rc = 1; break; }
+        if (cudaMalloc(&d_alpha, sizeof(double) * (size_t) (j->ncols ? j->ncols : 1)) != cudaSuccess) { rc = 1; break; }
+        if (cudaMalloc(&d_dec, sizeof(double) * (size_t) (j->nrows ? j->nrows : 1)) != cudaSuccess) { rc = 1; break; }
+        if (cudaMemcpyAsync(d_alpha, j->alpha, sizeof(double) * (size_t) j->ncols, cudaMemcpyHostToDevice, g->sc) != cudaSuccess) { rc = 1; break; }
+        if (cudaMemsetAsync(d_dec, 0, sizeof(double) * (size_t) j->nrows, g->sc) != cudaSuccess) { rc = 1; break; }
+        /* the second compute stream must see alpha and the zeroed accumulator too */
+        if (cudaEventRecord(g->join, g->sc) != cudaSuccess || cudaStreamWaitEvent(g->sc2, g->join, 0) != cudaSuccess) { rc = 1; break; }
+    } while (0);
+    if (rc) gkm_set_error("CUDA: decision-value buffers: %s", cudaGetErrorString(cudaGetLastError()));
+    gkm_kparams kp;
+    fill_kparams(p, &ds->img[j->slot], &kp);
+    kp.mode = GKM_MODE_RECT;
+    kp.alpha = d_alpha; kp.decision = d_dec;
+    kp.col_begin = kp.col_base = j->col0; kp.col_end = j->col0 + j->ncols;
+    kp.row_base = j->row0;
+    int launches = 0;
+    for (int r = j->row0; !rc && r < j->row0 + j->nrows; r += 8192) {
+        kp.row_begin = r;
+        kp.row_end = (r + 8192 < j->row0 + j->nrows) ? r + 8192 : j->row0 + j->nrows;
+        rc = launch_hist(p, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
+    }
+    if (!rc) {
+        rc = (cudaStreamSynchronize(g->sc2) != cudaSuccess) ||
+             (cudaMemcpyAsync(j->out, d_dec, sizeof(double) * (size_t) j->nrows, cudaMemcpyDeviceToHost, g->sc) != cudaSuccess) ||
+             (cudaStreamSynchronize(g->sc) != cudaSuccess);
+        if (rc) gkm_set_error("CUDA: decision values failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!rc) for (int i = 0; i < j->nrows; i++) j->out[i] += j->bias;
+    cudaFree(d_alpha);
+    cudaFree(d_dec);
+    return rc;
+}
+
+static void *decision_thread(void *arg)
+{
+    gkm_decjob *j = (gkm_decjob *) arg;
+    j->rc = decision_slice(j);
+    if (j->rc) snprintf(j->err, sizeof(j->err), "%s", gkmb200_last_error());
+    return NULL;
+}
+
+/* the test rows are cut into one contiguous slice per selected GPU; every GPU holds all columns (SVs) */
 extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
                                 const double *alpha, double bias, double *out)
 {
@@ -631,36 +692,30 @@ extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col
     }
     pthread_mutex_lock(&g_lock);
     int rc = upload_locked(p, 0);
-    double *d_alpha = NULL, *d_dec = NULL;
     if (!rc) {
         gkm_devstate *ds = p->dev;
-        gkm_gpu *g = &g_gpu[ds->dev[0]];
-        rc = (cudaSetDevice(ds->dev[0]) != cudaSuccess);
-        if (!rc) rc = (cudaMalloc(&d_alpha, sizeof(double) * (size_t) (ncols ? ncols : 1)) != cudaSuccess);
-        if (!rc) rc = (cudaMalloc(&d_dec, sizeof(double) * (size_t) (nrows ? nrows : 1)) != cudaSuccess);
-        if (!rc) rc = (cudaMemcpyAsync(d_alpha, alpha, sizeof(double) * (size_t) ncols, cudaMemcpyHostToDevice, g->sc) != cudaSuccess);
-        if (!rc) rc = (cudaMemsetAsync(d_dec, 0, sizeof(double) * (size_t) nrows, g->sc) != cudaSuccess);
-        if (rc) gkm_set_error("CUDA: decision-value buffers: %s", cudaGetErrorString(cudaGetLastError()));
-        gkm_kparams kp;
-        fill_kparams(p, &ds->img[0], &kp);
-        kp.mode = GKM_MODE_RECT;
-        kp.alpha = d_alpha; kp.decision = d_dec;
-        kp.col_begin = kp.col_base = col0; kp.col_end = col0 + ncols;
-        kp.row_base = row0;
-        for (int r = row0; !rc && r < row0 + nrows; r += 8192) {
-            kp.row_begin = r;
-            kp.row_end = (r + 8192 < row0 + nrows) ? r + 8192 : row0 + nrows;
-            rc = launch_hist(p, kp, g->sc, NULL);
+        const int nd = ds->ndev;
+        gkm_decjob jobs[GKM_MAX_DEV];
+        pthread_t th[GKM_MAX_DEV];
+        int started[GKM_MAX_DEV];
+        const int per = ((nrows + nd - 1) / nd + 7) & ~7;
+        for (int i = 0; i < nd; i++) {
+            int b = i * per, e = b + per;
+            if (b > nrows) b = nrows;
+            if (e > nrows) e = nrows;
+            memset(&jobs[i], 0, sizeof(jobs[i]));
+            jobs[i].p = p; jobs[i].slot = i; jobs[i].row0 = row0 + b; jobs[i].nrows = e - b;
+            jobs[i].col0 = col0; jobs[i].ncols = ncols; jobs[i].alpha = alpha; jobs[i].bias = bias; jobs[i].out = out + b;
+            started[i] = 0;
+            if (i > 0 && jobs[i].nrows > 0) started[i] = (pthread_create(&th[i], NULL, decision_thread, &jobs[i]) == 0);
         }
-        if (!rc) {
-            rc = (cudaMemcpyAsync(out, d_dec, sizeof(double) * (size_t) nrows, cudaMemcpyDeviceToHost, g->sc) != cudaSuccess) ||
-                 (cudaStreamSynchronize(g->sc) != cudaSuccess);
-            if (rc) gkm_set_error("CUDA: decision values failed: %s", cudaGetErrorString(cudaGetLastError()));
+        decision_thread(&jobs[0]);
+        for (int i = 1; i < nd; i++) {
+            if (started[i]) pthread_join(th[i], NULL);
+            else if (jobs[i].nrows > 0) decision_thread(&jobs[i]);
         }
-        if (!rc) for (int i = 0; i < nrows; i++) out[i] += bias;
+        for (int i = 0; i < nd; i++) if (jobs[i].rc) { gkm_set_error("%s", jobs[i].err); rc = 1; }
     }
-    cudaFree(d_alpha);
-    cudaFree(d_dec);
     pthread_mutex_unlock(&g_lock);
     return rc;
 }
