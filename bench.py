@@ -286,21 +286,32 @@ def main():
     peak_popc = capi.microbench("popc")
     per_gpu_entries_s = value / world
     achieved = per_gpu_entries_s * PAIRS_PER_ENTRY * INT_OPS_PER_PAIR / 1e9
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "dram_traffic_per_launch.json")
+    traffic, ncu = None, None
+    tf = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")   # written from the committed ncu --set full capture
     if os.path.exists(tf):
         try:
-            traffic = json.load(open(tf)).get("bytes_per_launch")
+            ncu = json.load(open(tf))
+            traffic = ncu.get("dram_bytes_per_launch")
         except Exception:
-            traffic = None
+            ncu = None
     roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak_lop3, "unit": "Gop/s", "frac": achieved / peak_lop3,
                 "traffic": traffic,
                 "note": "achieved = entries/s x 168200 L-mer pairs x 5 integer ops of the canonical XOR/LOP3/POPC form "
                         "(SURVEY.md 8d); peak = LOP3 lane-ops/s measured in this run (MEASURED_PEAKS.json has no integer "
                         "peak). The bit-sliced kernel needs < 1 op per pair, so frac > 1 is possible; see DESIGN.md",
                 "peak_popc_gops": peak_popc,
+                "ncu": ncu,   # pipe utilisation of the same kernel under ncu (profiles/): the executed-work view of the roofline
                 "avg_launch_ms": ms_per_step / max(1, st["launches"]),
                 "kernel_variant": {1: "lmer", 2: "diag", 3: "mma"}.get(st["kernel_variant"], "?")}
+
+    # secondary figure: gkmQC's default weighted kernel, type 4 (wgkm, M=50 H=50), same sequences
+    secondary = None
+    if world == 1:
+        with capi.Problem(4, L, K, D, 50, 50.0, 1.0) as P4:
+            P4.read(pos, neg)
+            ms4 = P4.bench_lower_resident(2, 1, flush_l2=True)
+            secondary = {"kernel_type": 4, "value": total_entries / (float(ms4.mean()) * 1e-3), "unit": "entries/s",
+                         "ms_per_step": float(ms4.mean()), "note": "wgkm (EST_TRUNC_PW) on the same workload, resident pass"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -314,7 +325,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * float(np.mean(walls)), "steps": e2e_steps,
                 "call": "gkm_main_pywrapper(FASTA paths, double** rows of a fresh numpy matrix, int[2])"},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}))
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}))
 
 
 if __name__ == "__main__":

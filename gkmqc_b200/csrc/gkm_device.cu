@@ -73,6 +73,10 @@ struct gkm_gpu {
     void *h_stage[2];
     size_t stage_cap;
     void *d_flush;
+    /* small cache of device blocks: cudaMalloc/cudaFree per call cost up to a second of host time on
+     * this driver (measured: sporadic 0.2-1.3 s inside gkm_main_pywrapper), so image buffers are recycled */
+    struct { void *ptr; size_t bytes; } pool[32];
+    int npool;
 };
 
 static gkm_gpu g_gpu[GKM_MAX_DEV];
@@ -85,6 +89,7 @@ struct gkm_image {
     int32_t *lens;
     uint8_t *wend;
     double *sqnorm;
+    size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes; /* block sizes as handed out by the pool */
     double *full;       /* resident N x ldfull result (bench) */
     size_t full_ld;
 };
@@ -269,17 +274,51 @@ static void fill_kparams(const gkmb200_problem *p, const gkm_image *im, gkm_kpar
 /* ------------------------------------------------------------------ */
 /* upload: packed image to every selected GPU; sqnorm = diagonal of the kernel */
 /* ------------------------------------------------------------------ */
+/* device blocks come from / go back to a per-GPU free list (current device must be g's) */
+static int pool_alloc(gkm_gpu *g, void **out, size_t *got, size_t bytes)
+{
+    const size_t need = (bytes + 65535) & ~(size_t) 65535;
+    int best = -1;
+    for (int i = 0; i < g->npool; i++)
+        if (g->pool[i].bytes >= need && g->pool[i].bytes <= 4 * need && (best < 0 || g->pool[i].bytes < g->pool[best].bytes)) best = i;
+    if (best >= 0) {
+        *out = g->pool[best].ptr;
+        *got = g->pool[best].bytes;
+        g->pool[best] = g->pool[--g->npool];
+        return 0;
+    }
+    CK(cudaMalloc(out, need));
+    *got = need;
+    return 0;
+}
+
+static void pool_free(gkm_gpu *g, void *ptr, size_t bytes)
+{
+    if (!ptr) return;
+    if (g->npool < 32 && bytes <= ((size_t) 512 << 20)) {
+        g->pool[g->npool].ptr = ptr;
+        g->pool[g->npool].bytes = bytes;
+        g->npool++;
+        return;
+    }
+    cudaFree(ptr);
+}
+
 extern "C" void gkm_dev_release(gkmb200_problem *p)
 {
     if (!p || !p->dev) return;
     gkm_devstate *ds = p->dev;
     for (int i = 0; i < ds->ndev; i++) {
         if (cudaSetDevice(ds->dev[i]) != cudaSuccess) { cudaGetLastError(); continue; }
-        cudaFree(ds->img[i].planes);
-        cudaFree(ds->img[i].lens);
-        cudaFree(ds->img[i].wend);
-        cudaFree(ds->img[i].sqnorm);
-        cudaFree(ds->img[i].full);
+        gkm_gpu *g = &g_gpu[ds->dev[i]];
+        gkm_image *im = &ds->img[i];
+        /* nothing of this problem may still be running when its blocks are recycled */
+        if (g->ready) { cudaStreamSynchronize(g->sc); cudaStreamSynchronize(g->sc2); cudaStreamSynchronize(g->sx); }
+        pool_free(g, im->planes, im->planes_bytes);
+        pool_free(g, im->lens, im->lens_bytes);
+        pool_free(g, im->wend, im->wend_bytes);
+        pool_free(g, im->sqnorm, im->sqnorm_bytes);
+        cudaFree(im->full);
     }
     free(ds);
     p->dev = NULL;
@@ -317,14 +356,14 @@ static int upload_locked(gkmb200_problem *p, int need_host)
         gkm_gpu *g = &g_gpu[g_sel[i]];
         if (gpu_prepare(g, g_sel[i], 0, 0)) return 1;
         gkm_image *im = &ds->img[i];
-        CK(cudaMalloc(&im->planes, n * 3 * W * sizeof(uint32_t)));
-        CK(cudaMalloc(&im->lens, n * sizeof(int32_t)));
-        CK(cudaMalloc(&im->sqnorm, n * sizeof(double)));
+        if (pool_alloc(g, (void **) &im->planes, &im->planes_bytes, n * 3 * W * sizeof(uint32_t))) return 1;
+        if (pool_alloc(g, (void **) &im->lens, &im->lens_bytes, n * sizeof(int32_t))) return 1;
+        if (pool_alloc(g, (void **) &im->sqnorm, &im->sqnorm_bytes, n * sizeof(double))) return 1;
         CK(cudaMemcpyAsync(im->planes, p->planes, n * 3 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
         CK(cudaMemcpyAsync(im->lens, p->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->sc));
         h2d += (long long) (n * 3 * W * sizeof(uint32_t) + n * sizeof(int32_t));
         if (p->weighted) {
-            CK(cudaMalloc(&im->wend, n * 32 * W));
+            if (pool_alloc(g, (void **) &im->wend, &im->wend_bytes, n * 32 * W)) return 1;
             CK(cudaMemcpyAsync(im->wend, p->wend, n * 32 * W, cudaMemcpyHostToDevice, g->sc));
             h2d += (long long) (n * 32 * W);
         }
