@@ -21,6 +21,7 @@
 #include "gkm_internal.h"
 #include "gkm_options.h"
 #include "gkm_lmer_kernel.cuh"
+#include "gkm_mma_kernel.cuh"
 
 #define GKM_MAX_DEV 16
 #define GKM_FLUSH_BYTES ((size_t) 256 << 20) /* > 126 MB L2 */
@@ -205,6 +206,7 @@ static int pick_variant(const gkmb200_problem *p)
 {
     int v = gkm_opt_kernel();
     if (v == GKM_KERNEL_LMER) return GKM_KERNEL_LMER;
+    if (v == GKM_KERNEL_MMA && p->param.d < p->param.L) return GKM_KERNEL_MMA; /* needs >= 1 matching base per hit */
     return GKM_KERNEL_DIAG;
 }
 
@@ -232,6 +234,13 @@ static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st
         if (chosen < 0) { gkm_set_error("sequence too long for shared memory"); return 1; }
         kp.TA = cand[chosen][0];
         kp.TB = cand[chosen][1];
+    } else if (variant == GKM_KERNEL_MMA) {
+        fn = p->weighted ? (const void *) gkm_mma_kernel<true> : (const void *) gkm_mma_kernel<false>;
+        smem = gkm_mma_smem_bytes(p->Wa, p->nbins, p->weighted);
+        if (smem > 220u * 1024u) { gkm_set_error("sequence too long for the mma kernel"); return 1; }
+        if (smem < 100u * 1024u) smem = 100u * 1024u; /* at most 2 CTAs per SM: each holds 256 of the 512 TMEM columns */
+        kp.TA = 1;
+        kp.TB = GKM_MMA_TB;
     } else {
         fn = p->weighted ? (const void *) gkm_lmer_kernel<true> : (const void *) gkm_lmer_kernel<false>;
         static const int cand[][2] = { {8, 8}, {4, 4}, {2, 2}, {1, 1} };
