@@ -22,6 +22,7 @@
 #include "gkm_options.h"
 #include "gkm_lmer_kernel.cuh"
 #include "gkm_mma_kernel.cuh"
+#include "gkm_index_dev.h"
 
 #define GKM_MAX_DEV 16
 #define GKM_FLUSH_BYTES ((size_t) 256 << 20) /* > 126 MB L2 */
@@ -78,6 +79,10 @@ struct gkm_gpu {
      * this driver (measured: sporadic 0.2-1.3 s inside gkm_main_pywrapper), so image buffers are recycled */
     struct { void *ptr; size_t bytes; } pool[32];
     int npool;
+    /* "index" variant: XOR masks of the (L, d) last used on this GPU */
+    uint32_t *d_deltas;
+    size_t deltas_bytes;
+    int delta_L, delta_d, ndelta;
 };
 
 static gkm_gpu g_gpu[GKM_MAX_DEV];
@@ -93,12 +98,16 @@ struct gkm_image {
     size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes; /* block sizes as handed out by the pool */
     double *full;       /* resident N x ldfull result (bench) */
     size_t full_ld;
+    /* "index" variant: one inverted index per block of blk_cols columns, built on first use */
+    gkm_idx_block *blk;
+    int nblk, blk_cols;
 };
 
 struct gkm_devstate {
     int ndev;
     int dev[GKM_MAX_DEV];
     gkm_image img[GKM_MAX_DEV];
+    int variant;        /* kernel variant of the compute call in progress (choose_variant) */
 };
 
 static double now_ms(void)
@@ -202,7 +211,8 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
 /* ------------------------------------------------------------------ */
 /* one launch of a histogram kernel over the block described by kp     */
 /* ------------------------------------------------------------------ */
-static int pick_variant(const gkmb200_problem *p)
+/* variant named by the option, without the index (which is decided per compute call, choose_variant) */
+static int base_variant(const gkmb200_problem *p)
 {
     int v = gkm_opt_kernel();
     if (v == GKM_KERNEL_LMER) return GKM_KERNEL_LMER;
@@ -210,11 +220,43 @@ static int pick_variant(const gkmb200_problem *p)
     return GKM_KERNEL_DIAG;
 }
 
-static int launch_hist(const gkmb200_problem *p, gkm_kparams kp, cudaStream_t st, int *variant_out)
+static int pick_variant(const gkmb200_problem *p, int mode)
 {
-    const int variant = pick_variant(p);
+    int v = (p->dev && p->dev->variant) ? p->dev->variant : base_variant(p);
+    if (v == GKM_KERNEL_INDEX && mode == GKM_MODE_DIAG) v = GKM_KERNEL_DIAG; /* sqnorm: n pairs only */
+    return v;
+}
+
+/* "index" variant: one row-kernel launch per index block that holds wanted columns */
+static int launch_index(const gkmb200_problem *p, const gkm_image *im, const gkm_gpu *g, const gkm_kparams &kp, cudaStream_t st)
+{
+    int a_max = kp.row_end - 1;
+    for (int k = 0; k < im->nblk; k++) {
+        const gkm_idx_block *b = &im->blk[k];
+        int lo = kp.col_begin > b->cb ? kp.col_begin : b->cb;
+        int hi = kp.col_end < b->ce ? kp.col_end : b->ce;
+        if (kp.mode == GKM_MODE_LOWER && hi > a_max) hi = a_max; /* columns < row only */
+        if (hi <= lo) continue;
+        if (!b->built) { gkm_set_error("index block %d is not built", k); return 1; }
+        gkm_idx_rowargs ra;
+        ra.tab = b->tab; ra.ovf = b->ovf; ra.deltas = g->d_deltas; ra.ndelta = g->ndelta;
+        ra.cb = b->cb; ra.blo = lo - b->cb; ra.bhi = hi - b->cb;
+        ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
+        ra.maxq = 32 * p->Wa;
+        if (gkm_idx_rows(&kp, &ra, p->weighted, st)) return 1;
+    }
+    return 0;
+}
+
+static int launch_hist(const gkmb200_problem *p, const gkm_image *im, const gkm_gpu *g, gkm_kparams kp, cudaStream_t st, int *variant_out)
+{
+    const int variant = pick_variant(p, kp.mode);
     const int rows = kp.row_end - kp.row_begin, cols = kp.col_end - kp.col_begin;
     if (rows <= 0 || cols <= 0) return 0;
+    if (variant == GKM_KERNEL_INDEX) {
+        if (variant_out) *variant_out = variant;
+        return launch_index(p, im, g, kp, st);
+    }
     const int forced_ta = gkm_opt_tile_rows();
     const void *fn = NULL;
     unsigned smem = 0;
@@ -313,6 +355,146 @@ static void pool_free(gkm_gpu *g, void *ptr, size_t bytes)
     cudaFree(ptr);
 }
 
+/* ------------------------------------------------------------------ */
+/* "index" variant: per-GPU mask list, per-image column-block indexes    */
+/* ------------------------------------------------------------------ */
+static void release_index(gkm_gpu *g, gkm_image *im)
+{
+    for (int k = 0; k < im->nblk; k++) {
+        pool_free(g, im->blk[k].tab, im->blk[k].tab_bytes);
+        pool_free(g, im->blk[k].ovf, im->blk[k].ovf_bytes);
+    }
+    free(im->blk);
+    im->blk = NULL;
+    im->nblk = 0;
+}
+
+static int ensure_deltas(gkm_gpu *g, int L, int d)
+{
+    if (g->d_deltas && g->delta_L == L && g->delta_d == d) return 0;
+    const long long nd = gkm_idx_delta_count(L, d);
+    if (nd <= 0) { gkm_set_error("index variant: too many masks for L=%d d=%d", L, d); return 1; }
+    uint32_t *h = (uint32_t *) malloc((size_t) nd * 4);
+    if (!h || gkm_idx_deltas(L, d, h, nd) != nd) { free(h); gkm_set_error("index variant: mask list failed"); return 1; }
+    if (g->d_deltas) { cudaStreamSynchronize(g->sc); cudaStreamSynchronize(g->sc2); pool_free(g, g->d_deltas, g->deltas_bytes); g->d_deltas = NULL; }
+    if (pool_alloc(g, (void **) &g->d_deltas, &g->deltas_bytes, (size_t) nd * 4)) { free(h); return 1; }
+    cudaError_t e = cudaMemcpyAsync(g->d_deltas, h, (size_t) nd * 4, cudaMemcpyHostToDevice, g->sc);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc); /* h is pageable and freed below */
+    free(h);
+    if (e != cudaSuccess) { gkm_set_error("CUDA: mask upload: %s", cudaGetErrorString(e)); return 1; }
+    g->delta_L = L; g->delta_d = d; g->ndelta = (int) nd;
+    return 0;
+}
+
+/* build the indexes of the column blocks that intersect [col_begin, col_end); queued on g->sc */
+static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_begin, int col_end)
+{
+    const int L = p->param.L;
+    if (ensure_deltas(g, L, p->param.d)) return 1;
+    if (!im->blk) {
+        const int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
+        if (cap <= 0) { gkm_set_error("index variant: sequences too long for shared memory"); return 1; }
+        const int nblk = (p->n + cap - 1) / cap;
+        int cols = (((p->n + nblk - 1) / nblk) + 31) & ~31;
+        if (cols > cap) cols = cap;
+        im->blk = (gkm_idx_block *) calloc((size_t) nblk, sizeof(gkm_idx_block));
+        if (!im->blk) { gkm_set_error("out of memory"); return 1; }
+        im->nblk = nblk;
+        im->blk_cols = cols;
+        for (int k = 0; k < nblk; k++) {
+            im->blk[k].cb = k * cols;
+            im->blk[k].ce = (k + 1) * cols < p->n ? (k + 1) * cols : p->n;
+        }
+    }
+    for (int k = 0; k < im->nblk; k++) {
+        gkm_idx_block *b = &im->blk[k];
+        if (b->built || b->ce <= col_begin || b->cb >= col_end || b->ce <= b->cb) continue;
+        const int nc = b->ce - b->cb;
+        uint32_t *offs = (uint32_t *) malloc((size_t) nc * 4);
+        if (!offs) { gkm_set_error("out of memory"); return 1; }
+        size_t P = 0;
+        for (int i = 0; i < nc; i++) { offs[i] = (uint32_t) P; P += 2 * (size_t) (p->len[b->cb + i] - L + 1); }
+        if (P > 0x7FFFFFF0u) { free(offs); gkm_set_error("index variant: column block too large"); return 1; }
+        size_t cub_bytes = 0;
+        const size_t sbytes = gkm_idx_scratch_bytes(P, L, &cub_bytes);
+        void *scratch = NULL, *d_offs = NULL;
+        size_t scratch_got = 0, offs_got = 0;
+        int rc = pool_alloc(g, (void **) &b->tab, &b->tab_bytes, gkm_idx_tab_bytes(L)) ||
+                 pool_alloc(g, (void **) &b->ovf, &b->ovf_bytes, (2 * P + 4) * 4) ||
+                 pool_alloc(g, &scratch, &scratch_got, sbytes) ||
+                 pool_alloc(g, &d_offs, &offs_got, (size_t) nc * 4);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(d_offs, offs, (size_t) nc * 4, cudaMemcpyHostToDevice, g->sc);
+            if (e != cudaSuccess) { gkm_set_error("CUDA: index offsets: %s", cudaGetErrorString(e)); rc = 1; }
+        }
+        if (!rc) {
+            gkm_idx_build_args a;
+            a.planes = im->planes; a.lens = im->lens; a.wend = p->weighted ? im->wend : NULL;
+            a.W = p->Wmax; a.L = L; a.cb = b->cb; a.ce = b->ce;
+            a.offs = (const uint32_t *) d_offs; a.P = P; a.scratch = scratch; a.cub_bytes = cub_bytes;
+            a.tab = b->tab; a.ovf = b->ovf;
+            rc = gkm_idx_build(&a, g->sc);
+        }
+        /* pageable source and recycled scratch: wait for the build before letting go of them */
+        if (cudaStreamSynchronize(g->sc) != cudaSuccess && !rc) { gkm_set_error("CUDA: index build failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+        free(offs);
+        pool_free(g, scratch, scratch_got);
+        pool_free(g, d_offs, offs_got);
+        if (rc) return 1;
+        b->built = 1;
+        p->stats.launches += 5;
+    }
+    return 0;
+}
+
+/* which kernel variant serves a block of rows x cols; for the index also makes sure that the
+ * indexes exist on every GPU.  Called under g_lock after upload_locked. */
+static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower)
+{
+    gkm_devstate *ds = p->dev;
+    const int opt = gkm_opt_kernel();
+    int v = base_variant(p);
+    if ((opt == GKM_KERNEL_AUTO || opt == GKM_KERNEL_INDEX) && nrows > 0 && ncols > 0 &&
+        gkm_idx_supported(p->param.L, p->param.d, p->nbins)) {
+        const int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
+        const int nblk_all = cap > 0 ? (p->n + cap - 1) / cap : 0;
+        int ok = cap > 0 && p->n <= (long long) nblk_all * (long long) GKM_IDX_MAX_COLS;
+        int blocks = 0;
+        if (ok) {
+            int cols = (((p->n + nblk_all - 1) / nblk_all) + 31) & ~31;
+            if (cols > cap) cols = cap;
+            blocks = (col0 + ncols - 1) / cols - col0 / cols + 1;
+            /* at most 8 GiB of slot tables per GPU */
+            if ((double) blocks * (double) gkm_idx_tab_bytes(p->param.L) > 8.0 * 1073741824.0) ok = 0;
+        }
+        if (ok && opt == GKM_KERNEL_AUTO) {
+            double sum = 0.0;
+            for (int i = 0; i < p->n; i++) sum += (double) (p->len[i] - p->param.L + 1);
+            const double nq = sum / (double) p->n;
+            const long long entries = (long long) nrows * (long long) ncols / (lower ? 2 : 1);
+            /* lower: row a probes only the blocks that start below it */
+            const int eff_blocks = lower ? (blocks + 1) / 2 : blocks;
+            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, nrows, nq, eff_blocks > 0 ? eff_blocks : 1, entries, 2.0 * nq * nq);
+            const double cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
+            ok = ci < cd;
+            gkm_log(GKM_LOG_DEBUG, "kernel = auto: index %.2f ms vs diag %.2f ms (estimates)", ci, cd);
+        }
+        if (ok) v = GKM_KERNEL_INDEX;
+    }
+    if (v == GKM_KERNEL_INDEX) {
+        for (int i = 0; i < ds->ndev; i++) {
+            gkm_gpu *g = &g_gpu[ds->dev[i]];
+            CK(cudaSetDevice(ds->dev[i]));
+            if (ensure_index(p, g, &ds->img[i], col0, col0 + ncols)) return 1;
+            CK(cudaEventRecord(g->join, g->sc));
+            CK(cudaStreamWaitEvent(g->sc2, g->join, 0));
+        }
+    }
+    (void) row0;
+    ds->variant = v;
+    return 0;
+}
+
 extern "C" void gkm_dev_release(gkmb200_problem *p)
 {
     if (!p || !p->dev) return;
@@ -327,6 +509,7 @@ extern "C" void gkm_dev_release(gkmb200_problem *p)
         pool_free(g, im->lens, im->lens_bytes);
         pool_free(g, im->wend, im->wend_bytes);
         pool_free(g, im->sqnorm, im->sqnorm_bytes);
+        release_index(g, im);
         cudaFree(im->full);
     }
     free(ds);
@@ -384,7 +567,7 @@ static int upload_locked(gkmb200_problem *p, int need_host)
         for (int r = 0; r < p->n; r += 1024) {
             kp.row_begin = kp.col_begin = kp.row_base = kp.col_base = r;
             kp.row_end = kp.col_end = (r + 1024 < p->n) ? r + 1024 : p->n;
-            if (launch_hist(p, kp, g->sc, NULL)) return 1;
+            if (launch_hist(p, im, g, kp, g->sc, NULL)) return 1;
             p->stats.launches++;
         }
         CK(cudaEventRecord(g->join, g->sc));            /* the second compute stream starts behind sqnorm too */
@@ -501,7 +684,7 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     kp.hist_cols = width;
     cudaStream_t st = buf ? g->sc2 : g->sc;
     CK(cudaEventRecord(g->k0[buf], st));
-    if (launch_hist(job->p, kp, st, &dt->variant)) return 1;
+    if (launch_hist(job->p, im, g, kp, st, &dt->variant)) return 1;
     CK(cudaEventRecord(g->k1[buf], st));
     CK(cudaStreamWaitEvent(g->sx, g->k1[buf], 0));
     const size_t bytes = (size_t) (c->row_end - c->row_begin) * (size_t) width * sizeof(double);
@@ -612,6 +795,7 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
     const double t0 = now_ms();
     p->stats.launches = 0;
     int rc = upload_locked(p, 0);
+    if (!rc) rc = choose_variant(p, row0, nrows, col0, ncols, lower);
     gkm_chunk *chunks = NULL;
     int *owned = NULL;
     if (!rc) {
@@ -707,7 +891,7 @@ static int decision_slice(gkm_decjob *j)
     for (int r = j->row0; !rc && r < j->row0 + j->nrows; r += 8192) {
         kp.row_begin = r;
         kp.row_end = (r + 8192 < j->row0 + j->nrows) ? r + 8192 : j->row0 + j->nrows;
-        rc = launch_hist(p, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
+        rc = launch_hist(p, &ds->img[j->slot], g, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
     }
     if (!rc) {
         rc = (cudaStreamSynchronize(g->sc2) != cudaSuccess) ||
@@ -740,6 +924,7 @@ extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col
     }
     pthread_mutex_lock(&g_lock);
     int rc = upload_locked(p, 0);
+    if (!rc) rc = choose_variant(p, row0, nrows, col0, ncols, 0);
     if (!rc) {
         gkm_devstate *ds = p->dev;
         const int nd = ds->ndev;
@@ -776,6 +961,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
     if (!p || steps < 1 || !ms_each) { gkm_set_error("bad bench arguments"); return 1; }
     pthread_mutex_lock(&g_lock);
     int rc = upload_locked(p, 0);
+    if (!rc) rc = choose_variant(p, 0, p->n, 0, p->n, 1);
     gkm_chunk *chunks = NULL;
     if (!rc) {
         gkm_devstate *ds = p->dev;
@@ -816,7 +1002,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
                 kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
                 kp.row_base = 0; kp.col_base = 0;
                 kp.out = im->full; kp.ld = (long long) im->full_ld;
-                rc = launch_hist(p, kp, (launches & 1) ? g->sc2 : g->sc, &variant);
+                rc = launch_hist(p, im, g, kp, (launches & 1) ? g->sc2 : g->sc, &variant);
                 launches++;
                 entries += chunks[c].entries;
             }

@@ -1,0 +1,369 @@
+/* gkm_index.cu -- sm_100a kernels of the "index" variant (see gkm_index.h for the idea).
+ *
+ * Build (once per column block of a problem, a few ms):
+ *   gkm_idx_keys_kernel   every valid L-mer window of both strands of the block's columns ->
+ *                         64-bit key  code << 32 | column << 8 | weight
+ *   cub radix sort        by (code, column)            [library call, set-up only]
+ *   gkm_idx_runs_kernel   run length of every distinct code; overflow demand of runs >= 3
+ *   cub exclusive scan    overflow offsets             [library call, set-up only]
+ *   gkm_idx_fill_kernel   slots {posting 0, posting 1 | pointer} and overflow lists
+ * Hot loop:
+ *   gkm_index_rows_kernel one CTA of 1024 threads per query row; histogram row in shared
+ *                         memory; fused fp64 epilogue identical to the other variants
+ *                         (ascending-m sum, one division, no FMA; libgkm.c:576-582,1169-1179).
+ */
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "gkm_index_dev.h"
+#include "gkm_internal.h"
+
+#define GKM_IDX_THREADS 1024
+#define GKM_IDX_UNROLL 4
+
+/* ------------------------------------------------------------------ */
+/* build                                                                */
+/* ------------------------------------------------------------------ */
+__device__ __forceinline__ uint32_t idx_window(const uint32_t *pl, int W, int lo, uint32_t mask)
+{
+    const int w = lo >> 5, s = lo & 31;
+    const uint32_t x = pl[w], y = (w + 1 < W) ? pl[w + 1] : 0u;
+    return __funnelshift_r(x, y, (uint32_t) s) & mask;
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(128)
+gkm_idx_keys_kernel(const uint32_t *__restrict__ planes, const int32_t *__restrict__ lens, const uint8_t *__restrict__ wend,
+                    int W, int L, int cb, const uint32_t *__restrict__ offs, unsigned long long *__restrict__ keys)
+{
+    const int b = (int) blockIdx.x, g = cb + b;
+    const int len = lens[g], nk = len - L + 1;
+    const uint32_t base = offs[b];
+    const uint32_t mask = (L >= 32) ? 0xFFFFFFFFu : ((1u << L) - 1u);
+    const uint32_t *pl = planes + (size_t) g * 3 * (size_t) W;
+    for (int j = (int) threadIdx.x; j < 2 * len; j += (int) blockDim.x) {
+        const int rel = (j < len) ? j : j - len;
+        if (rel < L - 1) continue;
+        const uint32_t x0 = idx_window(pl, W, j - L + 1, mask), x1 = idx_window(pl + W, W, j - L + 1, mask);
+        const uint32_t code = gkm_idx_code(x0, x1, L);
+        const uint32_t wt = WEIGHTED ? (uint32_t) wend[(size_t) g * 32 * (size_t) W + (size_t) j] : 1u;
+        const uint32_t slot = base + (uint32_t) ((j < len) ? rel - (L - 1) : nk + rel - (L - 1));
+        keys[slot] = ((unsigned long long) code << 32) | ((unsigned long long) (uint32_t) b << 8) | (unsigned long long) wt;
+    }
+}
+
+/* first index in [lo, hi) whose code is > code (keys sorted by code) */
+__device__ __forceinline__ uint32_t idx_upper(const unsigned long long *keys, uint32_t lo, uint32_t hi, uint32_t code)
+{
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((uint32_t) (keys[mid] >> 32) <= code) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* first index in [lo, hi) whose code is >= code */
+__device__ __forceinline__ uint32_t idx_lower(const unsigned long long *keys, uint32_t lo, uint32_t hi, uint32_t code)
+{
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((uint32_t) (keys[mid] >> 32) < code) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256)
+gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, uint32_t *__restrict__ runlen, uint32_t *__restrict__ need)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const uint32_t code = (uint32_t) (keys[i] >> 32);
+    uint32_t len = 0;
+    if (i == 0 || (uint32_t) (keys[i - 1] >> 32) != code) {
+        /* gallop, then bisect: runs are short (mean 1.4 at 10k x 300 bp) but homopolymers make long ones */
+        uint32_t lo = i + 1, hi = P, step = 1; /* [i, lo) holds `code`; keys[hi] does not (or hi == P) */
+        for (;;) {
+            const uint32_t probe = lo + step - 1;
+            if (probe >= P) { hi = P; break; }
+            if ((uint32_t) (keys[probe] >> 32) != code) { hi = probe; break; }
+            lo = probe + 1;
+            step <<= 1;
+        }
+        len = idx_upper(keys, lo, hi, code) - i;
+    }
+    runlen[i] = len;
+    need[i] = (len >= 3) ? ((len + 3u) & ~3u) : 0u; /* postings 1.. of the run plus end markers up to a multiple of 4 */
+}
+
+__global__ void __launch_bounds__(256)
+gkm_idx_fill_kernel(const unsigned long long *__restrict__ keys, uint32_t P, const uint32_t *__restrict__ runlen,
+                    const uint32_t *__restrict__ ovfofs, uint2 *__restrict__ tab, uint32_t *__restrict__ ovf)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const unsigned long long key = keys[i];
+    const uint32_t code = (uint32_t) (key >> 32);
+    uint32_t lb = i;
+    if (runlen[i] == 0) {
+        /* not a head: gallop back, then bisect */
+        uint32_t hi = i, lo = 0, step = 1; /* [hi, i] holds `code` */
+        for (;;) {
+            if (hi < step) { lo = 0; break; }
+            const uint32_t probe = hi - step;
+            if ((uint32_t) (keys[probe] >> 32) != code) { lo = probe + 1; break; }
+            hi = probe;
+            step <<= 1;
+        }
+        lb = idx_lower(keys, lo, hi, code);
+    }
+    const uint32_t len = runlen[lb], r = i - lb;
+    const uint32_t posting = gkm_idx_posting((uint32_t) (key >> 8) & GKM_IDX_COL_MASK, (uint32_t) key & 0xFFu);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(tab + code);
+    if (r == 0) {
+        slot[0] = posting;
+        if (len >= 3) {
+            slot[1] = GKM_IDX_PTR | ovfofs[lb];
+            const uint32_t end = (len + 3u) & ~3u; /* lists are read 16 bytes at a time */
+            for (uint32_t t = len - 1; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_EMPTY;
+        }
+    } else if (len == 2) {
+        slot[1] = posting;
+    } else {
+        ovf[ovfofs[lb] + r - 1] = posting;
+    }
+}
+
+size_t gkm_idx_tab_bytes(int L) { return ((size_t) 1 << (2 * L)) * sizeof(uint2); }
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out)
+{
+    size_t t1 = 0, t2 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t1, (const unsigned long long *) nullptr, (unsigned long long *) nullptr,
+                                   (int) P, 8, 32 + 2 * L);
+    cub::DeviceScan::ExclusiveSum(nullptr, t2, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) P);
+    const size_t cubb = align256(t1 > t2 ? t1 : t2);
+    if (cub_bytes_out) *cub_bytes_out = cubb;
+    return 2 * align256(P * 8) + 2 * align256(P * 4) + cubb + 256;
+}
+
+int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st)
+{
+    const size_t P = a->P;
+    if (P == 0 || P > 0x7FFFFFF0u) { gkm_set_error("index block with %zu postings", P); return 1; }
+    unsigned char *s = (unsigned char *) a->scratch;
+    unsigned long long *keys_a = (unsigned long long *) s; s += align256(P * 8);
+    unsigned long long *keys_b = (unsigned long long *) s; s += align256(P * 8);
+    uint32_t *runlen = (uint32_t *) s; s += align256(P * 4);
+    uint32_t *need = (uint32_t *) s; s += align256(P * 4);
+    void *cub_tmp = s;
+    size_t cub_bytes = a->cub_bytes;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(a->tab, 0xFF, gkm_idx_tab_bytes(a->L), st)) != cudaSuccess) goto fail;
+    if (a->wend) gkm_idx_keys_kernel<true><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
+    else gkm_idx_keys_kernel<false><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
+    if ((e = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, (int) P, 8, 32 + 2 * a->L, st)) != cudaSuccess) goto fail;
+    {
+        const unsigned blocks = (unsigned) ((P + 255) / 256);
+        gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, need);
+        uint32_t *ovfofs = (uint32_t *) keys_a; /* the unsorted keys are dead now */
+        cub_bytes = a->cub_bytes;
+        if ((e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, need, ovfofs, (int) P, st)) != cudaSuccess) goto fail;
+        gkm_idx_fill_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, a->tab, a->ovf);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) goto fail;
+    return 0;
+fail:
+    gkm_set_error("CUDA: index build: %s", cudaGetErrorString(e));
+    return 1;
+}
+
+/* ------------------------------------------------------------------ */
+/* hot loop                                                             */
+/* ------------------------------------------------------------------ */
+__device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, int w)
+{
+    const uint32_t b = e & GKM_IDX_COL_MASK;
+    if (b >= blo) atomicAdd(Hm + (b - blo), w * (int) (e >> GKM_IDX_COL_BITS));
+}
+
+/* Inline postings of one slot against the wanted column range [blo, bhi) (lists are sorted by column,
+ * the column field of an empty slot / end marker is all ones).  Returns the overflow list still to be
+ * read, or NULL. */
+__device__ __forceinline__ const uint4 *idx_slot(const uint2 sl, const uint32_t *__restrict__ ovf, int32_t *Hm,
+                                                 uint32_t blo, uint32_t bhi, int w)
+{
+    if ((sl.x & GKM_IDX_COL_MASK) >= bhi) return nullptr;
+    idx_hit(Hm, sl.x, blo, w);
+    const uint32_t y = sl.y;
+    if (!(y & GKM_IDX_PTR)) {
+        if ((y & GKM_IDX_COL_MASK) < bhi) idx_hit(Hm, y, blo, w);
+        return nullptr;
+    }
+    if (y == GKM_IDX_EMPTY) return nullptr;
+    return reinterpret_cast<const uint4 *>(ovf + (y & ~GKM_IDX_PTR));
+}
+
+/* four postings of an overflow list; true while the list may go on */
+__device__ __forceinline__ bool idx_quad(const uint4 q, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+{
+    if ((q.x & GKM_IDX_COL_MASK) >= bhi) return false;
+    idx_hit(Hm, q.x, blo, w);
+    if ((q.y & GKM_IDX_COL_MASK) >= bhi) return false;
+    idx_hit(Hm, q.y, blo, w);
+    if ((q.z & GKM_IDX_COL_MASK) >= bhi) return false;
+    idx_hit(Hm, q.z, blo, w);
+    if ((q.w & GKM_IDX_COL_MASK) >= bhi) return false;
+    idx_hit(Hm, q.w, blo, w);
+    return true;
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(GKM_IDX_THREADS, 1)
+gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gkm_idx_rowargs r)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = (int) threadIdx.x;
+    const int a = p.row_begin + (int) blockIdx.x;
+    const int L = p.L, nb = p.nbins;
+    /* wanted columns of this row inside the block, relative to the block's first column */
+    uint32_t blo = (uint32_t) r.blo, bhi = (uint32_t) r.bhi;
+    if (p.mode == GKM_MODE_LOWER) {
+        const int lim = a - r.cb; /* columns < a only */
+        if (lim <= (int) blo) return;
+        if ((uint32_t) lim < bhi) bhi = (uint32_t) lim;
+    }
+    if (bhi <= blo) return;
+    const int ldh = r.ldh;
+    int32_t *H = reinterpret_cast<int32_t *>(smem);
+    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nb * (size_t) ldh * 4);
+    uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
+
+    const int ncol = (int) (bhi - blo);
+    for (int m = 0; m < nb; m++)
+        for (int i = tid; i < ncol; i += GKM_IDX_THREADS) H[m * ldh + i] = 0;
+    /* forward L-mers of the query (window ending at e, L-1 <= e < len) */
+    const int len = p.lens[a], nq = len - L + 1;
+    {
+        const uint32_t *pl = p.planes + (size_t) a * 3 * (size_t) p.W;
+        const uint32_t mask = (1u << L) - 1u;
+        for (int i = tid; i < nq; i += GKM_IDX_THREADS) {
+            xq[i] = gkm_idx_code(idx_window(pl, p.W, i, mask), idx_window(pl + p.W, p.W, i, mask), L);
+            if (WEIGHTED) wq[i] = p.wend[(size_t) a * 32 * (size_t) p.W + (size_t) (i + L - 1)];
+        }
+    }
+    __syncthreads();
+
+    /* probes: tiles of <= 1024 masks; inside a tile a thread keeps its mask and walks the query
+     * L-mers, GKM_IDX_UNROLL independent slot loads in flight.  A short tile is shared by several
+     * "phases" of threads that take interleaved query L-mers. */
+    const uint2 *__restrict__ tab = r.tab;
+    for (int t0 = 0; t0 < r.ndelta; t0 += GKM_IDX_THREADS) {
+        const int rem = min(GKM_IDX_THREADS, r.ndelta - t0);
+        int T = (rem + 31) & ~31;
+        if (rem < 32) { T = 1; while (T < rem) T <<= 1; }
+        const int nph = GKM_IDX_THREADS / T;
+        const int ph = tid / T, tt = tid - ph * T;
+        if (ph >= nph || tt >= rem) continue;
+        const uint32_t dl = r.deltas[t0 + tt];
+        const uint32_t dx = dl & 0x0FFFFFFFu;
+        int32_t *Hm = H + (int) (dl >> 28) * ldh;
+        for (int xi = ph; xi < nq; xi += nph * GKM_IDX_UNROLL) {
+            uint2 sl[GKM_IDX_UNROLL];
+            int w[GKM_IDX_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+                const int x = xi + u * nph;
+                if (x < nq) {
+                    sl[u] = tab[xq[x] ^ dx];
+                    w[u] = WEIGHTED ? (int) wq[x] : 1;
+                } else {
+                    sl[u] = make_uint2(GKM_IDX_EMPTY, GKM_IDX_EMPTY);
+                    w[u] = 0;
+                }
+            }
+            /* inline postings, then the overflow lists of all GKM_IDX_UNROLL probes 16 bytes at a time */
+            const uint4 *ql[GKM_IDX_UNROLL];
+            uint4 qv[GKM_IDX_UNROLL];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+                ql[u] = idx_slot(sl[u], r.ovf, Hm, blo, bhi, w[u]);
+                if (ql[u]) { qv[u] = __ldg(ql[u]); any = true; }
+            }
+            while (any) {
+                any = false;
+#pragma unroll
+                for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+                    if (!ql[u]) continue;
+                    if (idx_quad(qv[u], Hm, blo, bhi, w[u])) { qv[u] = __ldg(++ql[u]); any = true; }
+                    else ql[u] = nullptr;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    /* epilogue: histogram -> normalised double, the reference's operation order */
+    double dsum = 0.0;
+    const double sqa = (p.out || p.decision) ? p.sqnorm[a] : 1.0;
+    for (int i = tid; i < ncol; i += GKM_IDX_THREADS) {
+        const int b_g = r.cb + (int) blo + i;
+        double kraw = 0.0;
+        if (p.hist) {
+            int32_t *dst = p.hist + ((size_t) (a - p.row_base) * (size_t) p.hist_cols + (size_t) (b_g - p.col_base)) * (size_t) nb;
+            for (int m = 0; m < nb; m++) dst[m] = H[m * ldh + i];
+        }
+        if (!p.out && !p.decision) continue;
+        for (int m = 0; m < nb; m++) kraw = __dadd_rn(kraw, __dmul_rn(p.w[m], (double) H[m * ldh + i]));
+        double v = __ddiv_rn(kraw, __dmul_rn(sqa, p.sqnorm[b_g]));
+        if (p.kernel_type == 3 || p.kernel_type == 5) v = exp(__dmul_rn(p.gamma, __dadd_rn(v, -1.0)));
+        if (p.out) p.out[(size_t) (a - p.row_base) * (size_t) p.ld + (size_t) (b_g - p.col_base)] = v;
+        if (p.decision) dsum += p.alpha[b_g - p.col_base] * v;
+    }
+    if (p.decision) {
+        __shared__ double red[GKM_IDX_THREADS / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_down_sync(0xFFFFFFFFu, dsum, o);
+        if ((tid & 31) == 0) red[tid >> 5] = dsum;
+        __syncthreads();
+        if (tid < 32) {
+            double s = red[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+            if (tid == 0) atomicAdd(p.decision + (a - p.row_base), s);
+        }
+    }
+}
+
+unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted)
+{
+    size_t s = (size_t) nbins * (size_t) ldh * 4 + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
+    return (unsigned) ((s + 15) & ~(size_t) 15);
+}
+
+int gkm_idx_max_cols(int nbins, int maxq, int weighted)
+{
+    const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - (long long) maxq * (weighted ? 5 : 4);
+    long long cols = budget / (4LL * nbins);
+    cols &= ~31LL;
+    if (cols > (long long) GKM_IDX_MAX_COLS) cols = GKM_IDX_MAX_COLS & ~31;
+    return cols < 32 ? 0 : (int) cols;
+}
+
+int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted, cudaStream_t st)
+{
+    const int rows = kp->row_end - kp->row_begin;
+    if (rows <= 0 || ra->bhi <= ra->blo) return 0;
+    const void *fn = weighted ? (const void *) gkm_index_rows_kernel<true> : (const void *) gkm_index_rows_kernel<false>;
+    const unsigned smem = gkm_idx_row_smem(kp->nbins, ra->ldh, ra->maxq, weighted);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e == cudaSuccess) {
+        void *args[] = { (void *) kp, (void *) ra };
+        e = cudaLaunchKernel(fn, dim3((unsigned) rows, 1, 1), dim3(GKM_IDX_THREADS, 1, 1), args, smem, st);
+    }
+    if (e != cudaSuccess) { gkm_set_error("CUDA: index row kernel (%u bytes of shared memory): %s", smem, cudaGetErrorString(e)); return 1; }
+    return 0;
+}

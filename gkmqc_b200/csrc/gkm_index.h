@@ -1,0 +1,81 @@
+/* gkm_index.h -- kernel variant "index": inverted L-mer index + neighbour enumeration.
+ *
+ * Candidate (c) next to the north star's (a) bit-sliced XOR/POPC and (b) tcgen05 one-hot
+ * GEMM.  It replaces the same reference code as they do -- kmertree_dfs +
+ * gkmkernel_kernelfunc_batch_single (libgkm.c:315-387,:553-589) -- and, like the
+ * reference's k-mer tree, avoids touching L-mer pairs that are more than d mismatches
+ * apart, but by a different construction that suits the GPU:
+ *
+ *   target side   every L-mer of both strands of the columns [cb, ce) is a POSTING
+ *                 (column - cb, positional weight); postings are sorted by (L-mer,
+ *                 column) and laid out in a direct-addressed table of 4^L eight-byte
+ *                 slots {first posting, second posting | overflow pointer}.  The table
+ *                 (33.5 MB at L = 11) stays in the 126 MB L2.
+ *   query side    for every forward L-mer x of row a and every XOR mask `delta` with at
+ *                 most d non-zero 2-bit fields (sum_m C(L,m) 3^m of them: 4984 at L=11,
+ *                 d=3) the slot of y = x ^ delta is fetched; each posting (b, wt) found
+ *                 there is one L-mer pair at Hamming distance m = weight(delta), added as
+ *                 wt_a * wt_b to the row histogram H[m][b] held in shared memory.
+ *
+ * Work per entry is ~290 slot probes + ~200 shared atomics instead of 168 200 pair
+ * evaluations; the bound is the L1/LSU sector rate of the random slot probes, not the
+ * integer pipe.  Counting is exact, so the integer histograms are the
+ * same ones the reference's DFS produces.
+ *
+ * This header holds what host C, the CPU tests and the CUDA code share: the L-mer code,
+ * the posting / slot encoding and the delta list.
+ */
+#ifndef GKM_INDEX_H_INCLUDED
+#define GKM_INDEX_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GKM_IDX_MAX_L 14              /* 4^14 slots = 2 GiB; beyond that the variant is refused */
+#define GKM_IDX_EMPTY 0xFFFFFFFFu     /* slot.x: no posting; slot.y: no second posting; overflow list: end */
+#define GKM_IDX_PTR 0x80000000u       /* slot.y: bits 0..30 = offset of postings 1.. in the overflow array */
+#define GKM_IDX_COL_BITS 23
+#define GKM_IDX_COL_MASK 0x007FFFFFu  /* posting = column | weight << 23, bit 31 clear */
+#define GKM_IDX_MAX_COLS 0x007FFFFEu
+
+#if defined(__CUDACC__)
+#define GKM_IDX_HD __host__ __device__ __forceinline__
+#else
+#define GKM_IDX_HD static inline
+#endif
+
+/* table address of an L-mer given its two L-bit plane windows (bit t = base t of the window).
+ * Base 0 occupies the two lowest bits so that the four L-mers that differ only there share one
+ * 32-byte sector of the table; the other bases stay planar. */
+GKM_IDX_HD uint32_t gkm_idx_code(uint32_t p0, uint32_t p1, int L)
+{
+    return (p0 & 1u) | ((p1 & 1u) << 1) | ((p0 >> 1) << 2) | ((p1 >> 1) << (L + 1));
+}
+
+GKM_IDX_HD uint32_t gkm_idx_posting(uint32_t col, uint32_t wt) { return col | (wt << GKM_IDX_COL_BITS); }
+
+/* number of XOR masks with at most d substituted bases: sum_{m<=d} C(L,m) 3^m (0 if it overflows 2^31) */
+long long gkm_idx_delta_count(int L, int d);
+
+/* the masks, in probe order: out[i] = mask | m << 28.  First the groups of four that differ only in
+ * base 0 (adjacent lanes -> one sector), then the masks with d substitutions all outside base 0.
+ * Returns the number written (= gkm_idx_delta_count), or -1. */
+long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap);
+
+/* is the variant applicable at all (table and masks representable)? */
+int gkm_idx_supported(int L, int d, int nbins);
+
+/* rough cost model used by kernel = auto: estimated device milliseconds */
+double gkm_idx_cost_ms(int L, int d, long long rows, double mean_query_lmers, int col_blocks, long long entries,
+                       double mean_pairs_per_entry);
+double gkm_diag_cost_ms(int d, int weighted, long long entries, double mean_pairs_per_entry);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GKM_INDEX_H_INCLUDED */

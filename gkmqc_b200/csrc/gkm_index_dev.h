@@ -1,0 +1,48 @@
+/* gkm_index_dev.h -- device-side interface of the "index" variant (gkm_index.cu), used by gkm_device.cu */
+#ifndef GKM_INDEX_DEV_H_INCLUDED
+#define GKM_INDEX_DEV_H_INCLUDED
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gkm_index.h"
+#include "gkm_kparams.h"
+
+/* the index of one block of columns [cb, ce) on one GPU */
+struct gkm_idx_block {
+    int cb, ce;
+    uint2 *tab;          /* 4^L slots */
+    uint32_t *ovf;       /* overflow lists (16-byte aligned, padded with end markers), <= 2P entries */
+    size_t tab_bytes, ovf_bytes; /* block sizes as handed out by the pool */
+    int built;
+};
+
+struct gkm_idx_build_args {
+    const uint32_t *planes; const int32_t *lens; const uint8_t *wend; /* wend = NULL: unit weights */
+    int W, L, cb, ce;
+    const uint32_t *offs;  /* device, [ce - cb]: first posting of every column (2 * (len - L + 1) each) */
+    size_t P;              /* postings of the block */
+    void *scratch;         /* gkm_idx_scratch_bytes(P, L) bytes */
+    size_t cub_bytes;
+    uint2 *tab; uint32_t *ovf;
+};
+
+struct gkm_idx_rowargs {
+    const uint2 *tab; const uint32_t *ovf; const uint32_t *deltas;
+    int ndelta;
+    int cb;        /* first column of the index block */
+    int blo, bhi;  /* wanted columns, relative to cb */
+    int ldh;       /* histogram row stride in shared memory (>= bhi - blo) */
+    int maxq;      /* upper bound of query L-mers per row */
+};
+
+size_t gkm_idx_tab_bytes(int L);
+size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out);
+int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st);
+/* most columns one block may hold so that nbins histogram rows + the query fit 227 KB of shared memory (0: none) */
+int gkm_idx_max_cols(int nbins, int maxq, int weighted);
+unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted);
+/* rows [kp->row_begin, kp->row_end) against the wanted columns of one block; outputs as in gkm_kparams */
+int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted, cudaStream_t st);
+
+#endif

@@ -1,0 +1,106 @@
+/* gkm_index_host.c -- host logic of the "index" kernel variant (gkm_index.h): the list of
+ * XOR masks a query L-mer is probed with, applicability, and the cost model behind
+ * kernel = auto.  Pure C, no CUDA: covered by the CPU test tier. */
+#include <math.h>
+
+#include "gkm_index.h"
+
+static long long binom(int n, int k)
+{
+    if (k < 0 || k > n) return 0;
+    long long r = 1;
+    for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+    return r;
+}
+
+long long gkm_idx_delta_count(int L, int d)
+{
+    if (L < 1 || d < 0) return 0;
+    if (d > L) d = L;
+    long long total = 0, p3 = 1;
+    for (int m = 0; m <= d; m++) {
+        total += binom(L, m) * p3;
+        if (total > 0x7FFFFFFFLL) return 0;
+        p3 *= 3;
+    }
+    return total;
+}
+
+/* mask of a substitution by XOR value v (1..3) at base t (gkm_idx_code layout) */
+static uint32_t sub_mask(int t, int v, int L)
+{
+    if (t == 0) return (uint32_t) v;
+    return ((uint32_t) (v & 1) << (t + 1)) | ((uint32_t) (v >> 1) << (t + L));
+}
+
+/* all masks over bases 1..L-1 with exactly `m` substitutions, appended through `emit` */
+struct emit_ctx {
+    uint32_t *out;
+    long long n, cap;
+    int L, d, pass; /* pass 0: groups of four (m < d), pass 1: singles (m == d) */
+};
+
+static void emit_upper(struct emit_ctx *c, uint32_t du, int m)
+{
+    if (c->pass == 0) {
+        for (int last = 0; last < 4; last++) {
+            if (c->n < c->cap) c->out[c->n] = (du | (uint32_t) last) | ((uint32_t) (m + (last != 0)) << 28);
+            c->n++;
+        }
+    } else {
+        if (c->n < c->cap) c->out[c->n] = du | ((uint32_t) m << 28);
+        c->n++;
+    }
+}
+
+static void rec_upper(struct emit_ctx *c, int first, int left, uint32_t du, int m)
+{
+    if (left == 0) { emit_upper(c, du, m); return; }
+    for (int t = first; t <= c->L - left; t++)
+        for (int v = 1; v <= 3; v++) rec_upper(c, t + 1, left - 1, du | sub_mask(t, v, c->L), m);
+}
+
+long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap)
+{
+    if (L < 1 || L > GKM_IDX_MAX_L || d < 0 || d > 15 || !out) return -1;
+    if (d > L) d = L;
+    struct emit_ctx c;
+    c.out = out; c.n = 0; c.cap = cap; c.L = L; c.d = d;
+    c.pass = 0;
+    for (int mu = 0; mu < d && mu <= L - 1; mu++) rec_upper(&c, 1, mu, 0u, mu);
+    c.pass = 1;
+    if (d <= L - 1) rec_upper(&c, 1, d, 0u, d);
+    return (c.n <= cap) ? c.n : -1;
+}
+
+int gkm_idx_supported(int L, int d, int nbins)
+{
+    if (L < 2 || L > GKM_IDX_MAX_L) return 0;
+    if (d < 0 || d > 15 || nbins != d + 1) return 0;
+    const long long nd = gkm_idx_delta_count(L, d);
+    return nd > 0 && nd <= (64LL << 20); /* the mask list itself must stay small (256 MB) */
+}
+
+/* Device-time estimates, from round-1 measurements on one B200:
+ *   probes  2.6e11 /s while the slot table sits in L2 (<= 64 MB), ~1.3e11 /s beyond;
+ *   hits    3e12 shared atomics /s;
+ *   build   ~3 ms per column block;
+ *   diag    2.94e13 L-mer pairs /s (d <= 3), 2.3e13 (d = 4), ~1.2e13 (d <= 7), ~6e12 above;
+ *           the weighted types run at ~0.6 of that. */
+double gkm_idx_cost_ms(int L, int d, long long rows, double mean_query_lmers, int col_blocks, long long entries,
+                       double mean_pairs_per_entry)
+{
+    const double nd = (double) gkm_idx_delta_count(L, d);
+    const double slots = pow(4.0, (double) L);
+    const double probe_rate = (slots * 8.0 <= 64.0 * 1048576.0) ? 2.6e11 : 1.3e11;
+    const double probes = (double) rows * mean_query_lmers * nd * (double) col_blocks;
+    const double hits = (double) entries * mean_pairs_per_entry * nd / slots;
+    return 1e3 * (probes / probe_rate + hits / 3e12) + 3.0 * (double) col_blocks + slots * 8.0 / 3e12 * 1e3;
+}
+
+double gkm_diag_cost_ms(int d, int weighted, long long entries, double mean_pairs_per_entry)
+{
+    double rate = (d <= 3) ? 2.94e13 : (d == 4) ? 2.3e13 : (d <= 7) ? 1.2e13 : 6e12;
+    if (weighted) rate *= 0.6;
+    return 1e3 * (double) entries * mean_pairs_per_entry / rate;
+}

@@ -1,7 +1,8 @@
 /* gkm_options.c -- process-wide knobs.  The reference's whole configuration surface is
  * the gkmOpt struct (libgkm.h:149-161), which cannot grow without breaking the ABI, so
  * everything GPU-specific comes from gkmb200_set_option() or the environment:
- *   GKM_KERNEL   = auto | lmer | diag | mma   kernel variant (mma = tcgen05 one-hot GEMM candidate)
+ *   GKM_KERNEL   = auto | lmer | diag | mma | index   kernel variant (mma = tcgen05 one-hot GEMM candidate,
+ *                                           index = inverted L-mer index; auto picks diag or index by a cost model)
  *   GKM_MAX_L    = 12 | 16                 ceiling of the parameter gate in gkm_main_pywrapper
  *   GKM_CHUNK_MB = n                       upper bound of one chunk's dense output
  *   GKM_DEVICES  = "0,1,.."                GPUs to use (gkm_device.cu)
@@ -25,6 +26,7 @@ static int parse_kernel(const char *v, int *out)
     else if (!strcmp(v, "lmer")) *out = GKM_KERNEL_LMER;
     else if (!strcmp(v, "diag")) *out = GKM_KERNEL_DIAG;
     else if (!strcmp(v, "mma")) *out = GKM_KERNEL_MMA;
+    else if (!strcmp(v, "index")) *out = GKM_KERNEL_INDEX;
     else return 1;
     return 0;
 }
@@ -52,7 +54,7 @@ int gkmb200_set_option(const char *key, const char *value)
     load_env();
     if (!key || !value) { gkm_set_error("null option"); return 1; }
     if (!strcmp(key, "kernel")) {
-        if (parse_kernel(value, &g_kernel)) { gkm_set_error("kernel must be auto, lmer, diag or mma"); return 1; }
+        if (parse_kernel(value, &g_kernel)) { gkm_set_error("kernel must be auto, lmer, diag, mma or index"); return 1; }
         return 0;
     }
     int x = atoi(value);

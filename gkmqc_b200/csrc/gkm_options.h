@@ -3,7 +3,7 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-enum { GKM_KERNEL_AUTO = 0, GKM_KERNEL_LMER = 1, GKM_KERNEL_DIAG = 2, GKM_KERNEL_MMA = 3 };
+enum { GKM_KERNEL_AUTO = 0, GKM_KERNEL_LMER = 1, GKM_KERNEL_DIAG = 2, GKM_KERNEL_MMA = 3, GKM_KERNEL_INDEX = 4 };
 int gkm_opt_kernel(void);
 int gkm_opt_max_L(void);
 int gkm_opt_chunk_mb(void);

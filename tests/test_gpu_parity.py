@@ -25,7 +25,7 @@ def _need_gpu():
         pytest.fail("no B200 visible; the product has no CPU fallback")
 
 
-@pytest.fixture(params=["diag", "lmer", "mma"])
+@pytest.fixture(params=["diag", "lmer", "mma", "index"])
 def variant(request):
     capi.set_option("kernel", request.param)
     yield request.param
@@ -52,7 +52,7 @@ def test_golden_histograms_and_kernel(name, variant):
         K = P.kernel_lower()
         check_kmat(K, g["kmat"], cfg["kernel_type"])
         st = P.stats()
-        assert st["launches"] > 0 and st["kernel_variant"] == {"lmer": 1, "diag": 2, "mma": 3}[variant]
+        assert st["launches"] > 0 and st["kernel_variant"] == {"lmer": 1, "diag": 2, "mma": 3, "index": 4}[variant]
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names() if int(n.split("_L")[1].split("k")[0]) <= 12])
