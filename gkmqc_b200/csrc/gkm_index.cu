@@ -4,9 +4,9 @@
  *   gkm_idx_keys_kernel   every valid L-mer window of both strands of the block's columns ->
  *                         64-bit key  code << 32 | column << 8 | weight
  *   cub radix sort        by (code, column)            [library call, set-up only]
- *   gkm_idx_runs_kernel   run length of every distinct code; overflow demand of runs >= 3
+ *   gkm_idx_runs_kernel   run length of every distinct code; overflow demand of runs >= 5
  *   cub exclusive scan    overflow offsets             [library call, set-up only]
- *   gkm_idx_fill_kernel   slots {posting 0, posting 1 | pointer} and overflow lists
+ *   gkm_idx_fill_kernel   slots {posting 0, 1, 2, posting 3 | pointer} and overflow lists
  * Hot loop:
  *   gkm_index_rows_kernel one CTA of 1024 threads per query row; histogram row in shared
  *                         memory; fused fp64 epilogue identical to the other variants
@@ -93,12 +93,12 @@ gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, uin
         len = idx_upper(keys, lo, hi, code) - i;
     }
     runlen[i] = len;
-    need[i] = (len >= 3) ? ((len + 3u) & ~3u) : 0u; /* postings 1.. of the run plus end markers up to a multiple of 4 */
+    need[i] = (len >= 5) ? ((len - 3u + 4u) & ~3u) : 0u; /* postings 3.. of the run plus end markers up to a multiple of 4 */
 }
 
 __global__ void __launch_bounds__(256)
 gkm_idx_fill_kernel(const unsigned long long *__restrict__ keys, uint32_t P, const uint32_t *__restrict__ runlen,
-                    const uint32_t *__restrict__ ovfofs, uint2 *__restrict__ tab, uint32_t *__restrict__ ovf)
+                    const uint32_t *__restrict__ ovfofs, uint4 *__restrict__ tab, uint32_t *__restrict__ ovf)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -120,21 +120,19 @@ gkm_idx_fill_kernel(const unsigned long long *__restrict__ keys, uint32_t P, con
     const uint32_t len = runlen[lb], r = i - lb;
     const uint32_t posting = gkm_idx_posting((uint32_t) (key >> 8) & GKM_IDX_COL_MASK, (uint32_t) key & 0xFFu);
     uint32_t *slot = reinterpret_cast<uint32_t *>(tab + code);
-    if (r == 0) {
-        slot[0] = posting;
-        if (len >= 3) {
-            slot[1] = GKM_IDX_PTR | ovfofs[lb];
-            const uint32_t end = (len + 3u) & ~3u; /* lists are read 16 bytes at a time */
-            for (uint32_t t = len - 1; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_EMPTY;
-        }
-    } else if (len == 2) {
-        slot[1] = posting;
+    if (r < 3 || (r == 3 && len == 4)) {
+        slot[r] = posting;
     } else {
-        ovf[ovfofs[lb] + r - 1] = posting;
+        ovf[ovfofs[lb] + r - 3] = posting;
+    }
+    if (r == 0 && len >= 5) {
+        slot[3] = GKM_IDX_PTR | ovfofs[lb];
+        const uint32_t end = (len - 3u + 4u) & ~3u; /* lists are read 16 bytes at a time */
+        for (uint32_t t = len - 3; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_EMPTY;
     }
 }
 
-size_t gkm_idx_tab_bytes(int L) { return ((size_t) 1 << (2 * L)) * sizeof(uint2); }
+size_t gkm_idx_tab_bytes(int L) { return ((size_t) 1 << (2 * L)) * sizeof(uint4); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 
@@ -183,44 +181,43 @@ fail:
 /* ------------------------------------------------------------------ */
 /* hot loop                                                             */
 /* ------------------------------------------------------------------ */
-__device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, int w)
+/* one posting against the wanted column range [blo, bhi): the column field of an empty word / end marker is
+ * all ones, so `b < bhi` is the validity test as well */
+template <bool WEIGHTED, bool RANGE>
+__device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, uint32_t bhi, int w)
 {
     const uint32_t b = e & GKM_IDX_COL_MASK;
-    if (b >= blo) atomicAdd(Hm + (b - blo), w * (int) (e >> GKM_IDX_COL_BITS));
+    bool ok = b < bhi;
+    if (RANGE) ok = ok && b >= blo;
+    if (ok) atomicAdd(Hm + (RANGE ? b - blo : b), WEIGHTED ? w * (int) (e >> GKM_IDX_COL_BITS) : 1);
 }
 
-/* Inline postings of one slot against the wanted column range [blo, bhi) (lists are sorted by column,
- * the column field of an empty slot / end marker is all ones).  Returns the overflow list still to be
- * read, or NULL. */
-__device__ __forceinline__ const uint4 *idx_slot(const uint2 sl, const uint32_t *__restrict__ ovf, int32_t *Hm,
-                                                 uint32_t blo, uint32_t bhi, int w)
+/* the postings of one slot; lists are sorted by column, so the tail of a list is skipped as soon as one
+ * posting falls behind the range */
+template <bool WEIGHTED, bool RANGE>
+__device__ __forceinline__ void idx_slot(const uint4 sl, const uint32_t *__restrict__ ovf, int32_t *Hm,
+                                         uint32_t blo, uint32_t bhi, int w)
 {
-    if ((sl.x & GKM_IDX_COL_MASK) >= bhi) return nullptr;
-    idx_hit(Hm, sl.x, blo, w);
-    const uint32_t y = sl.y;
-    if (!(y & GKM_IDX_PTR)) {
-        if ((y & GKM_IDX_COL_MASK) < bhi) idx_hit(Hm, y, blo, w);
-        return nullptr;
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.x, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.y, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.z, blo, bhi, w);
+    if (!(sl.w & GKM_IDX_PTR)) {
+        idx_hit<WEIGHTED, RANGE>(Hm, sl.w, blo, bhi, w);
+    } else if (sl.w != GKM_IDX_EMPTY && (sl.z & GKM_IDX_COL_MASK) < bhi) {
+        /* five or more postings (1.7 % of the slots at 10k x 300 bp): the rest, 16 bytes at a time */
+        const uint4 *q = reinterpret_cast<const uint4 *>(ovf + (sl.w & ~GKM_IDX_PTR));
+        for (;;) {
+            const uint4 v = __ldg(q++);
+            idx_hit<WEIGHTED, RANGE>(Hm, v.x, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE>(Hm, v.y, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE>(Hm, v.z, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE>(Hm, v.w, blo, bhi, w);
+            if ((v.w & GKM_IDX_COL_MASK) >= bhi) break;
+        }
     }
-    if (y == GKM_IDX_EMPTY) return nullptr;
-    return reinterpret_cast<const uint4 *>(ovf + (y & ~GKM_IDX_PTR));
 }
 
-/* four postings of an overflow list; true while the list may go on */
-__device__ __forceinline__ bool idx_quad(const uint4 q, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
-{
-    if ((q.x & GKM_IDX_COL_MASK) >= bhi) return false;
-    idx_hit(Hm, q.x, blo, w);
-    if ((q.y & GKM_IDX_COL_MASK) >= bhi) return false;
-    idx_hit(Hm, q.y, blo, w);
-    if ((q.z & GKM_IDX_COL_MASK) >= bhi) return false;
-    idx_hit(Hm, q.z, blo, w);
-    if ((q.w & GKM_IDX_COL_MASK) >= bhi) return false;
-    idx_hit(Hm, q.w, blo, w);
-    return true;
-}
-
-template <bool WEIGHTED>
+template <bool WEIGHTED, bool RANGE>
 __global__ void __launch_bounds__(GKM_IDX_THREADS, 1)
 gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gkm_idx_rowargs r)
 {
@@ -259,7 +256,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     /* probes: tiles of <= 1024 masks; inside a tile a thread keeps its mask and walks the query
      * L-mers, GKM_IDX_UNROLL independent slot loads in flight.  A short tile is shared by several
      * "phases" of threads that take interleaved query L-mers. */
-    const uint2 *__restrict__ tab = r.tab;
+    const uint4 *__restrict__ tab = r.tab;
     for (int t0 = 0; t0 < r.ndelta; t0 += GKM_IDX_THREADS) {
         const int rem = min(GKM_IDX_THREADS, r.ndelta - t0);
         int T = (rem + 31) & ~31;
@@ -270,39 +267,18 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
         const uint32_t dl = r.deltas[t0 + tt];
         const uint32_t dx = dl & 0x0FFFFFFFu;
         int32_t *Hm = H + (int) (dl >> 28) * ldh;
-        for (int xi = ph; xi < nq; xi += nph * GKM_IDX_UNROLL) {
-            uint2 sl[GKM_IDX_UNROLL];
-            int w[GKM_IDX_UNROLL];
+        const int step = nph * GKM_IDX_UNROLL;
+        int xi = ph;
+        for (; xi + (GKM_IDX_UNROLL - 1) * nph < nq; xi += step) {
+            uint4 sl[GKM_IDX_UNROLL];
 #pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
-                const int x = xi + u * nph;
-                if (x < nq) {
-                    sl[u] = tab[xq[x] ^ dx];
-                    w[u] = WEIGHTED ? (int) wq[x] : 1;
-                } else {
-                    sl[u] = make_uint2(GKM_IDX_EMPTY, GKM_IDX_EMPTY);
-                    w[u] = 0;
-                }
-            }
-            /* inline postings, then the overflow lists of all GKM_IDX_UNROLL probes 16 bytes at a time */
-            const uint4 *ql[GKM_IDX_UNROLL];
-            uint4 qv[GKM_IDX_UNROLL];
-            bool any = false;
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) sl[u] = __ldg(tab + (xq[xi + u * nph] ^ dx));
 #pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
-                ql[u] = idx_slot(sl[u], r.ovf, Hm, blo, bhi, w[u]);
-                if (ql[u]) { qv[u] = __ldg(ql[u]); any = true; }
-            }
-            while (any) {
-                any = false;
-#pragma unroll
-                for (int u = 0; u < GKM_IDX_UNROLL; u++) {
-                    if (!ql[u]) continue;
-                    if (idx_quad(qv[u], Hm, blo, bhi, w[u])) { qv[u] = __ldg(++ql[u]); any = true; }
-                    else ql[u] = nullptr;
-                }
-            }
+            for (int u = 0; u < GKM_IDX_UNROLL; u++)
+                idx_slot<WEIGHTED, RANGE>(sl[u], r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi + u * nph] : 1);
         }
+        for (; xi < nq; xi += nph)
+            idx_slot<WEIGHTED, RANGE>(__ldg(tab + (xq[xi] ^ dx)), r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
     }
     __syncthreads();
 
@@ -320,7 +296,8 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
         for (int m = 0; m < nb; m++) kraw = __dadd_rn(kraw, __dmul_rn(p.w[m], (double) H[m * ldh + i]));
         double v = __ddiv_rn(kraw, __dmul_rn(sqa, p.sqnorm[b_g]));
         if (p.kernel_type == 3 || p.kernel_type == 5) v = exp(__dmul_rn(p.gamma, __dadd_rn(v, -1.0)));
-        if (p.out) p.out[(size_t) (a - p.row_base) * (size_t) p.ld + (size_t) (b_g - p.col_base)] = v;
+        /* streaming store: the matrix is written once and must not push the slot table out of L2 */
+        if (p.out) __stcs(p.out + (size_t) (a - p.row_base) * (size_t) p.ld + (size_t) (b_g - p.col_base), v);
         if (p.decision) dsum += p.alpha[b_g - p.col_base] * v;
     }
     if (p.decision) {
@@ -357,7 +334,9 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
 {
     const int rows = kp->row_end - kp->row_begin;
     if (rows <= 0 || ra->bhi <= ra->blo) return 0;
-    const void *fn = weighted ? (const void *) gkm_index_rows_kernel<true> : (const void *) gkm_index_rows_kernel<false>;
+    const bool range = ra->blo != 0;
+    const void *fn = weighted ? (range ? (const void *) gkm_index_rows_kernel<true, true> : (const void *) gkm_index_rows_kernel<true, false>)
+                              : (range ? (const void *) gkm_index_rows_kernel<false, true> : (const void *) gkm_index_rows_kernel<false, false>);
     const unsigned smem = gkm_idx_row_smem(kp->nbins, ra->ldh, ra->maxq, weighted);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess) {

@@ -8,9 +8,9 @@
  *
  *   target side   every L-mer of both strands of the columns [cb, ce) is a POSTING
  *                 (column - cb, positional weight); postings are sorted by (L-mer,
- *                 column) and laid out in a direct-addressed table of 4^L eight-byte
- *                 slots {first posting, second posting | overflow pointer}.  The table
- *                 (33.5 MB at L = 11) stays in the 126 MB L2.
+ *                 column) and laid out in a direct-addressed table of 4^L sixteen-byte
+ *                 slots {posting 0, 1, 2, posting 3 | overflow pointer}.  The table
+ *                 (67 MB at L = 11) stays in the 126 MB L2.
  *   query side    for every forward L-mer x of row a and every XOR mask `delta` with at
  *                 most d non-zero 2-bit fields (sum_m C(L,m) 3^m of them: 4984 at L=11,
  *                 d=3) the slot of y = x ^ delta is fetched; each posting (b, wt) found
@@ -35,9 +35,9 @@
 extern "C" {
 #endif
 
-#define GKM_IDX_MAX_L 14              /* 4^14 slots = 2 GiB; beyond that the variant is refused */
-#define GKM_IDX_EMPTY 0xFFFFFFFFu     /* slot.x: no posting; slot.y: no second posting; overflow list: end */
-#define GKM_IDX_PTR 0x80000000u       /* slot.y: bits 0..30 = offset of postings 1.. in the overflow array */
+#define GKM_IDX_MAX_L 14              /* 4^14 slots = 4 GiB; beyond that the variant is refused */
+#define GKM_IDX_EMPTY 0xFFFFFFFFu     /* no posting here / end of an overflow list */
+#define GKM_IDX_PTR 0x80000000u       /* slot.w: bits 0..30 = offset of postings 3.. in the overflow array */
 #define GKM_IDX_COL_BITS 23
 #define GKM_IDX_COL_MASK 0x007FFFFFu  /* posting = column | weight << 23, bit 31 clear */
 #define GKM_IDX_MAX_COLS 0x007FFFFEu
@@ -49,11 +49,17 @@ extern "C" {
 #endif
 
 /* table address of an L-mer given its two L-bit plane windows (bit t = base t of the window).
- * Base 0 occupies the two lowest bits so that the four L-mers that differ only there share one
- * 32-byte sector of the table; the other bases stay planar. */
+ * The first GKM_IDX_LOWB bases occupy the lowest bits, two bits each, so that the L-mers that differ
+ * only there share one 128-byte line of the table (16 slots; the four that differ only in base 0
+ * share a 32-byte sector); the other bases stay planar. */
+#define GKM_IDX_LOWB 2
+GKM_IDX_HD int gkm_idx_lowb(int L) { return L < GKM_IDX_LOWB ? L : GKM_IDX_LOWB; }
 GKM_IDX_HD uint32_t gkm_idx_code(uint32_t p0, uint32_t p1, int L)
 {
-    return (p0 & 1u) | ((p1 & 1u) << 1) | ((p0 >> 1) << 2) | ((p1 >> 1) << (L + 1));
+    const int lb = gkm_idx_lowb(L);
+    uint32_t c = ((p0 >> lb) << (2 * lb)) | ((p1 >> lb) << (L + lb));
+    for (int t = 0; t < lb; t++) c |= (((p0 >> t) & 1u) | (((p1 >> t) & 1u) << 1)) << (2 * t);
+    return c;
 }
 
 GKM_IDX_HD uint32_t gkm_idx_posting(uint32_t col, uint32_t wt) { return col | (wt << GKM_IDX_COL_BITS); }
@@ -61,8 +67,8 @@ GKM_IDX_HD uint32_t gkm_idx_posting(uint32_t col, uint32_t wt) { return col | (w
 /* number of XOR masks with at most d substituted bases: sum_{m<=d} C(L,m) 3^m (0 if it overflows 2^31) */
 long long gkm_idx_delta_count(int L, int d);
 
-/* the masks, in probe order: out[i] = mask | m << 28.  First the groups of four that differ only in
- * base 0 (adjacent lanes -> one sector), then the masks with d substitutions all outside base 0.
+/* the masks, in probe order: out[i] = mask | m << 28.  Masks that differ only in the low bases are
+ * adjacent (adjacent lanes -> one line of the table), largest groups first.
  * Returns the number written (= gkm_idx_delta_count), or -1. */
 long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap);
 

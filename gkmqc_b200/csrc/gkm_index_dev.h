@@ -11,7 +11,7 @@
 /* the index of one block of columns [cb, ce) on one GPU */
 struct gkm_idx_block {
     int cb, ce;
-    uint2 *tab;          /* 4^L slots */
+    uint4 *tab;          /* 4^L slots of 16 bytes: postings 0..2, posting 3 or pointer */
     uint32_t *ovf;       /* overflow lists (16-byte aligned, padded with end markers), <= 2P entries */
     size_t tab_bytes, ovf_bytes; /* block sizes as handed out by the pool */
     int built;
@@ -24,11 +24,11 @@ struct gkm_idx_build_args {
     size_t P;              /* postings of the block */
     void *scratch;         /* gkm_idx_scratch_bytes(P, L) bytes */
     size_t cub_bytes;
-    uint2 *tab; uint32_t *ovf;
+    uint4 *tab; uint32_t *ovf;
 };
 
 struct gkm_idx_rowargs {
-    const uint2 *tab; const uint32_t *ovf; const uint32_t *deltas;
+    const uint4 *tab; const uint32_t *ovf; const uint32_t *deltas;
     int ndelta;
     int cb;        /* first column of the index block */
     int blo, bhi;  /* wanted columns, relative to cb */

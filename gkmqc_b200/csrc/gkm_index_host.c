@@ -29,35 +29,36 @@ long long gkm_idx_delta_count(int L, int d)
 /* mask of a substitution by XOR value v (1..3) at base t (gkm_idx_code layout) */
 static uint32_t sub_mask(int t, int v, int L)
 {
-    if (t == 0) return (uint32_t) v;
-    return ((uint32_t) (v & 1) << (t + 1)) | ((uint32_t) (v >> 1) << (t + L));
+    const int lb = gkm_idx_lowb(L);
+    if (t < lb) return (uint32_t) v << (2 * t);
+    return ((uint32_t) (v & 1) << (lb + t)) | ((uint32_t) (v >> 1) << (L + t));
 }
 
-/* all masks over bases 1..L-1 with exactly `m` substitutions, appended through `emit` */
 struct emit_ctx {
     uint32_t *out;
     long long n, cap;
-    int L, d, pass; /* pass 0: groups of four (m < d), pass 1: singles (m == d) */
+    int L, d, lb;
 };
 
-static void emit_upper(struct emit_ctx *c, uint32_t du, int m)
+/* every combination of the low bases with at most `budget` substitutions, in ascending address order */
+static void emit_low(struct emit_ctx *c, uint32_t du, int mu, int budget)
 {
-    if (c->pass == 0) {
-        for (int last = 0; last < 4; last++) {
-            if (c->n < c->cap) c->out[c->n] = (du | (uint32_t) last) | ((uint32_t) (m + (last != 0)) << 28);
-            c->n++;
-        }
-    } else {
-        if (c->n < c->cap) c->out[c->n] = du | ((uint32_t) m << 28);
+    const int nlow = 1 << (2 * c->lb);
+    for (int low = 0; low < nlow; low++) {
+        int ml = 0;
+        for (int t = 0; t < c->lb; t++) ml += ((low >> (2 * t)) & 3) != 0;
+        if (ml > budget) continue;
+        if (c->n < c->cap) c->out[c->n] = (du | (uint32_t) low) | ((uint32_t) (mu + ml) << 28);
         c->n++;
     }
 }
 
-static void rec_upper(struct emit_ctx *c, int first, int left, uint32_t du, int m)
+/* all masks over the upper bases lb..L-1 with exactly `left` more substitutions */
+static void rec_upper(struct emit_ctx *c, int first, int left, uint32_t du, int mu)
 {
-    if (left == 0) { emit_upper(c, du, m); return; }
+    if (left == 0) { emit_low(c, du, mu, c->d - mu); return; }
     for (int t = first; t <= c->L - left; t++)
-        for (int v = 1; v <= 3; v++) rec_upper(c, t + 1, left - 1, du | sub_mask(t, v, c->L), m);
+        for (int v = 1; v <= 3; v++) rec_upper(c, t + 1, left - 1, du | sub_mask(t, v, c->L), mu);
 }
 
 long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap)
@@ -65,11 +66,9 @@ long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap)
     if (L < 1 || L > GKM_IDX_MAX_L || d < 0 || d > 15 || !out) return -1;
     if (d > L) d = L;
     struct emit_ctx c;
-    c.out = out; c.n = 0; c.cap = cap; c.L = L; c.d = d;
-    c.pass = 0;
-    for (int mu = 0; mu < d && mu <= L - 1; mu++) rec_upper(&c, 1, mu, 0u, mu);
-    c.pass = 1;
-    if (d <= L - 1) rec_upper(&c, 1, d, 0u, d);
+    c.out = out; c.n = 0; c.cap = cap; c.L = L; c.d = d; c.lb = gkm_idx_lowb(L);
+    /* fewest upper substitutions first: those leave the largest groups of low-base variants */
+    for (int mu = 0; mu <= d && mu <= L - c.lb; mu++) rec_upper(&c, c.lb, mu, 0u, mu);
     return (c.n <= cap) ? c.n : -1;
 }
 
