@@ -25,6 +25,7 @@
 #include "gkm_index_dev.h"
 
 #define GKM_MAX_DEV 16
+#define GKM_NBUF 4 /* chunks in flight per GPU: kernels run ahead while the host scatters finished ones */
 #define GKM_FLUSH_BYTES ((size_t) 256 << 20) /* > 126 MB L2 */
 
 #define CK(call)                                                                              \
@@ -68,11 +69,11 @@ struct gkm_gpu {
     int ready;
     cudaStream_t sc, sc2, sx;  /* compute (two, so that the tail of one chunk overlaps the head of the next), copy */
     cudaEvent_t join;
-    cudaEvent_t k0[2], k1[2];  /* kernel start / end per staging slot */
-    cudaEvent_t cdone[2];      /* D2H complete per staging slot */
-    void *d_band[2];
+    cudaEvent_t k0[GKM_NBUF], k1[GKM_NBUF];  /* kernel start / end per staging slot */
+    cudaEvent_t cdone[GKM_NBUF];             /* D2H complete per staging slot */
+    void *d_band[GKM_NBUF];
     size_t band_cap;
-    void *h_stage[2];
+    void *h_stage[GKM_NBUF];
     size_t stage_cap;
     void *d_flush;
     /* small cache of device blocks: cudaMalloc/cudaFree per call cost up to a second of host time on
@@ -186,7 +187,7 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
         CK(cudaStreamCreateWithFlags(&g->sc2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&g->join, cudaEventDisableTiming));
         CK(cudaStreamCreateWithFlags(&g->sx, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < GKM_NBUF; i++) {
             CK(cudaEventCreate(&g->k0[i]));
             CK(cudaEventCreate(&g->k1[i]));
             CK(cudaEventCreateWithFlags(&g->cdone[i], cudaEventDisableTiming));
@@ -194,15 +195,15 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
         g->ready = 1;
     }
     if (band_bytes > g->band_cap) {
-        for (int i = 0; i < 2; i++) { if (g->d_band[i]) cudaFree(g->d_band[i]); g->d_band[i] = NULL; }
+        for (int i = 0; i < GKM_NBUF; i++) { if (g->d_band[i]) cudaFree(g->d_band[i]); g->d_band[i] = NULL; }
         g->band_cap = 0;
-        for (int i = 0; i < 2; i++) CK(cudaMalloc(&g->d_band[i], band_bytes));
+        for (int i = 0; i < GKM_NBUF; i++) CK(cudaMalloc(&g->d_band[i], band_bytes));
         g->band_cap = band_bytes;
     }
     if (stage_bytes > g->stage_cap) {
-        for (int i = 0; i < 2; i++) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); g->h_stage[i] = NULL; }
+        for (int i = 0; i < GKM_NBUF; i++) { if (g->h_stage[i]) cudaFreeHost(g->h_stage[i]); g->h_stage[i] = NULL; }
         g->stage_cap = 0;
-        for (int i = 0; i < 2; i++) CK(cudaMallocHost(&g->h_stage[i], stage_bytes));
+        for (int i = 0; i < GKM_NBUF; i++) CK(cudaMallocHost(&g->h_stage[i], stage_bytes));
         g->stage_cap = stage_bytes;
     }
     return 0;
@@ -682,7 +683,7 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     kp.ld = width;
     kp.hist = d_hist;
     kp.hist_cols = width;
-    cudaStream_t st = buf ? g->sc2 : g->sc;
+    cudaStream_t st = (buf & 1) ? g->sc2 : g->sc;
     CK(cudaEventRecord(g->k0[buf], st));
     if (launch_hist(job->p, im, g, kp, st, &dt->variant)) return 1;
     CK(cudaEventRecord(g->k1[buf], st));
@@ -717,26 +718,31 @@ static int dev_thread_body(gkm_devthread *dt)
         h_hist = (int32_t *) malloc(maxhist ? maxhist : 4);
         if (!h_hist) { gkm_set_error("out of memory"); return 1; }
     }
-    int cur = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
-    int curbuf = 0;
-    int rc = 0;
-    if (cur < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[cur]], curbuf, d_hist);
-    while (!rc && cur < job->nowned) {
-        const gkm_chunk *c = &job->chunks[job->owned[cur]];
-        int nxt = job->nowned;
-        if (!job->hist) { /* histogram dumps run one chunk at a time (single device buffer) */
-            nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
-            if (nxt < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], curbuf ^ 1, d_hist);
-            if (rc) break;
-        }
-        if (cudaEventSynchronize(g->cdone[curbuf]) != cudaSuccess) {
+    /* up to `depth` chunks are in flight: slot s holds chunk inslot[s]; the oldest is retired (D2H done ->
+     * scattered into the caller's rows) while the GPU works on the younger ones.  Histogram dumps (tests)
+     * run one chunk at a time: they share a single device buffer. */
+    const int depth = job->hist ? 1 : GKM_NBUF;
+    int inslot[GKM_NBUF];
+    int head = 0, inflight = 0, rc = 0;
+    while (!rc && inflight < depth) {
+        const int nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+        if (nxt >= job->nowned) break;
+        const int s = (head + inflight) % GKM_NBUF;
+        inslot[s] = nxt;
+        rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], s, d_hist);
+        inflight++;
+    }
+    while (!rc && inflight > 0) {
+        const int s = head % GKM_NBUF;
+        const gkm_chunk *c = &job->chunks[job->owned[inslot[s]]];
+        if (cudaEventSynchronize(g->cdone[s]) != cudaSuccess) {
             gkm_set_error("CUDA: kernel or copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = 1;
             break;
         }
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g->k0[curbuf], g->k1[curbuf]) == cudaSuccess) dt->kernel_ms += ms;
-        if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[curbuf]);
+        if (cudaEventElapsedTime(&ms, g->k0[s], g->k1[s]) == cudaSuccess) dt->kernel_ms += ms;
+        if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[s]);
         if (job->hist) {
             const int width = c->col_end - c->col_begin, nb = p->nbins;
             const size_t cells = (size_t) (c->row_end - c->row_begin) * (size_t) width;
@@ -753,11 +759,16 @@ static int dev_thread_body(gkm_devthread *dt)
                            h_hist + ((size_t) (r - c->row_begin) * (size_t) width + (size_t) (cc - c->col_begin)) * (size_t) nb,
                            (size_t) nb * 4);
             }
-            nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
-            if (nxt < job->nowned) rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], curbuf ^ 1, d_hist);
         }
-        cur = nxt;
-        curbuf ^= 1;
+        head++;
+        inflight--;
+        const int nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
+        if (nxt < job->nowned) {
+            const int ns = (head + inflight) % GKM_NBUF;
+            inslot[ns] = nxt;
+            rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], ns, d_hist);
+            inflight++;
+        }
     }
     if (rc) cudaDeviceSynchronize();
     if (d_hist) cudaFree(d_hist);

@@ -9,6 +9,8 @@
  * the diagonal of the kernel and comes from the GPU (gkm_device.cu).
  */
 #include <ctype.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,16 +68,19 @@ int gkm_problem_reserve(gkmb200_problem *p, int extra)
     return 0;
 }
 
-/* A,C,G,T (either case) -> 0..3; anything else counts as 'A' (libgkm.c:864-875) */
-static inline int base_code(int ch, int *bad)
+/* A,C,G,T (either case) -> 0..3; anything else counts as 'A' (libgkm.c:864-875) and is flagged with 0x80 */
+static uint8_t g_code_tab[256];
+static int g_code_tab_ready = 0;
+
+static void code_tab_init(void)
 {
-    switch (ch) {
-        case 'A': case 'a': return 0;
-        case 'C': case 'c': return 1;
-        case 'G': case 'g': return 2;
-        case 'T': case 't': return 3;
-        default: *bad = 1; return 0;
-    }
+    if (g_code_tab_ready) return;
+    for (int i = 0; i < 256; i++) g_code_tab[i] = 0x80;
+    g_code_tab['A'] = g_code_tab['a'] = 0;
+    g_code_tab['C'] = g_code_tab['c'] = 1;
+    g_code_tab['G'] = g_code_tab['g'] = 2;
+    g_code_tab['T'] = g_code_tab['t'] = 3;
+    __atomic_store_n(&g_code_tab_ready, 1, __ATOMIC_RELEASE);
 }
 
 int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
@@ -90,13 +95,20 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
     if (gkm_problem_reserve(p, 1)) { gkm_set_error("out of memory"); return -1; }
     uint8_t *c = (uint8_t *) malloc((size_t) len);
     if (!c) { gkm_set_error("out of memory"); return -1; }
+    code_tab_init();
+    unsigned any_bad = 0;
     for (int i = 0; i < len; i++) {
-        int bad = 0;
-        c[i] = (uint8_t) base_code((unsigned char) seq[i], &bad);
-        if (bad) {
+        const uint8_t v = g_code_tab[(unsigned char) seq[i]];
+        c[i] = v;
+        any_bad |= v;
+    }
+    if (any_bad & 0x80) { /* rare: name the offenders like the reference does, then fold them to 'A' */
+        for (int i = 0; i < len; i++) {
+            if (!(c[i] & 0x80)) continue;
             if (p->nonacgt < 10)
                 gkm_log(GKM_LOG_WARN, "'%c' at sequence %d(%d) is not a valid nucleotide. Only ACGT are allowed", seq[i], p->n, i);
             p->nonacgt++;
+            c[i] = 0;
         }
     }
     p->len[p->n] = len;
@@ -112,23 +124,47 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
 int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
 {
     if (!p || !path) { gkm_set_error("null argument"); return -1; }
-    FILE *fp = fopen(path, "r");
+    FILE *fp = fopen(path, "rb");
     if (!fp) { gkm_set_error("can't open file %s", path); return -1; }
-    char *line = NULL;
-    size_t cap = 0;
+    /* the whole file in one buffer (bins of gkmQC are a few MB), then one pass with memchr */
+    size_t cap = (size_t) 1 << 20, got = 0;
+    if (fseek(fp, 0, SEEK_END) == 0) {
+        long sz = ftell(fp);
+        if (sz > 0) cap = (size_t) sz + 1;
+        rewind(fp);
+    }
+    char *buf = (char *) malloc(cap);
     char *seq = (char *) malloc(GKM_MAX_BASES + 1);
+    if (!buf || !seq) { free(buf); free(seq); fclose(fp); gkm_set_error("out of memory reading %s", path); return -1; }
+    for (;;) {
+        size_t r = fread(buf + got, 1, cap - got, fp);
+        got += r;
+        if (got < cap) break;
+        char *nb = (char *) realloc(buf, cap * 2);
+        if (!nb) { free(buf); free(seq); fclose(fp); gkm_set_error("out of memory reading %s", path); return -1; }
+        buf = nb;
+        cap *= 2;
+    }
+    fclose(fp);
     int seqlen = 0, open_rec = 0, added = 0, warned = 0, fail = 0;
-    ssize_t got;
-    while (!fail && (got = getline(&line, &cap, fp)) >= 0) {
-        line[strcspn(line, "\r\n")] = '\0';
-        if (line[0] == '>') {
+    const char *cur = buf, *end = buf + got;
+    while (!fail && cur < end) {
+        const char *nl = (const char *) memchr(cur, '\n', (size_t) (end - cur));
+        const char *next = nl ? nl + 1 : end;
+        const char *le = nl ? nl : end;
+        /* the line ends at the first CR, LF or NUL (libgkm.c:1207-1225 reads lines as C strings) */
+        const char *cr = (const char *) memchr(cur, '\r', (size_t) (le - cur));
+        if (cr) le = cr;
+        const char *nul = (const char *) memchr(cur, '\0', (size_t) (le - cur));
+        if (nul) le = nul;
+        if (le > cur && cur[0] == '>') {
             if (open_rec) {
                 if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
             }
             if ((added % 1000) == 0) gkm_log(GKM_LOG_INFO, "reading... %d", added);
             open_rec = 1; seqlen = 0; warned = 0;
         } else if (open_rec && seqlen < GKM_MAX_BASES) {
-            size_t ll = strlen(line);
+            size_t ll = (size_t) (le - cur);
             if ((size_t) seqlen + ll > GKM_MAX_BASES) {
                 if (!warned)
                     gkm_log(GKM_LOG_WARN, "maximum sequence length allowed is %d. The first %d nucleotides of record %d will only be used",
@@ -136,17 +172,17 @@ int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
                 warned = 1;
                 ll = (size_t) (GKM_MAX_BASES - seqlen);
             }
-            memcpy(seq + seqlen, line, ll);
+            memcpy(seq + seqlen, cur, ll);
             seqlen += (int) ll;
         }
+        cur = next;
     }
     if (!fail && open_rec) {
         if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
     }
     gkm_log(GKM_LOG_INFO, "reading... done");
-    free(line);
+    free(buf);
     free(seq);
-    fclose(fp);
     return fail ? -1 : added;
 }
 
@@ -209,31 +245,16 @@ void gkm_unpack_problem(gkmb200_problem *p)
     p->host_sqnorm = 0;
 }
 
-/* build the device image on the host.
- * Per sequence one circular string of 32*Wc positions: forward strand at [0,len), reverse
- * complement at [len,2len), zero padding behind.  planes[i][0..1][Wc] = the two code bit planes,
- * planes[i][2][Wc] = E, the positions at which an L-mer of either strand may END
- * (L-1 <= j < len and len+L-1 <= j < 2len).  wend[i][32*Wc] = weight of the L-mer ending at j. */
-int gkm_pack_problem(gkmb200_problem *p)
+struct pack_job { gkmb200_problem *p; int i0, i1; };
+
+static void *pack_worker(void *arg)
 {
-    if (p->packed) return 0;
-    if (p->n == 0) { gkm_set_error("problem has no sequences"); return 1; }
-    const int L = p->param.L;
-    int maxlen = 0;
-    for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
-    const int W = (2 * maxlen + 31) / 32;
-    p->Wmax = W;
-    p->Wa = (maxlen + 31) / 32;
-    p->planes = (uint32_t *) calloc((size_t) p->n * 3 * (size_t) W, sizeof(uint32_t));
-    p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
-    if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 32 * (size_t) W, 1);
-    if (!p->planes || !p->sqnorm || (p->weighted && !p->wend)) {
-        gkm_unpack_problem(p);
-        gkm_set_error("out of memory packing %d sequences", p->n);
-        return 1;
-    }
+    const struct pack_job *job = (const struct pack_job *) arg;
+    gkmb200_problem *p = job->p;
+    const int L = p->param.L, W = p->Wmax;
     uint8_t wt[GKM_MAX_BASES + 1], wt_rc[GKM_MAX_BASES + 1];
-    for (int i = 0; i < p->n; i++) {
+    int wt_nk = -1; /* positional weights depend on the number of L-mers only: reuse them across equal lengths */
+    for (int i = job->i0; i < job->i1; i++) {
         const int n = p->len[i];
         const uint8_t *c = p->code[i];
         uint32_t *pl = p->planes + (size_t) i * 3 * (size_t) W;
@@ -256,13 +277,59 @@ int gkm_pack_problem(gkmb200_problem *p)
         }
         if (p->weighted) {
             const int nk = n - L + 1;
-            gkm_calc_posweights(nk, p->param.kernel_type, p->param.M, p->param.H, wt, wt_rc);
+            if (nk != wt_nk) { gkm_calc_posweights(nk, p->param.kernel_type, p->param.M, p->param.H, wt, wt_rc); wt_nk = nk; }
             uint8_t *we = p->wend + (size_t) i * 32 * (size_t) W;
             for (int s = 0; s < nk; s++) {
                 we[s + L - 1] = wt[s];
                 we[n + s + L - 1] = wt_rc[s];
             }
         }
+    }
+    return NULL;
+}
+
+/* build the device image on the host.
+ * Per sequence one circular string of 32*Wc positions: forward strand at [0,len), reverse
+ * complement at [len,2len), zero padding behind.  planes[i][0..1][Wc] = the two code bit planes,
+ * planes[i][2][Wc] = E, the positions at which an L-mer of either strand may END
+ * (L-1 <= j < len and len+L-1 <= j < 2len).  wend[i][32*Wc] = weight of the L-mer ending at j. */
+int gkm_pack_problem(gkmb200_problem *p)
+{
+    if (p->packed) return 0;
+    if (p->n == 0) { gkm_set_error("problem has no sequences"); return 1; }
+    int maxlen = 0;
+    for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
+    const int W = (2 * maxlen + 31) / 32;
+    p->Wmax = W;
+    p->Wa = (maxlen + 31) / 32;
+    p->planes = (uint32_t *) calloc((size_t) p->n * 3 * (size_t) W, sizeof(uint32_t));
+    p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
+    if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 32 * (size_t) W, 1);
+    if (!p->planes || !p->sqnorm || (p->weighted && !p->wend)) {
+        gkm_unpack_problem(p);
+        gkm_set_error("out of memory packing %d sequences", p->n);
+        return 1;
+    }
+    /* sequences are independent: a few host threads share them (the reference builds its per-sequence
+     * arrays serially inside read_fasta_file, libgkm.c:1251-1314) */
+    int nt = (int) sysconf(_SC_NPROCESSORS_ONLN);
+    if (nt > 8) nt = 8;
+    if (nt > p->n / 512) nt = p->n / 512;
+    if (nt < 1) nt = 1;
+    pthread_t th[8];
+    struct pack_job jobs[8];
+    int started[8];
+    for (int t = 0; t < nt; t++) {
+        jobs[t].p = p;
+        jobs[t].i0 = (int) ((long long) p->n * t / nt);
+        jobs[t].i1 = (int) ((long long) p->n * (t + 1) / nt);
+        started[t] = 0;
+        if (t > 0) started[t] = (pthread_create(&th[t], NULL, pack_worker, &jobs[t]) == 0);
+    }
+    pack_worker(&jobs[0]);
+    for (int t = 1; t < nt; t++) {
+        if (started[t]) pthread_join(th[t], NULL);
+        else pack_worker(&jobs[t]);
     }
     p->packed = 1;
     p->have_sqnorm = 0;
