@@ -140,6 +140,27 @@ def dist_barrier(dist):
         dist.barrier()
 
 
+def index_probe_counts(L, d):
+    """probes and distinct 32-byte sectors per query L-mer of the index variant, from the product's own mask list"""
+    from gkmqc_b200 import capi
+    import ctypes
+    lib = capi.load()
+    lib.gkm_idx_delta_count.restype = ctypes.c_longlong
+    lib.gkm_idx_deltas.restype = ctypes.c_longlong
+    lib.gkm_idx_deltas.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
+    nd = lib.gkm_idx_delta_count(L, d)
+    a = np.zeros(nd, dtype=np.uint32)
+    assert lib.gkm_idx_deltas(L, d, a.ctypes.data, nd) == nd
+    return int(nd), int(len(np.unique((a & 0x0FFFFFFF) >> 1)))   # two 16-byte slots per sector
+
+
+def measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        return None
+
+
 def cpu_reference_rate(pos, neg, n, budget_s, threads):
     """the reference's own CPU path (oracle/_ref, unmodified sources) on a stated subsample of rows of the SAME
     problem (tree over all n sequences); falls back to the oracle port when the reference was not built here"""
@@ -281,28 +302,50 @@ def main():
     if rank != 0:
         return
 
-    # roofline of the dominant (only) kernel: algorithmic integer operations over measured LOP3 issue rate
+    # roofline of the dominant kernel, by the variant that actually ran:
+    #   index: random 16-byte slot probes of an L2-resident table -> L1/L2 sector rate, measured by an in-run gather
+    #          micro-benchmark (neither HBM nor the tensor pipe binds: SURVEY.md 8d)
+    #   diag / lmer / mma: integer-ALU issue rate (LOP3 lane-ops/s measured in-run)
+    variant = {1: "lmer", 2: "diag", 3: "mma", 4: "index"}.get(st["kernel_variant"], "?")
     peak_lop3 = capi.microbench("lop3")       # 1e9 lane-ops/s on this GPU, measured now
     peak_popc = capi.microbench("popc")
     per_gpu_entries_s = value / world
-    achieved = per_gpu_entries_s * PAIRS_PER_ENTRY * INT_OPS_PER_PAIR / 1e9
-    traffic, ncu = None, None
+    int_alu_equiv = per_gpu_entries_s * PAIRS_PER_ENTRY * INT_OPS_PER_PAIR / 1e9
+    ncu = None
     tf = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")   # written from the committed ncu --set full capture
     if os.path.exists(tf):
         try:
             ncu = json.load(open(tf))
-            traffic = ncu.get("dram_bytes_per_launch")
+            if ncu.get("variant", "diag") != variant:
+                ncu = None
         except Exception:
             ncu = None
-    roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak_lop3, "unit": "Gop/s", "frac": achieved / peak_lop3,
-                "traffic": traffic,
-                "note": "achieved = entries/s x 168200 L-mer pairs x 5 integer ops of the canonical XOR/LOP3/POPC form "
-                        "(SURVEY.md 8d); peak = LOP3 lane-ops/s measured in this run (MEASURED_PEAKS.json has no integer "
-                        "peak). The bit-sliced kernel needs < 1 op per pair, so frac > 1 is possible; see DESIGN.md",
-                "peak_popc_gops": peak_popc,
-                "ncu": ncu,   # pipe utilisation of the same kernel under ncu (profiles/): the executed-work view of the roofline
-                "avg_launch_ms": ms_per_step / max(1, st["launches"]),
-                "kernel_variant": {1: "lmer", 2: "diag", 3: "mma"}.get(st["kernel_variant"], "?")}
+    traffic = ncu.get("dram_bytes_per_launch") if ncu else None
+    avg_launch_ms = ms_per_step / max(1, st["launches"])
+    if variant == "index":
+        peak_gather = capi.microbench("gather16")     # 1e9 random 16-byte gathers (one 32-byte sector each) per second
+        probes, sectors = index_probe_counts(L, D)
+        nq = SEQLEN - L + 1
+        my_rows = n / world                            # chunks of equal row counts, round-robin over the ranks
+        sector_bytes = my_rows * nq * sectors * 32.0   # algorithmic: distinct sectors the probes of one pass must fetch
+        achieved = sector_bytes / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "l2_sector", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
+                    "frac": achieved / (peak_gather * 32.0), "traffic": traffic,
+                    "note": "index variant: every forward L-mer of a row probes %d slots of the L2-resident table (%d distinct 32-byte "
+                            "sectors); achieved = rows x %d L-mers x sectors x 32 B per pass / time; peak = random 16-byte gathers from a "
+                            "64 MB table measured in this run (x 32 B per sector). MEASURED_PEAKS.json hbm_gbs = %s for scale: the "
+                            "probes are served by L2, DRAM traffic is `traffic`" % (probes, sectors, nq, measured_hbm()),
+                    "probes_per_lmer": probes, "sectors_per_lmer": sectors, "peak_gather_gsectors": peak_gather,
+                    "int_alu_equivalent": {"achieved_gops": int_alu_equiv, "peak_lop3_gops": peak_lop3, "ratio": int_alu_equiv / peak_lop3,
+                                           "note": "what the canonical 5-op XOR/POPC form would need for the same entries/s (SURVEY.md 8d)"},
+                    "ncu": ncu, "avg_launch_ms": avg_launch_ms, "kernel_variant": variant}
+    else:
+        roofline = {"bound": "int_alu", "achieved": int_alu_equiv, "peak": peak_lop3, "unit": "Gop/s", "frac": int_alu_equiv / peak_lop3,
+                    "traffic": traffic,
+                    "note": "achieved = entries/s x 168200 L-mer pairs x 5 integer ops of the canonical XOR/LOP3/POPC form "
+                            "(SURVEY.md 8d); peak = LOP3 lane-ops/s measured in this run (MEASURED_PEAKS.json has no integer "
+                            "peak). The bit-sliced kernel needs < 1 op per pair, so frac > 1 is possible; see DESIGN.md",
+                    "peak_popc_gops": peak_popc, "ncu": ncu, "avg_launch_ms": avg_launch_ms, "kernel_variant": variant}
 
     # secondary figure: gkmQC's default weighted kernel, type 4 (wgkm, M=50 H=50), same sequences
     secondary = None

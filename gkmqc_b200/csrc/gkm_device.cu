@@ -69,6 +69,7 @@ struct gkm_gpu {
     int ready;
     cudaStream_t sc, sc2, sx;  /* compute (two, so that the tail of one chunk overlaps the head of the next), copy */
     cudaEvent_t join;
+    cudaEvent_t span0;         /* start of the first kernel of a compute call */
     cudaEvent_t k0[GKM_NBUF], k1[GKM_NBUF];  /* kernel start / end per staging slot */
     cudaEvent_t cdone[GKM_NBUF];             /* D2H complete per staging slot */
     void *d_band[GKM_NBUF];
@@ -186,6 +187,7 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
         CK(cudaStreamCreateWithFlags(&g->sc, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&g->sc2, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&g->join, cudaEventDisableTiming));
+        CK(cudaEventCreate(&g->span0));
         CK(cudaStreamCreateWithFlags(&g->sx, cudaStreamNonBlocking));
         for (int i = 0; i < GKM_NBUF; i++) {
             CK(cudaEventCreate(&g->k0[i]));
@@ -724,6 +726,7 @@ static int dev_thread_body(gkm_devthread *dt)
     const int depth = job->hist ? 1 : GKM_NBUF;
     int inslot[GKM_NBUF];
     int head = 0, inflight = 0, rc = 0;
+    if (cudaEventRecord(g->span0, g->sc) != cudaSuccess) { gkm_set_error("CUDA: event record failed"); return 1; }
     while (!rc && inflight < depth) {
         const int nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
         if (nxt >= job->nowned) break;
@@ -741,7 +744,8 @@ static int dev_thread_body(gkm_devthread *dt)
             break;
         }
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, g->k0[s], g->k1[s]) == cudaSuccess) dt->kernel_ms += ms;
+        /* device time of the call so far: first kernel start -> end of this chunk's kernel (chunks overlap) */
+        if (cudaEventElapsedTime(&ms, g->span0, g->k1[s]) == cudaSuccess && ms > dt->kernel_ms) dt->kernel_ms = ms;
         if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[s]);
         if (job->hist) {
             const int width = c->col_end - c->col_begin, nb = p->nbins;
@@ -812,12 +816,14 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
     if (!rc) {
         gkm_devstate *ds = p->dev;
         const long long total_cells = (long long) nrows * ncols / (lower ? 2 : 1);
-        const int tile_rows = 16;
+        /* index variant: every row costs the same, so chunks are whole waves of rows (one CTA per row and SM) */
+        const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
+        const int tile_rows = by_rows ? 148 : 16;
         const int maxc = nrows / tile_rows + 2;
         chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
         owned = (int *) malloc(sizeof(int) * (size_t) maxc);
-        int nchunks = (chunks && owned) ? gkm_plan_chunks(row0, nrows, col0, ncols, lower, tile_rows,
-                                                          plan_budget(p, total_cells, ds->ndev), chunks, maxc) : -1;
+        int nchunks = (chunks && owned) ? gkm_plan_chunks_rows(row0, nrows, col0, ncols, lower, tile_rows,
+                                                               plan_budget(p, total_cells, ds->ndev), by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
         if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
         if (!rc) {
             gkm_job job;
@@ -991,8 +997,10 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
         const int maxc = n / 16 + 2;
         int nchunks = -1;
         if (!rc) {
+            const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
             chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
-            nchunks = chunks ? gkm_plan_chunks(0, n, 0, n, 1, 16, plan_budget(p, (long long) n * n / 2, 1), chunks, maxc) : -1;
+            nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, 1),
+                                                    by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
             if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
         }
         cudaEvent_t e0 = NULL, e1 = NULL;
@@ -1077,6 +1085,58 @@ __global__ void __launch_bounds__(256) gkm_mb_kernel(uint32_t *out, int iters, u
     if (s == 0x12345u) out[0] = s;
 }
 
+/* random 16-byte gathers from a 64 MB (L2-resident) table, four independent loads per thread in flight:
+ * the sector rate the "index" variant's slot probes can reach at best */
+__global__ void __launch_bounds__(1024, 1) gkm_mb_gather_kernel(const uint4 *__restrict__ tab, uint32_t mask, int iters, uint32_t *out)
+{
+    uint32_t s = (blockIdx.x * 1024u + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; i++) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            s = s * 1664525u + 1013904223u;
+            v[u] = __ldg(tab + ((s >> 4) & mask));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+    }
+    if (acc == 0x9E3779B9u) out[0] = acc;
+}
+
+static int microbench_gather(gkm_gpu *g, double *result)
+{
+    const size_t slots = (size_t) 1 << 22; /* 4 Mi x 16 B = 64 MB, the size of the L = 11 slot table */
+    uint4 *tab = NULL;
+    uint32_t *d = NULL;
+    if (cudaMalloc(&tab, slots * sizeof(uint4)) != cudaSuccess || cudaMalloc(&d, 64) != cudaSuccess) {
+        gkm_set_error("CUDA: microbench buffers: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(tab);
+        return 1;
+    }
+    cudaMemsetAsync(tab, 0x5A, slots * sizeof(uint4), g->sc);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->id);
+    const int iters = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    int rc = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0, g->sc);
+        gkm_mb_gather_kernel<<<sms, 1024, 0, g->sc>>>(tab, (uint32_t) (slots - 1), iters, d);
+        cudaEventRecord(e1, g->sc);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { gkm_set_error("CUDA: microbench failed"); rc = 1; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(tab); cudaFree(d);
+    if (!rc) *result = (double) sms * 1024.0 * (double) iters * 4.0 / ((double) best * 1e-3) / 1e9; /* 1e9 gathers (sectors) per second */
+    return rc;
+}
+
 extern "C" int gkm_dev_microbench(const char *what, double *result)
 {
     if (!what || !result) { gkm_set_error("null argument"); return 1; }
@@ -1086,6 +1146,7 @@ extern "C" int gkm_dev_microbench(const char *what, double *result)
         do {
             gkm_gpu *g = &g_gpu[g_sel[0]];
             if (gpu_prepare(g, g_sel[0], 0, 0)) { rc = 1; break; }
+            if (!strcmp(what, "gather16")) { rc = microbench_gather(g, result); break; }
             uint32_t *d = NULL;
             if (cudaMalloc(&d, 64) != cudaSuccess) { rc = 1; break; }
             int sms = 148;

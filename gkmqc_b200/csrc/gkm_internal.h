@@ -72,6 +72,8 @@ typedef struct gkm_chunk {
  * Returns the number of chunks written (<= max_chunks) or -1. */
 int gkm_plan_chunks(int row0, int nrows, int col0, int ncols, int lower, int tile_rows,
                     long long max_chunk_bytes, gkm_chunk *out, int max_chunks);
+int gkm_plan_chunks_rows(int row0, int nrows, int col0, int ncols, int lower, int tile_rows,
+                         long long max_chunk_bytes, int max_rows, gkm_chunk *out, int max_chunks);
 /* which chunks belong to shard `rank` of `world` (round-robin by descending cost) */
 int gkm_chunk_owner(int chunk_index, int nchunks, int world);
 

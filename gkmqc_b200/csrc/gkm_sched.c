@@ -13,6 +13,15 @@
 int gkm_plan_chunks(int row0, int nrows, int col0, int ncols, int lower, int tile_rows,
                     long long max_chunk_bytes, gkm_chunk *out, int max_chunks)
 {
+    return gkm_plan_chunks_rows(row0, nrows, col0, ncols, lower, tile_rows, max_chunk_bytes, 0, out, max_chunks);
+}
+
+/* max_rows > 0 also bounds the rows of a chunk.  The "index" kernel variant costs the same for every row
+ * whatever the number of columns (it probes the whole index), so its chunks are cut by rows, which keeps
+ * round-robin ownership balanced there too. */
+int gkm_plan_chunks_rows(int row0, int nrows, int col0, int ncols, int lower, int tile_rows,
+                         long long max_chunk_bytes, int max_rows, gkm_chunk *out, int max_chunks)
+{
     if (nrows < 0 || ncols < 0 || tile_rows < 1 || max_chunks < 1) return -1;
     int n = 0;
     int r = row0;
@@ -28,7 +37,7 @@ int gkm_plan_chunks(int row0, int nrows, int col0, int ncols, int lower, int til
             if (lower && cend > ne) cend = ne; /* columns j < last row of the chunk */
             long long width = (long long) (cend > col0 ? cend - col0 : 0);
             long long bytes = (long long) (ne - r) * width * 8;
-            if (e > r && bytes > max_chunk_bytes) break;
+            if (e > r && (bytes > max_chunk_bytes || (max_rows > 0 && ne - r > max_rows))) break;
             e = ne;
             if (e >= rend) break;
         }
