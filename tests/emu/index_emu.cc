@@ -1,0 +1,170 @@
+/* tests/emu/index_emu.cc -- CPU emulator of the "index" kernel variant (gkm_index.h / gkm_index.cu).
+ *
+ * TEST INFRASTRUCTURE, not a fallback: nothing in the product links it.  It runs on the host, over
+ * the product's own packed image (gkm_seq.c), the same steps the sm_100a code runs:
+ *   keys   -> every valid window of both strands, coded by gkm_idx_code()         (gkm_idx_keys_kernel)
+ *   sort   -> by (code, column)                                                    (cub radix sort)
+ *   slots  -> {posting 0, 1, 2, posting 3 | pointer}, overflow lists padded to     (gkm_idx_runs_kernel,
+ *             quads with end markers                                                gkm_idx_fill_kernel)
+ *   probes -> x ^ mask for every mask of gkm_idx_deltas(), postings walked with    (gkm_index_rows_kernel,
+ *             the same sorted-list / end-marker rules                               idx_slot)
+ * so that the code layout, the mask list, the slot encoding and the walk rules are checked against
+ * the reference's histograms in the CPU-only tier.  The slot "table" is a hash map here: 4^L slots
+ * do not fit a test box for L = 14.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "../../gkmqc_b200/csrc/gkm_internal.h"
+#include "../../gkmqc_b200/csrc/gkm_index.h"
+
+struct emu_slot { uint32_t v[4]; };
+
+static uint32_t window(const uint32_t *pl, int W, int lo, uint32_t mask)
+{
+    const int w = lo >> 5, s = lo & 31;
+    const uint64_t x = pl[w] | ((uint64_t) ((w + 1 < W) ? pl[w + 1] : 0u) << 32);
+    return (uint32_t) (x >> s) & mask;
+}
+
+struct emu_index {
+    std::unordered_map<uint32_t, emu_slot> tab;
+    std::vector<uint32_t> ovf;
+};
+
+/* index over the columns [cb, ce) */
+static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
+{
+    const int L = p->param.L, W = p->Wmax;
+    const uint32_t mask = (1u << L) - 1u;
+    std::vector<uint64_t> keys;
+    for (int g = cb; g < ce; g++) {
+        const int len = p->len[g];
+        const uint32_t *pl = p->planes + (size_t) g * 3 * W;
+        for (int j = 0; j < 2 * len; j++) {
+            const int rel = j < len ? j : j - len;
+            if (rel < L - 1) continue;
+            const uint32_t code = gkm_idx_code(window(pl, W, j - L + 1, mask), window(pl + W, W, j - L + 1, mask), L);
+            const uint32_t wt = p->weighted ? p->wend[(size_t) g * 32 * W + j] : 1u;
+            keys.push_back(((uint64_t) code << 32) | ((uint64_t) (uint32_t) (g - cb) << 8) | wt);
+        }
+    }
+    std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return (a >> 8) < (b >> 8); });
+    size_t i = 0;
+    while (i < keys.size()) {
+        size_t e = i;
+        while (e < keys.size() && (keys[e] >> 32) == (keys[i] >> 32)) e++;
+        const size_t len = e - i;
+        emu_slot s;
+        for (int t = 0; t < 4; t++) s.v[t] = GKM_IDX_EMPTY;
+        for (size_t r = 0; r < len; r++) {
+            const uint32_t posting = gkm_idx_posting((uint32_t) (keys[i + r] >> 8) & GKM_IDX_COL_MASK, (uint32_t) keys[i + r] & 0xFFu);
+            if (r < 3 || (r == 3 && len == 4)) s.v[r] = posting;
+            else {
+                if (r == 3) {
+                    while (ix.ovf.size() & 3) ix.ovf.push_back(GKM_IDX_EMPTY); /* lists start on 16 bytes */
+                    s.v[3] = GKM_IDX_PTR | (uint32_t) ix.ovf.size();
+                }
+                ix.ovf.push_back(posting);
+            }
+        }
+        if (len >= 5) { /* at least one end marker, up to a multiple of four */
+            ix.ovf.push_back(GKM_IDX_EMPTY);
+            while (ix.ovf.size() & 3) ix.ovf.push_back(GKM_IDX_EMPTY);
+        }
+        ix.tab[(uint32_t) (keys[i] >> 32)] = s;
+        i = e;
+    }
+}
+
+static inline void hit(int32_t *H, int nb, int m, uint32_t e, uint32_t blo, uint32_t bhi, int w)
+{
+    const uint32_t b = e & GKM_IDX_COL_MASK;
+    if (b < bhi && b >= blo) H[(size_t) (b - blo) * nb + m] += w * (int) (e >> GKM_IDX_COL_BITS);
+}
+
+/* H[(b - blo) * nbins + m] += ... for row a against the indexed columns [blo, bhi) (relative) */
+static void probe_row(const gkmb200_problem *p, const emu_index &ix, const std::vector<uint32_t> &deltas, int a,
+                      uint32_t blo, uint32_t bhi, int32_t *H)
+{
+    const int L = p->param.L, W = p->Wmax, nb = p->nbins;
+    const uint32_t mask = (1u << L) - 1u;
+    const uint32_t *pl = p->planes + (size_t) a * 3 * W;
+    const int nq = p->len[a] - L + 1;
+    for (int i = 0; i < nq; i++) {
+        const uint32_t x = gkm_idx_code(window(pl, W, i, mask), window(pl + W, W, i, mask), L);
+        const int w = p->weighted ? p->wend[(size_t) a * 32 * W + i + L - 1] : 1;
+        for (uint32_t dl : deltas) {
+            const int m = (int) (dl >> 28);
+            auto it = ix.tab.find(x ^ (dl & 0x0FFFFFFFu));
+            if (it == ix.tab.end()) continue;
+            const uint32_t *sl = it->second.v;
+            hit(H, nb, m, sl[0], blo, bhi, w);
+            hit(H, nb, m, sl[1], blo, bhi, w);
+            hit(H, nb, m, sl[2], blo, bhi, w);
+            if (!(sl[3] & GKM_IDX_PTR)) hit(H, nb, m, sl[3], blo, bhi, w);
+            else if (sl[3] != GKM_IDX_EMPTY && (sl[2] & GKM_IDX_COL_MASK) < bhi) {
+                const uint32_t *q = ix.ovf.data() + (sl[3] & ~GKM_IDX_PTR);
+                for (;;) {
+                    for (int t = 0; t < 4; t++) hit(H, nb, m, q[t], blo, bhi, w);
+                    if ((q[3] & GKM_IDX_COL_MASK) >= bhi) break;
+                    q += 4;
+                }
+            }
+        }
+    }
+}
+
+extern "C" {
+
+/* how much work the emulation of a problem is: masks x query L-mers */
+long long gkm_emu_index_cost(gkmb200_problem *p)
+{
+    long long nq = 0;
+    for (int i = 0; i < p->n; i++) nq += p->len[i] - p->param.L + 1;
+    return nq * gkm_idx_delta_count(p->param.L, p->param.d);
+}
+
+/* H[(a * n + b) * nbins + m] for b <= a (the diagonal included), the columns cut into blocks of
+ * `block_cols` like the product cuts them when a histogram row does not fit shared memory */
+int gkm_emu_index_hist_lower(gkmb200_problem *p, int block_cols, int32_t *H)
+{
+    if (!gkm_idx_supported(p->param.L, p->param.d, p->nbins)) return 2;
+    if (gkm_pack_problem(p)) return 1;
+    const int n = p->n, nb = p->nbins;
+    const long long nd = gkm_idx_delta_count(p->param.L, p->param.d);
+    std::vector<uint32_t> deltas((size_t) nd);
+    if (gkm_idx_deltas(p->param.L, p->param.d, deltas.data(), nd) != nd) return 1;
+    if (block_cols < 1) block_cols = n;
+    for (int cb = 0; cb < n; cb += block_cols) {
+        const int ce = cb + block_cols < n ? cb + block_cols : n;
+        emu_index ix;
+        build_index(p, cb, ce, ix);
+        for (int a = cb; a < n; a++) {
+            const uint32_t bhi = (uint32_t) ((a + 1 < ce ? a + 1 : ce) - cb); /* columns <= a */
+            probe_row(p, ix, deltas, a, 0u, bhi, H + ((size_t) a * n + cb) * nb);
+        }
+    }
+    return 0;
+}
+
+/* one rectangular block with a lower column bound inside the index block (the RANGE path of the kernel) */
+int gkm_emu_index_hist_rect(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int32_t *H)
+{
+    if (!gkm_idx_supported(p->param.L, p->param.d, p->nbins)) return 2;
+    if (gkm_pack_problem(p)) return 1;
+    const int nb = p->nbins;
+    const long long nd = gkm_idx_delta_count(p->param.L, p->param.d);
+    std::vector<uint32_t> deltas((size_t) nd);
+    if (gkm_idx_deltas(p->param.L, p->param.d, deltas.data(), nd) != nd) return 1;
+    emu_index ix;
+    build_index(p, 0, p->n, ix); /* the whole problem is one block; only [col0, col0 + ncols) is wanted */
+    for (int r = 0; r < nrows; r++)
+        probe_row(p, ix, deltas, row0 + r, (uint32_t) col0, (uint32_t) (col0 + ncols), H + (size_t) r * ncols * nb);
+    return 0;
+}
+
+}
