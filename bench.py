@@ -111,7 +111,22 @@ def dist_setup(world):
     backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    dist.init_process_group(backend=backend)
+    # NCCL prints its version banner on stdout when the first communicator comes up; stdout carries the
+    # one JSON line only, so that banner goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group(backend=backend)
+        dev = "cuda" if backend == "nccl" else "cpu"
+        t = torch.zeros(1, device=dev)
+        dist.all_reduce(t)
+        if backend == "nccl":
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
     return dist
 
 
@@ -298,6 +313,10 @@ def main():
     h2d = int(dist_sum(dist, h2d))
     d2h = int(dist_sum(dist, d2h))
     clocks = sampler.finish() if rank == 0 else None
+    if dist is not None:   # the last collective is behind us: what follows is rank 0's own reporting
+        dist.barrier()
+        dist.destroy_process_group()
+        dist = None
 
     if rank != 0:
         return
@@ -369,6 +388,7 @@ def main():
                 "ms_per_step": 1e3 * float(np.mean(walls)), "steps": e2e_steps,
                 "call": "gkm_main_pywrapper(FASTA paths, double** rows of a fresh numpy matrix, int[2])"},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary}))
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
