@@ -84,7 +84,9 @@ struct gkm_gpu {
     /* "index" variant: XOR masks of the (L, d) last used on this GPU */
     uint32_t *d_deltas;
     size_t deltas_bytes;
-    int delta_L, delta_d, ndelta;
+    int delta_L, delta_d, ndelta, ncold;
+    int32_t *d_cold[2];   /* cold-bin scratch of the launches on sc / sc2 */
+    size_t cold_cap[2];
 };
 
 static gkm_gpu g_gpu[GKM_MAX_DEV];
@@ -231,7 +233,7 @@ static int pick_variant(const gkmb200_problem *p, int mode)
 }
 
 /* "index" variant: one row-kernel launch per index block that holds wanted columns */
-static int launch_index(const gkmb200_problem *p, const gkm_image *im, const gkm_gpu *g, const gkm_kparams &kp, cudaStream_t st)
+static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g, const gkm_kparams &kp, cudaStream_t st)
 {
     int a_max = kp.row_end - 1;
     for (int k = 0; k < im->nblk; k++) {
@@ -246,12 +248,26 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, const gkm
         ra.cb = b->cb; ra.blo = lo - b->cb; ra.bhi = hi - b->cb;
         ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
         ra.maxq = 32 * p->Wa;
+        ra.ncold = g->ncold;
+        {   /* cold-bin scratch of this stream, grown on demand (the stream is drained before a block is replaced) */
+            const int si = (st == g->sc2) ? 1 : 0;
+            const size_t need = gkm_idx_cold_bytes(p->nbins, ra.ldh, kp.row_end - kp.row_begin);
+            if (need > g->cold_cap[si]) {
+                CK(cudaStreamSynchronize(st));
+                if (g->d_cold[si]) cudaFree(g->d_cold[si]);
+                g->d_cold[si] = NULL; g->cold_cap[si] = 0;
+                const size_t want = need + need / 4 + 4096;
+                CK(cudaMalloc((void **) &g->d_cold[si], want));
+                g->cold_cap[si] = want;
+            }
+            ra.cold = g->d_cold[si];
+        }
         if (gkm_idx_rows(&kp, &ra, p->weighted, st)) return 1;
     }
     return 0;
 }
 
-static int launch_hist(const gkmb200_problem *p, const gkm_image *im, const gkm_gpu *g, gkm_kparams kp, cudaStream_t st, int *variant_out)
+static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g, gkm_kparams kp, cudaStream_t st, int *variant_out)
 {
     const int variant = pick_variant(p, kp.mode);
     const int rows = kp.row_end - kp.row_begin, cols = kp.col_end - kp.col_begin;
@@ -361,6 +377,19 @@ static void pool_free(gkm_gpu *g, void *ptr, size_t bytes)
 /* ------------------------------------------------------------------ */
 /* "index" variant: per-GPU mask list, per-image column-block indexes    */
 /* ------------------------------------------------------------------ */
+/* columns one index block may hold: what fits shared memory, or less when the option says so */
+static int index_block_cap(const gkmb200_problem *p)
+{
+    int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
+    /* beyond ~16k columns the posting lists grow past the four inline postings of a slot often enough that the
+     * overflow walks cost more than probing a second block does (measured: 6.0 us per row at 14k columns in one
+     * block, 10.9 us at 20k in one block against 7.5 us in two) */
+    if (cap > 16384) cap = 16384;
+    const int opt = gkm_opt_index_cols();
+    if (opt > 0 && opt < cap) cap = opt;
+    return cap;
+}
+
 static void release_index(gkm_gpu *g, gkm_image *im)
 {
     for (int k = 0; k < im->nblk; k++) {
@@ -385,7 +414,7 @@ static int ensure_deltas(gkm_gpu *g, int L, int d)
     if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc); /* h is pageable and freed below */
     free(h);
     if (e != cudaSuccess) { gkm_set_error("CUDA: mask upload: %s", cudaGetErrorString(e)); return 1; }
-    g->delta_L = L; g->delta_d = d; g->ndelta = (int) nd;
+    g->delta_L = L; g->delta_d = d; g->ndelta = (int) nd; g->ncold = (int) gkm_idx_cold_count(L, d);
     return 0;
 }
 
@@ -395,7 +424,7 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
     const int L = p->param.L;
     if (ensure_deltas(g, L, p->param.d)) return 1;
     if (!im->blk) {
-        const int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
+        const int cap = index_block_cap(p);
         if (cap <= 0) { gkm_set_error("index variant: sequences too long for shared memory"); return 1; }
         const int nblk = (p->n + cap - 1) / cap;
         int cols = (((p->n + nblk - 1) / nblk) + 31) & ~31;
@@ -459,7 +488,7 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     int v = base_variant(p);
     if ((opt == GKM_KERNEL_AUTO || opt == GKM_KERNEL_INDEX) && nrows > 0 && ncols > 0 &&
         gkm_idx_supported(p->param.L, p->param.d, p->nbins)) {
-        const int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
+        const int cap = index_block_cap(p);
         const int nblk_all = cap > 0 ? (p->n + cap - 1) / cap : 0;
         int ok = cap > 0 && p->n <= (long long) nblk_all * (long long) GKM_IDX_MAX_COLS;
         int blocks = 0;
@@ -905,9 +934,11 @@ static int decision_slice(gkm_decjob *j)
     kp.col_begin = kp.col_base = j->col0; kp.col_end = j->col0 + j->ncols;
     kp.row_base = j->row0;
     int launches = 0;
-    for (int r = j->row0; !rc && r < j->row0 + j->nrows; r += 8192) {
+    /* index variant: whole waves of rows per launch, and a bounded cold-bin scratch */
+    const int rows_per_launch = (ds->variant == GKM_KERNEL_INDEX) ? 16 * 148 : 8192;
+    for (int r = j->row0; !rc && r < j->row0 + j->nrows; r += rows_per_launch) {
         kp.row_begin = r;
-        kp.row_end = (r + 8192 < j->row0 + j->nrows) ? r + 8192 : j->row0 + j->nrows;
+        kp.row_end = (r + rows_per_launch < j->row0 + j->nrows) ? r + rows_per_launch : j->row0 + j->nrows;
         rc = launch_hist(p, &ds->img[j->slot], g, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
     }
     if (!rc) {

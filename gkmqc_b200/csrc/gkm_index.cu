@@ -19,6 +19,10 @@
 #include "gkm_index_dev.h"
 #include "gkm_internal.h"
 
+#ifndef GKM_MAX_BINS
+#define GKM_MAX_BINS 16
+#endif
+
 #define GKM_IDX_THREADS 1024
 #define GKM_IDX_UNROLL 4
 
@@ -182,38 +186,74 @@ fail:
 /* hot loop                                                             */
 /* ------------------------------------------------------------------ */
 /* one posting against the wanted column range [blo, bhi): the column field of an empty word / end marker is
- * all ones, so `b < bhi` is the validity test as well */
-template <bool WEIGHTED, bool RANGE>
+ * all ones, so `b < bhi` is the validity test as well.  COLD: the bin lives in global memory (L2). */
+template <bool WEIGHTED, bool RANGE, bool COLD>
 __device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, uint32_t bhi, int w)
 {
     const uint32_t b = e & GKM_IDX_COL_MASK;
     bool ok = b < bhi;
     if (RANGE) ok = ok && b >= blo;
     if (ok) atomicAdd(Hm + (RANGE ? b - blo : b), WEIGHTED ? w * (int) (e >> GKM_IDX_COL_BITS) : 1);
+    (void) COLD;
 }
 
 /* the postings of one slot; lists are sorted by column, so the tail of a list is skipped as soon as one
  * posting falls behind the range */
-template <bool WEIGHTED, bool RANGE>
+template <bool WEIGHTED, bool RANGE, bool COLD>
 __device__ __forceinline__ void idx_slot(const uint4 sl, const uint32_t *__restrict__ ovf, int32_t *Hm,
                                          uint32_t blo, uint32_t bhi, int w)
 {
-    idx_hit<WEIGHTED, RANGE>(Hm, sl.x, blo, bhi, w);
-    idx_hit<WEIGHTED, RANGE>(Hm, sl.y, blo, bhi, w);
-    idx_hit<WEIGHTED, RANGE>(Hm, sl.z, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.x, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.y, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.z, blo, bhi, w);
     if (!(sl.w & GKM_IDX_PTR)) {
-        idx_hit<WEIGHTED, RANGE>(Hm, sl.w, blo, bhi, w);
+        idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.w, blo, bhi, w);
     } else if (sl.w != GKM_IDX_EMPTY && (sl.z & GKM_IDX_COL_MASK) < bhi) {
         /* five or more postings (1.7 % of the slots at 10k x 300 bp): the rest, 16 bytes at a time */
         const uint4 *q = reinterpret_cast<const uint4 *>(ovf + (sl.w & ~GKM_IDX_PTR));
         for (;;) {
             const uint4 v = __ldg(q++);
-            idx_hit<WEIGHTED, RANGE>(Hm, v.x, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE>(Hm, v.y, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE>(Hm, v.z, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE>(Hm, v.w, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.x, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.y, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.z, blo, bhi, w);
+            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.w, blo, bhi, w);
             if ((v.w & GKM_IDX_COL_MASK) >= bhi) break;
         }
+    }
+}
+
+/* probes of the masks [t_begin, t_end): tiles of <= 1024 masks; inside a tile a thread keeps its mask and
+ * walks the query L-mers, GKM_IDX_UNROLL independent slot loads in flight.  A short tile is shared by
+ * several "phases" of threads that take interleaved query L-mers.  Hbins = bin 0 of this part of the
+ * histogram (shared memory, or the global scratch row when COLD), mbase = the m of that bin. */
+template <bool WEIGHTED, bool RANGE, bool COLD>
+__device__ __forceinline__ void idx_probe(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
+                                          int nq, int32_t *Hbins, int mbase, int ldh, uint32_t blo, uint32_t bhi)
+{
+    const int tid = (int) threadIdx.x;
+    const uint4 *__restrict__ tab = r.tab;
+    for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
+        const int rem = min(GKM_IDX_THREADS, t_end - t0);
+        int T = (rem + 31) & ~31;
+        if (rem < 32) { T = 1; while (T < rem) T <<= 1; }
+        const int nph = GKM_IDX_THREADS / T;
+        const int ph = tid / T, tt = tid - ph * T;
+        if (ph >= nph || tt >= rem) continue;
+        const uint32_t dl = r.deltas[t0 + tt];
+        const uint32_t dx = dl & 0x0FFFFFFFu;
+        int32_t *Hm = Hbins + (size_t) ((int) (dl >> 28) - mbase) * (size_t) ldh;
+        const int step = nph * GKM_IDX_UNROLL;
+        int xi = ph;
+        for (; xi + (GKM_IDX_UNROLL - 1) * nph < nq; xi += step) {
+            uint4 sl[GKM_IDX_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) sl[u] = __ldg(tab + (xq[xi + u * nph] ^ dx));
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++)
+                idx_slot<WEIGHTED, RANGE, COLD>(sl[u], r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi + u * nph] : 1);
+        }
+        for (; xi < nq; xi += nph)
+            idx_slot<WEIGHTED, RANGE, COLD>(__ldg(tab + (xq[xi] ^ dx)), r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
     }
 }
 
@@ -225,6 +265,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     const int tid = (int) threadIdx.x;
     const int a = p.row_begin + (int) blockIdx.x;
     const int L = p.L, nb = p.nbins;
+    const int nhot = nb < GKM_IDX_HOT_BINS ? nb : GKM_IDX_HOT_BINS, ncoldb = nb - nhot;
     /* wanted columns of this row inside the block, relative to the block's first column */
     uint32_t blo = (uint32_t) r.blo, bhi = (uint32_t) r.bhi;
     if (p.mode == GKM_MODE_LOWER) {
@@ -234,13 +275,16 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
     if (bhi <= blo) return;
     const int ldh = r.ldh;
-    int32_t *H = reinterpret_cast<int32_t *>(smem);
-    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nb * (size_t) ldh * 4);
+    int32_t *H = reinterpret_cast<int32_t *>(smem);                       /* bins ncoldb .. nb-1 */
+    int32_t *C = r.cold + (size_t) blockIdx.x * (size_t) ncoldb * (size_t) ldh; /* bins 0 .. ncoldb-1, this row's scratch */
+    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nhot * (size_t) ldh * 4);
     uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
 
     const int ncol = (int) (bhi - blo);
-    for (int m = 0; m < nb; m++)
+    for (int m = 0; m < nhot; m++)
         for (int i = tid; i < ncol; i += GKM_IDX_THREADS) H[m * ldh + i] = 0;
+    for (int m = 0; m < ncoldb; m++)
+        for (int i = tid; i < ncol; i += GKM_IDX_THREADS) __stcg(C + (size_t) m * ldh + i, 0);
     /* forward L-mers of the query (window ending at e, L-1 <= e < len) */
     const int len = p.lens[a], nq = len - L + 1;
     {
@@ -253,33 +297,8 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
     __syncthreads();
 
-    /* probes: tiles of <= 1024 masks; inside a tile a thread keeps its mask and walks the query
-     * L-mers, GKM_IDX_UNROLL independent slot loads in flight.  A short tile is shared by several
-     * "phases" of threads that take interleaved query L-mers. */
-    const uint4 *__restrict__ tab = r.tab;
-    for (int t0 = 0; t0 < r.ndelta; t0 += GKM_IDX_THREADS) {
-        const int rem = min(GKM_IDX_THREADS, r.ndelta - t0);
-        int T = (rem + 31) & ~31;
-        if (rem < 32) { T = 1; while (T < rem) T <<= 1; }
-        const int nph = GKM_IDX_THREADS / T;
-        const int ph = tid / T, tt = tid - ph * T;
-        if (ph >= nph || tt >= rem) continue;
-        const uint32_t dl = r.deltas[t0 + tt];
-        const uint32_t dx = dl & 0x0FFFFFFFu;
-        int32_t *Hm = H + (int) (dl >> 28) * ldh;
-        const int step = nph * GKM_IDX_UNROLL;
-        int xi = ph;
-        for (; xi + (GKM_IDX_UNROLL - 1) * nph < nq; xi += step) {
-            uint4 sl[GKM_IDX_UNROLL];
-#pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) sl[u] = __ldg(tab + (xq[xi + u * nph] ^ dx));
-#pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++)
-                idx_slot<WEIGHTED, RANGE>(sl[u], r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi + u * nph] : 1);
-        }
-        for (; xi < nq; xi += nph)
-            idx_slot<WEIGHTED, RANGE>(__ldg(tab + (xq[xi] ^ dx)), r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
-    }
+    if (r.ncold > 0) idx_probe<WEIGHTED, RANGE, true>(r, 0, r.ncold, xq, wq, nq, C, 0, ldh, blo, bhi);
+    idx_probe<WEIGHTED, RANGE, false>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi);
     __syncthreads();
 
     /* epilogue: histogram -> normalised double, the reference's operation order */
@@ -287,13 +306,16 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     const double sqa = (p.out || p.decision) ? p.sqnorm[a] : 1.0;
     for (int i = tid; i < ncol; i += GKM_IDX_THREADS) {
         const int b_g = r.cb + (int) blo + i;
-        double kraw = 0.0;
+        int32_t h[GKM_MAX_BINS];
+        for (int m = 0; m < ncoldb; m++) h[m] = __ldcg(C + (size_t) m * ldh + i);
+        for (int m = 0; m < nhot; m++) h[ncoldb + m] = H[m * ldh + i];
         if (p.hist) {
             int32_t *dst = p.hist + ((size_t) (a - p.row_base) * (size_t) p.hist_cols + (size_t) (b_g - p.col_base)) * (size_t) nb;
-            for (int m = 0; m < nb; m++) dst[m] = H[m * ldh + i];
+            for (int m = 0; m < nb; m++) dst[m] = h[m];
         }
         if (!p.out && !p.decision) continue;
-        for (int m = 0; m < nb; m++) kraw = __dadd_rn(kraw, __dmul_rn(p.w[m], (double) H[m * ldh + i]));
+        double kraw = 0.0;
+        for (int m = 0; m < nb; m++) kraw = __dadd_rn(kraw, __dmul_rn(p.w[m], (double) h[m]));
         double v = __ddiv_rn(kraw, __dmul_rn(sqa, p.sqnorm[b_g]));
         if (p.kernel_type == 3 || p.kernel_type == 5) v = exp(__dmul_rn(p.gamma, __dadd_rn(v, -1.0)));
         /* streaming store: the matrix is written once and must not push the slot table out of L2 */
@@ -317,14 +339,21 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
 
 unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted)
 {
-    size_t s = (size_t) nbins * (size_t) ldh * 4 + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
+    const int nhot = nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS;
+    size_t s = (size_t) nhot * (size_t) ldh * 4 + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
     return (unsigned) ((s + 15) & ~(size_t) 15);
+}
+
+size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows)
+{
+    const int ncoldb = nbins > GKM_IDX_HOT_BINS ? nbins - GKM_IDX_HOT_BINS : 0;
+    return (size_t) rows * (size_t) ncoldb * (size_t) ldh * 4;
 }
 
 int gkm_idx_max_cols(int nbins, int maxq, int weighted)
 {
     const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - (long long) maxq * (weighted ? 5 : 4);
-    long long cols = budget / (4LL * nbins);
+    long long cols = budget / (4LL * (nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS));
     cols &= ~31LL;
     if (cols > (long long) GKM_IDX_MAX_COLS) cols = GKM_IDX_MAX_COLS & ~31;
     return cols < 32 ? 0 : (int) cols;

@@ -15,7 +15,9 @@
  *                 most d non-zero 2-bit fields (sum_m C(L,m) 3^m of them: 4984 at L=11,
  *                 d=3) the slot of y = x ^ delta is fetched; each posting (b, wt) found
  *                 there is one L-mer pair at Hamming distance m = weight(delta), added as
- *                 wt_a * wt_b to the row histogram H[m][b] held in shared memory.
+ *                 wt_a * wt_b to the row histogram H[m][b]: bins d and d-1 (99 % of the hits
+ *                 on random sequences) in shared memory, the rarer ones in an L2-resident
+ *                 scratch row, so that a block holds twice as many columns.
  *
  * Work per entry is ~290 slot probes + ~200 shared atomics instead of 168 200 pair
  * evaluations; the bound is the L1/LSU sector rate of the random slot probes, not the
@@ -41,6 +43,7 @@ extern "C" {
 #define GKM_IDX_COL_BITS 23
 #define GKM_IDX_COL_MASK 0x007FFFFFu  /* posting = column | weight << 23, bit 31 clear */
 #define GKM_IDX_MAX_COLS 0x007FFFFEu
+#define GKM_IDX_HOT_BINS 2            /* bins d and d-1 (99 % of the hits) live in shared memory, the others in L2 */
 
 #if defined(__CUDACC__)
 #define GKM_IDX_HD __host__ __device__ __forceinline__
@@ -67,10 +70,12 @@ GKM_IDX_HD uint32_t gkm_idx_posting(uint32_t col, uint32_t wt) { return col | (w
 /* number of XOR masks with at most d substituted bases: sum_{m<=d} C(L,m) 3^m (0 if it overflows 2^31) */
 long long gkm_idx_delta_count(int L, int d);
 
-/* the masks, in probe order: out[i] = mask | m << 28.  Masks that differ only in the low bases are
+/* the masks, in probe order: out[i] = mask | m << 28.  The masks of the cold bins (m <= d - 2,
+ * gkm_idx_cold_count of them) come first; inside each part masks that differ only in the low bases are
  * adjacent (adjacent lanes -> one line of the table), largest groups first.
  * Returns the number written (= gkm_idx_delta_count), or -1. */
 long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap);
+long long gkm_idx_cold_count(int L, int d);
 
 /* is the variant applicable at all (table and masks representable)? */
 int gkm_idx_supported(int L, int d, int nbins);

@@ -29,7 +29,9 @@ struct gkm_idx_build_args {
 
 struct gkm_idx_rowargs {
     const uint4 *tab; const uint32_t *ovf; const uint32_t *deltas;
-    int ndelta;
+    int ndelta;    /* masks in all */
+    int ncold;     /* the first ncold masks belong to the cold bins (m <= d - 2) */
+    int32_t *cold; /* [rows of the launch][cold bins][ldh] scratch in global memory, zeroed by the kernel */
     int cb;        /* first column of the index block */
     int blo, bhi;  /* wanted columns, relative to cb */
     int ldh;       /* histogram row stride in shared memory (>= bhi - blo) */
@@ -39,9 +41,11 @@ struct gkm_idx_rowargs {
 size_t gkm_idx_tab_bytes(int L);
 size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out);
 int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st);
-/* most columns one block may hold so that nbins histogram rows + the query fit 227 KB of shared memory (0: none) */
+/* most columns one block may hold so that the hot histogram rows + the query fit 227 KB of shared memory (0: none) */
 int gkm_idx_max_cols(int nbins, int maxq, int weighted);
 unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted);
+/* bytes of cold-bin scratch a launch of `rows` rows needs */
+size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows);
 /* rows [kp->row_begin, kp->row_end) against the wanted columns of one block; outputs as in gkm_kparams */
 int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted, cudaStream_t st);
 

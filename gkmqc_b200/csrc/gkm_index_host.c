@@ -38,6 +38,7 @@ struct emit_ctx {
     uint32_t *out;
     long long n, cap;
     int L, d, lb;
+    int m_lo, m_hi; /* only masks with m_lo <= m <= m_hi are emitted in this pass */
 };
 
 /* every combination of the low bases with at most `budget` substitutions, in ascending address order */
@@ -47,7 +48,7 @@ static void emit_low(struct emit_ctx *c, uint32_t du, int mu, int budget)
     for (int low = 0; low < nlow; low++) {
         int ml = 0;
         for (int t = 0; t < c->lb; t++) ml += ((low >> (2 * t)) & 3) != 0;
-        if (ml > budget) continue;
+        if (ml > budget || mu + ml < c->m_lo || mu + ml > c->m_hi) continue;
         if (c->n < c->cap) c->out[c->n] = (du | (uint32_t) low) | ((uint32_t) (mu + ml) << 28);
         c->n++;
     }
@@ -67,9 +68,20 @@ long long gkm_idx_deltas(int L, int d, uint32_t *out, long long cap)
     if (d > L) d = L;
     struct emit_ctx c;
     c.out = out; c.n = 0; c.cap = cap; c.L = L; c.d = d; c.lb = gkm_idx_lowb(L);
-    /* fewest upper substitutions first: those leave the largest groups of low-base variants */
+    /* the masks of the cold bins (m <= d - 2) first, then the others; inside each part the fewest upper
+     * substitutions first: those leave the largest groups of low-base variants */
+    c.m_lo = 0; c.m_hi = d - GKM_IDX_HOT_BINS;
+    if (c.m_hi >= 0)
+        for (int mu = 0; mu <= c.m_hi && mu <= L - c.lb; mu++) rec_upper(&c, c.lb, mu, 0u, mu);
+    c.m_lo = c.m_hi + 1; c.m_hi = d;
+    if (c.m_lo < 0) c.m_lo = 0;
     for (int mu = 0; mu <= d && mu <= L - c.lb; mu++) rec_upper(&c, c.lb, mu, 0u, mu);
     return (c.n <= cap) ? c.n : -1;
+}
+
+long long gkm_idx_cold_count(int L, int d)
+{
+    return d >= GKM_IDX_HOT_BINS ? gkm_idx_delta_count(L, d - GKM_IDX_HOT_BINS) : 0;
 }
 
 int gkm_idx_supported(int L, int d, int nbins)

@@ -5,6 +5,7 @@
  *                                           index = inverted L-mer index; auto picks diag or index by a cost model)
  *   GKM_MAX_L    = 12 | 16                 ceiling of the parameter gate in gkm_main_pywrapper
  *   GKM_CHUNK_MB = n                       upper bound of one chunk's dense output
+ *   GKM_INDEX_COLS = n                     upper bound of the columns of one index block (tests: forces several blocks)
  *   GKM_DEVICES  = "0,1,.."                GPUs to use (gkm_device.cu)
  */
 #include <stdlib.h>
@@ -19,6 +20,7 @@ static int g_max_L = 12;
 static int g_chunk_mb = 64;
 static int g_tile_rows = 0;
 static int g_diag_flavor = -1;
+static int g_index_cols = 0;
 
 static int parse_kernel(const char *v, int *out)
 {
@@ -40,6 +42,7 @@ static void load_env(void)
     if ((v = getenv("GKM_MAX_L")) != NULL) { int x = atoi(v); if (x == 12 || x == 16) g_max_L = x; }
     if ((v = getenv("GKM_CHUNK_MB")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 4096) g_chunk_mb = x; }
     if ((v = getenv("GKM_DIAG_FLAVOR")) != NULL) { int x = atoi(v); if (x >= -1 && x <= 7) g_diag_flavor = x; }
+    if ((v = getenv("GKM_INDEX_COLS")) != NULL) { int x = atoi(v); if (x >= 32) g_index_cols = x & ~31; }
     if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
 }
 
@@ -48,6 +51,7 @@ int gkm_opt_max_L(void) { load_env(); return g_max_L; }
 int gkm_opt_chunk_mb(void) { load_env(); return g_chunk_mb; }
 int gkm_opt_tile_rows(void) { load_env(); return g_tile_rows; }
 int gkm_opt_diag_flavor(void) { load_env(); return g_diag_flavor; }
+int gkm_opt_index_cols(void) { load_env(); return g_index_cols; }
 
 int gkmb200_set_option(const char *key, const char *value)
 {
@@ -71,6 +75,11 @@ int gkmb200_set_option(const char *key, const char *value)
     if (!strcmp(key, "diag_flavor")) { /* A/B switch for the pipe-balancing variants of the diag kernel */
         if (x < -1 || x > 7) { gkm_set_error("diag_flavor out of range"); return 1; }
         g_diag_flavor = x;
+        return 0;
+    }
+    if (!strcmp(key, "index_cols")) { /* upper bound of the columns of one index block (0 = what fits shared memory) */
+        if (x != 0 && x < 32) { gkm_set_error("index_cols must be 0 or >= 32"); return 1; }
+        g_index_cols = x & ~31;
         return 0;
     }
     if (!strcmp(key, "tile_rows")) {

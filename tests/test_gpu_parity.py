@@ -122,6 +122,41 @@ def test_seeded_against_oracle(kernel_type, L, k, d, length, ragged, variant):
         np.testing.assert_allclose(dv, Kr @ alpha + 0.25, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("kernel_type,L,k,d,cols", [(2, 11, 7, 3, 32), (4, 10, 6, 3, 64), (2, 8, 4, 4, 32), (4, 6, 5, 1, 32), (0, 9, 9, 0, 32)])
+def test_index_column_blocks(kernel_type, L, k, d, cols):
+    """index variant with the columns cut into several index blocks (what a problem larger than one
+    shared-memory histogram row gets), long posting lists (short L, repeats) and a column window that
+    starts inside a block"""
+    n = 150
+    seqs = random_seqs(n, 120, seed=11 * L + d + kernel_type, ragged=True)
+    seqs = [s if len(s) >= L else s + "ACGT" * 4 for s in seqs]
+    seqs[3] = seqs[2]
+    seqs[70] = "A" * 100
+    seqs[71] = "ACAC" * 25
+    seqs[140] = seqs[2]
+    o = pyoracle.Oracle(kernel_type, L, k, d, 50, 50.0, 0.7)
+    capi.set_option("kernel", "index")
+    capi.set_option("index_cols", str(cols))
+    try:
+        with capi.Problem(kernel_type, L, k, d, 50, 50.0, 0.7) as P:
+            for s in seqs:
+                o.add(s)
+                P.add(s)
+            Ko, Ho = o.matrix_lower()
+            assert np.array_equal(P.hist_block(0, n, 0, n, lower=True), Ho)
+            assert P.stats()["kernel_variant"] == 4
+            check_kmat(P.kernel_lower(), Ko, kernel_type)
+            Kr, Hr = o.rect(np.arange(100, n), 100)
+            assert np.array_equal(P.hist_block(100, n - 100, 40, 60), Hr[:, 40:100])
+            check_kmat(P.kernel_block(100, n - 100, 40, 60), Kr[:, 40:100], kernel_type)
+            alpha = np.random.default_rng(2).standard_normal(60)
+            dv = P.decision_values(100, n - 100, 40, 60, alpha, bias=-0.5)
+            np.testing.assert_allclose(dv, Kr[:, 40:100] @ alpha - 0.5, rtol=1e-9, atol=1e-12)
+    finally:
+        capi.set_option("index_cols", "0")
+        capi.set_option("kernel", "auto")
+
+
 def test_edge_cases(variant):
     L, k, d = 11, 7, 3
     seqs = ["ACGTACGTACG",               # exactly one L-mer

@@ -19,6 +19,8 @@ def lib(product_lib):
     product_lib.gkm_idx_deltas.restype = ctypes.c_longlong
     product_lib.gkm_idx_deltas.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
     product_lib.gkm_idx_supported.argtypes = [ctypes.c_int] * 3
+    product_lib.gkm_idx_cold_count.restype = ctypes.c_longlong
+    product_lib.gkm_idx_cold_count.argtypes = [ctypes.c_int, ctypes.c_int]
     product_lib.gkm_idx_cost_ms.restype = ctypes.c_double
     product_lib.gkm_idx_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_int,
                                             ctypes.c_longlong, ctypes.c_double]
@@ -62,10 +64,17 @@ def test_mask_list_is_the_hamming_ball(L, d, lib):
         assert sum(int(u != v) for u, v in zip(x, y)) == m
         assert code_of(y, L) == y_code
         seen.add(y_code)
-    # masks that differ only in the low bases are adjacent: at most one group per upper mask
-    upper = masks >> 4 if L >= 2 else masks
-    changes = int(np.count_nonzero(np.diff(upper.astype(np.int64)))) + 1
-    assert changes == len(np.unique(upper))
+    # the masks of the cold bins (m <= d - 2) come first; inside each part masks that differ only in the low
+    # bases are adjacent: at most one group per upper mask
+    ncold = lib.gkm_idx_cold_count(L, d)
+    assert ncold == sum(comb(L, m) * 3 ** m for m in range(min(d, L) - 1))
+    assert np.all(ms[:ncold] <= d - 2) and np.all(ms[ncold:] >= max(0, min(d, L) - 1))
+    for part in (masks[:ncold], masks[ncold:]):
+        if len(part) == 0:
+            continue
+        upper = part >> 4
+        changes = int(np.count_nonzero(np.diff(upper.astype(np.int64)))) + 1
+        assert changes == len(np.unique(upper))
 
 
 def test_supported_and_cost_model(lib):
