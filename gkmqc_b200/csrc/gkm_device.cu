@@ -244,9 +244,10 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
         if (hi <= lo) continue;
         if (!b->built) { gkm_set_error("index block %d is not built", k); return 1; }
         gkm_idx_rowargs ra;
-        ra.tab = b->tab; ra.ovf = b->ovf; ra.deltas = g->d_deltas; ra.ndelta = g->ndelta;
+        ra.fmt = b->fmt; ra.tab = b->tab; ra.ovf = b->ovf; ra.deltas = g->d_deltas; ra.ndelta = g->ndelta;
         ra.cb = b->cb; ra.blo = lo - b->cb; ra.bhi = hi - b->cb;
         ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
+        ra.blk_cols = b->ce - b->cb;
         ra.maxq = 32 * p->Wa;
         ra.ncold = g->ncold;
         {   /* cold-bin scratch of this stream, grown on demand (the stream is drained before a block is replaced) */
@@ -451,8 +452,10 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
         const size_t sbytes = gkm_idx_scratch_bytes(P, L, &cub_bytes);
         void *scratch = NULL, *d_offs = NULL;
         size_t scratch_got = 0, offs_got = 0;
-        int rc = pool_alloc(g, (void **) &b->tab, &b->tab_bytes, gkm_idx_tab_bytes(L)) ||
-                 pool_alloc(g, (void **) &b->ovf, &b->ovf_bytes, (2 * P + 4) * 4) ||
+        /* unit-weight kernel types get the compact 16-bit slots (a block never holds more than 16384 columns) */
+        b->fmt = (!p->weighted && nc <= GKM_IDX_C16_MAX_COLS && !gkm_opt_index_wide()) ? GKM_IDX_FMT_C16 : GKM_IDX_FMT_P32;
+        int rc = pool_alloc(g, (void **) &b->tab, &b->tab_bytes, gkm_idx_tab_bytes(L, b->fmt)) ||
+                 pool_alloc(g, (void **) &b->ovf, &b->ovf_bytes, gkm_idx_ovf_bytes(P, b->fmt)) ||
                  pool_alloc(g, &scratch, &scratch_got, sbytes) ||
                  pool_alloc(g, &d_offs, &offs_got, (size_t) nc * 4);
         if (!rc) {
@@ -464,7 +467,7 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
             a.planes = im->planes; a.lens = im->lens; a.wend = p->weighted ? im->wend : NULL;
             a.W = p->Wmax; a.L = L; a.cb = b->cb; a.ce = b->ce;
             a.offs = (const uint32_t *) d_offs; a.P = P; a.scratch = scratch; a.cub_bytes = cub_bytes;
-            a.tab = b->tab; a.ovf = b->ovf;
+            a.fmt = b->fmt; a.tab = b->tab; a.ovf = b->ovf;
             rc = gkm_idx_build(&a, g->sc);
         }
         /* pageable source and recycled scratch: wait for the build before letting go of them */
@@ -497,7 +500,7 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             if (cols > cap) cols = cap;
             blocks = (col0 + ncols - 1) / cols - col0 / cols + 1;
             /* at most 8 GiB of slot tables per GPU */
-            if ((double) blocks * (double) gkm_idx_tab_bytes(p->param.L) > 8.0 * 1073741824.0) ok = 0;
+            if ((double) blocks * (double) gkm_idx_tab_bytes(p->param.L, p->weighted ? GKM_IDX_FMT_P32 : GKM_IDX_FMT_C16) > 8.0 * 1073741824.0) ok = 0;
         }
         if (ok && opt == GKM_KERNEL_AUTO) {
             double sum = 0.0;

@@ -13,6 +13,7 @@
  *                         (ascending-m sum, one division, no FMA; libgkm.c:576-582,1169-1179).
  */
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -24,7 +25,11 @@
 #endif
 
 #define GKM_IDX_THREADS 1024
+#ifndef GKM_IDX_UNROLL
 #define GKM_IDX_UNROLL 4
+#endif
+#define GKM_IDX_QCAP 64 /* queued overflow walks per warp: < 32 waiting + <= 32 new */
+#define GKM_IDX_QBYTES ((GKM_IDX_THREADS / 32) * GKM_IDX_QCAP * 8)
 
 /* ------------------------------------------------------------------ */
 /* build                                                                */
@@ -78,7 +83,7 @@ __device__ __forceinline__ uint32_t idx_lower(const unsigned long long *keys, ui
 }
 
 __global__ void __launch_bounds__(256)
-gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, uint32_t *__restrict__ runlen, uint32_t *__restrict__ need)
+gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int fmt, uint32_t *__restrict__ runlen, uint32_t *__restrict__ need)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -97,7 +102,10 @@ gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, uin
         len = idx_upper(keys, lo, hi, code) - i;
     }
     runlen[i] = len;
-    need[i] = (len >= 5) ? ((len - 3u + 4u) & ~3u) : 0u; /* postings 3.. of the run plus end markers up to a multiple of 4 */
+    /* overflow entries of a run of 5 or more: P32 keeps postings 3.. (32-bit entries, quads), C16 columns 2..
+     * (16-bit entries, octets); both padded with at least one end marker */
+    if (fmt == GKM_IDX_FMT_C16) need[i] = (len >= 5) ? ((len - 2u + 8u) & ~7u) : 0u;
+    else need[i] = (len >= 5) ? ((len - 3u + 4u) & ~3u) : 0u;
 }
 
 __global__ void __launch_bounds__(256)
@@ -136,7 +144,46 @@ gkm_idx_fill_kernel(const unsigned long long *__restrict__ keys, uint32_t P, con
     }
 }
 
-size_t gkm_idx_tab_bytes(int L) { return ((size_t) 1 << (2 * L)) * sizeof(uint4); }
+__global__ void __launch_bounds__(256)
+gkm_idx_fill_c16_kernel(const unsigned long long *__restrict__ keys, uint32_t P, const uint32_t *__restrict__ runlen,
+                        const uint32_t *__restrict__ ovfofs, uint2 *__restrict__ tab, uint16_t *__restrict__ ovf)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const unsigned long long key = keys[i];
+    const uint32_t code = (uint32_t) (key >> 32);
+    uint32_t lb = i;
+    if (runlen[i] == 0) {
+        uint32_t hi = i, lo = 0, step = 1;
+        for (;;) {
+            if (hi < step) { lo = 0; break; }
+            const uint32_t probe = hi - step;
+            if ((uint32_t) (keys[probe] >> 32) != code) { lo = probe + 1; break; }
+            hi = probe;
+            step <<= 1;
+        }
+        lb = idx_lower(keys, lo, hi, code);
+    }
+    const uint32_t len = runlen[lb], r = i - lb;
+    const uint16_t col = (uint16_t) ((key >> 8) & 0x7FFFu);
+    uint16_t *slot = reinterpret_cast<uint16_t *>(tab + code);
+    if (len <= 4) {
+        slot[r] = col;
+    } else {
+        if (r < 2) slot[r] = col;
+        else ovf[ovfofs[lb] + r - 2] = col;
+        if (r == 0) {
+            reinterpret_cast<uint32_t *>(tab + code)[1] = GKM_IDX_PTR | ovfofs[lb];
+            const uint32_t end = (len - 2u + 8u) & ~7u;
+            for (uint32_t t = len - 2; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_C16_NONE;
+        }
+    }
+}
+
+size_t gkm_idx_tab_bytes(int L, int fmt) { return ((size_t) 1 << (2 * L)) * (fmt == GKM_IDX_FMT_C16 ? sizeof(uint2) : sizeof(uint4)); }
+
+/* overflow demand is at most 2 entries per posting in either format */
+size_t gkm_idx_ovf_bytes(size_t P, int fmt) { return (2 * P + 16) * (fmt == GKM_IDX_FMT_C16 ? 2 : 4); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
 
@@ -163,17 +210,18 @@ int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st)
     void *cub_tmp = s;
     size_t cub_bytes = a->cub_bytes;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(a->tab, 0xFF, gkm_idx_tab_bytes(a->L), st)) != cudaSuccess) goto fail;
+    if ((e = cudaMemsetAsync(a->tab, 0xFF, gkm_idx_tab_bytes(a->L, a->fmt), st)) != cudaSuccess) goto fail;
     if (a->wend) gkm_idx_keys_kernel<true><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
     else gkm_idx_keys_kernel<false><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
     if ((e = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, (int) P, 8, 32 + 2 * a->L, st)) != cudaSuccess) goto fail;
     {
         const unsigned blocks = (unsigned) ((P + 255) / 256);
-        gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, need);
+        gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, a->fmt, runlen, need);
         uint32_t *ovfofs = (uint32_t *) keys_a; /* the unsorted keys are dead now */
         cub_bytes = a->cub_bytes;
         if ((e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, need, ovfofs, (int) P, st)) != cudaSuccess) goto fail;
-        gkm_idx_fill_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, a->tab, a->ovf);
+        if (a->fmt == GKM_IDX_FMT_C16) gkm_idx_fill_c16_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, (uint2 *) a->tab, (uint16_t *) a->ovf);
+        else gkm_idx_fill_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, (uint4 *) a->tab, a->ovf);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) goto fail;
     return 0;
@@ -185,53 +233,102 @@ fail:
 /* ------------------------------------------------------------------ */
 /* hot loop                                                             */
 /* ------------------------------------------------------------------ */
-/* one posting against the wanted column range [blo, bhi): the column field of an empty word / end marker is
- * all ones, so `b < bhi` is the validity test as well.  COLD: the bin lives in global memory (L2). */
-template <bool WEIGHTED, bool RANGE, bool COLD>
-__device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, uint32_t bhi, int w)
+/* One posting against the wanted column range [blo, bhi): H[b] += v iff blo <= b < bhi.  The column field of an
+ * empty word / end marker is all ones, so the range test is the validity test as well.  (ptxas turns a
+ * predicated red.shared back into a branch around ATOMS, so this is plain C++.) */
+template <bool RANGE>
+__device__ __forceinline__ void idx_red(int32_t *Hm, uint32_t b, uint32_t blo, uint32_t bhi, int v)
 {
-    const uint32_t b = e & GKM_IDX_COL_MASK;
     bool ok = b < bhi;
     if (RANGE) ok = ok && b >= blo;
-    if (ok) atomicAdd(Hm + (RANGE ? b - blo : b), WEIGHTED ? w * (int) (e >> GKM_IDX_COL_BITS) : 1);
-    (void) COLD;
+    if (ok) atomicAdd(Hm + (RANGE ? b - blo : b), v);
 }
 
-/* the postings of one slot; lists are sorted by column, so the tail of a list is skipped as soon as one
- * posting falls behind the range */
-template <bool WEIGHTED, bool RANGE, bool COLD>
-__device__ __forceinline__ void idx_slot(const uint4 sl, const uint32_t *__restrict__ ovf, int32_t *Hm,
-                                         uint32_t blo, uint32_t bhi, int w)
+template <bool WEIGHTED, bool RANGE>
+__device__ __forceinline__ void idx_hit(int32_t *Hm, uint32_t e, uint32_t blo, uint32_t bhi, int w)
 {
-    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.x, blo, bhi, w);
-    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.y, blo, bhi, w);
-    idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.z, blo, bhi, w);
-    if (!(sl.w & GKM_IDX_PTR)) {
-        idx_hit<WEIGHTED, RANGE, COLD>(Hm, sl.w, blo, bhi, w);
-    } else if (sl.w != GKM_IDX_EMPTY && (sl.z & GKM_IDX_COL_MASK) < bhi) {
-        /* five or more postings (1.7 % of the slots at 10k x 300 bp): the rest, 16 bytes at a time */
-        const uint4 *q = reinterpret_cast<const uint4 *>(ovf + (sl.w & ~GKM_IDX_PTR));
-        for (;;) {
-            const uint4 v = __ldg(q++);
-            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.x, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.y, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.z, blo, bhi, w);
-            idx_hit<WEIGHTED, RANGE, COLD>(Hm, v.w, blo, bhi, w);
-            if ((v.w & GKM_IDX_COL_MASK) >= bhi) break;
-        }
+    idx_red<RANGE>(Hm, e & GKM_IDX_COL_MASK, blo, bhi, WEIGHTED ? w * (int) (e >> GKM_IDX_COL_BITS) : 1);
+}
+
+/* ---- 16-byte slots (GKM_IDX_FMT_P32) ---- */
+/* inline postings of one slot; returns the offset of the overflow list that still has to be walked, or ~0u.
+ * Lists are sorted by column, so a list whose third posting is behind the range needs no walk. */
+template <bool WEIGHTED, bool RANGE>
+__device__ __forceinline__ uint32_t idx_slot(const uint4 sl, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+{
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.x, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.y, blo, bhi, w);
+    idx_hit<WEIGHTED, RANGE>(Hm, sl.z, blo, bhi, w);
+    if (!(sl.w & GKM_IDX_PTR)) { idx_hit<WEIGHTED, RANGE>(Hm, sl.w, blo, bhi, w); return ~0u; }
+    return (sl.w != GKM_IDX_EMPTY && (sl.z & GKM_IDX_COL_MASK) < bhi) ? (sl.w & ~GKM_IDX_PTR) : ~0u;
+}
+
+/* postings 3.. of a list of five or more (1.7 % of the slots at 10k x 300 bp), 16 bytes at a time */
+template <bool WEIGHTED, bool RANGE>
+__device__ __forceinline__ void idx_walk(const uint32_t *__restrict__ ovf, uint32_t ofs, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(ovf + ofs);
+    for (;;) {
+        const uint4 v = __ldg(q++);
+        idx_hit<WEIGHTED, RANGE>(Hm, v.x, blo, bhi, w);
+        idx_hit<WEIGHTED, RANGE>(Hm, v.y, blo, bhi, w);
+        idx_hit<WEIGHTED, RANGE>(Hm, v.z, blo, bhi, w);
+        idx_hit<WEIGHTED, RANGE>(Hm, v.w, blo, bhi, w);
+        if ((v.w & GKM_IDX_COL_MASK) >= bhi) break;
     }
 }
 
-/* probes of the masks [t_begin, t_end): tiles of <= 1024 masks; inside a tile a thread keeps its mask and
- * walks the query L-mers, GKM_IDX_UNROLL independent slot loads in flight.  A short tile is shared by
- * several "phases" of threads that take interleaved query L-mers.  Hbins = bin 0 of this part of the
- * histogram (shared memory, or the global scratch row when COLD), mbase = the m of that bin. */
-template <bool WEIGHTED, bool RANGE, bool COLD>
-__device__ __forceinline__ void idx_probe(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
-                                          int nq, int32_t *Hbins, int mbase, int ldh, uint32_t blo, uint32_t bhi)
+/* ---- compact slots (GKM_IDX_FMT_C16): unit weights, 16-bit columns; 0xFFFF (none) fails the range test ---- */
+template <bool RANGE>
+__device__ __forceinline__ uint32_t idx_slot16(const uint2 sl, int32_t *Hm, uint32_t blo, uint32_t bhi)
+{
+    const uint32_t c1 = sl.x >> 16, c3 = sl.y >> 16;
+    idx_red<RANGE>(Hm, sl.x & 0xFFFFu, blo, bhi, 1);
+    idx_red<RANGE>(Hm, c1, blo, bhi, 1);
+    if (!(sl.y & GKM_IDX_PTR) || c3 == GKM_IDX_C16_NONE) {
+        idx_red<RANGE>(Hm, sl.y & 0xFFFFu, blo, bhi, 1);
+        idx_red<RANGE>(Hm, c3, blo, bhi, 1);
+        return ~0u;
+    }
+    return (c1 < bhi) ? (sl.y & ~GKM_IDX_PTR) : ~0u;
+}
+
+/* columns 2.. of a list of five or more, eight at a time */
+template <bool RANGE>
+__device__ __forceinline__ void idx_walk16(const uint32_t *__restrict__ ovf, uint32_t ofs, int32_t *Hm, uint32_t blo, uint32_t bhi)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(ovf) + ofs);
+    for (;;) {
+        const uint4 v = __ldg(q++);
+        idx_red<RANGE>(Hm, v.x & 0xFFFFu, blo, bhi, 1); idx_red<RANGE>(Hm, v.x >> 16, blo, bhi, 1);
+        idx_red<RANGE>(Hm, v.y & 0xFFFFu, blo, bhi, 1); idx_red<RANGE>(Hm, v.y >> 16, blo, bhi, 1);
+        idx_red<RANGE>(Hm, v.z & 0xFFFFu, blo, bhi, 1); idx_red<RANGE>(Hm, v.z >> 16, blo, bhi, 1);
+        idx_red<RANGE>(Hm, v.w & 0xFFFFu, blo, bhi, 1); idx_red<RANGE>(Hm, v.w >> 16, blo, bhi, 1);
+        if ((v.w >> 16) >= bhi) break;
+    }
+}
+
+/* one probe, walks included, for the phases that need no warp-level bookkeeping (cold bins) */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_probe_one(const gkm_idx_rowargs &r, uint32_t y, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+{
+    if constexpr (C16) {
+        const uint32_t o = idx_slot16<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi);
+        if (o != ~0u) idx_walk16<RANGE>(r.ovf, o, Hm, blo, bhi);
+    } else {
+        const uint32_t o = idx_slot<WEIGHTED, RANGE>(__ldg(reinterpret_cast<const uint4 *>(r.tab) + y), Hm, blo, bhi, w);
+        if (o != ~0u) idx_walk<WEIGHTED, RANGE>(r.ovf, o, Hm, blo, bhi, w);
+    }
+}
+
+/* Probes of the masks [t_begin, t_end) into the COLD bins (global scratch row C; m <= d - 2, ~1 % of the hits and
+ * a handful of masks): tiles of <= 1024 masks; inside a tile a thread keeps its mask and walks the query L-mers.
+ * A short tile is shared by several "phases" of threads that take interleaved query L-mers. */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
+                                               int nq, int32_t *C, int ldh, uint32_t blo, uint32_t bhi)
 {
     const int tid = (int) threadIdx.x;
-    const uint4 *__restrict__ tab = r.tab;
     for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
         const int rem = min(GKM_IDX_THREADS, t_end - t0);
         int T = (rem + 31) & ~31;
@@ -241,24 +338,91 @@ __device__ __forceinline__ void idx_probe(const gkm_idx_rowargs &r, int t_begin,
         if (ph >= nph || tt >= rem) continue;
         const uint32_t dl = r.deltas[t0 + tt];
         const uint32_t dx = dl & 0x0FFFFFFFu;
-        int32_t *Hm = Hbins + (size_t) ((int) (dl >> 28) - mbase) * (size_t) ldh;
-        const int step = nph * GKM_IDX_UNROLL;
-        int xi = ph;
-        for (; xi + (GKM_IDX_UNROLL - 1) * nph < nq; xi += step) {
-            uint4 sl[GKM_IDX_UNROLL];
-#pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) sl[u] = __ldg(tab + (xq[xi + u * nph] ^ dx));
-#pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++)
-                idx_slot<WEIGHTED, RANGE, COLD>(sl[u], r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi + u * nph] : 1);
-        }
-        for (; xi < nq; xi += nph)
-            idx_slot<WEIGHTED, RANGE, COLD>(__ldg(tab + (xq[xi] ^ dx)), r.ovf, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
+        int32_t *Hm = C + (size_t) (dl >> 28) * (size_t) ldh;
+        for (int xi = ph; xi < nq; xi += nph)
+            idx_probe_one<WEIGHTED, RANGE, C16>(r, xq[xi] ^ dx, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
     }
 }
 
-template <bool WEIGHTED, bool RANGE>
-__global__ void __launch_bounds__(GKM_IDX_THREADS, 1)
+/* Probes of the masks [t_begin, t_end) into the HOT bins (shared memory H; bin 0 of H holds m = mbase).
+ * Same tiling as above, GKM_IDX_UNROLL independent slot loads in flight per thread.  Every lane of a warp runs the
+ * same iterations (lanes without work probe with an empty column range), so that the overflow lists can be handled
+ * at warp level: a lane that meets a list of five or more postings does NOT walk it on the spot -- one walking lane
+ * would stall the other 31 behind a dependent load in divergent code, and nearly every warp probe has one -- but
+ * pushes (list, bin row, weight) on the warp's queue in shared memory; whenever 32 walks are queued the warp runs
+ * them together, one list per lane. */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
+                                              int nq, int32_t *H, int mbase, int ldh, uint32_t blo, uint32_t bhi, uint2 *queue)
+{
+    const int tid = (int) threadIdx.x, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint4 *__restrict__ tab = reinterpret_cast<const uint4 *>(r.tab);
+    const uint2 *__restrict__ tab16 = reinterpret_cast<const uint2 *>(r.tab);
+    const uint32_t h0 = (uint32_t) __cvta_generic_to_shared(H);
+    int qn = 0; /* queued walks of this warp (warp-uniform) */
+    for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
+        const int rem = min(GKM_IDX_THREADS, t_end - t0);
+        int T = (rem + 31) & ~31;
+        if (rem < 32) { T = 1; while (T < rem) T <<= 1; }
+        const int nph = GKM_IDX_THREADS / T;
+        const int ph = tid / T, tt = tid - ph * T;
+        const bool lane_ok = ph < nph && tt < rem;
+        if (!__any_sync(0xFFFFFFFFu, lane_ok)) continue;
+        const uint32_t dl = lane_ok ? r.deltas[t0 + tt] : 0u;
+        const uint32_t dx = dl & 0x0FFFFFFFu;
+        const int mrow = lane_ok ? (int) (dl >> 28) - mbase : 0;
+        int32_t *Hm = H + (size_t) mrow * (size_t) ldh;
+        const uint32_t bhi_l = lane_ok ? bhi : 0u; /* a lane without a mask never hits */
+        const int n_it = (nq + nph - 1) / nph;     /* the same for every lane */
+        for (int it = 0; it < n_it; it += GKM_IDX_UNROLL) {
+            uint32_t bh[GKM_IDX_UNROLL];
+            int w[GKM_IDX_UNROLL];
+            uint4 sl[GKM_IDX_UNROLL];
+            uint2 sc[GKM_IDX_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+                const int xi = ph + (it + u) * nph;
+                const bool ok = (it + u < n_it) && xi < nq;
+                const uint32_t y = (ok ? xq[xi] : 0u) ^ dx;
+                bh[u] = ok ? bhi_l : 0u;
+                w[u] = (WEIGHTED && ok) ? (int) wq[xi] : 1;
+                if constexpr (C16) sc[u] = __ldg(tab16 + y); else sl[u] = __ldg(tab + y);
+            }
+#pragma unroll
+            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+                uint32_t o;
+                if constexpr (C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bh[u]);
+                else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bh[u], w[u]);
+                const uint32_t mk = __ballot_sync(0xFFFFFFFFu, o != ~0u);
+                if (mk) {
+                    if (o != ~0u) queue[qn + __popc(mk & lt)] = make_uint2(o, (uint32_t) mrow | ((uint32_t) w[u] << 8));
+                    qn += __popc(mk);
+                    if (qn >= 32) {
+                        __syncwarp();
+                        const uint2 e = queue[qn - 32 + lane];
+                        int32_t *He = H + (size_t) (e.y & 0xFFu) * (size_t) ldh;
+                        if constexpr (C16) idx_walk16<RANGE>(r.ovf, e.x, He, blo, bhi);
+                        else idx_walk<WEIGHTED, RANGE>(r.ovf, e.x, He, blo, bhi, (int) (e.y >> 8));
+                        qn -= 32;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < qn) {
+        const uint2 e = queue[lane];
+        int32_t *He = H + (size_t) (e.y & 0xFFu) * (size_t) ldh;
+        if constexpr (C16) idx_walk16<RANGE>(r.ovf, e.x, He, blo, bhi);
+        else idx_walk<WEIGHTED, RANGE>(r.ovf, e.x, He, blo, bhi, (int) (e.y >> 8));
+    }
+    (void) h0;
+}
+
+template <bool WEIGHTED, bool RANGE, bool C16, int MINB>
+__global__ void __launch_bounds__(GKM_IDX_THREADS, MINB)
 gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gkm_idx_rowargs r)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -277,7 +441,8 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     const int ldh = r.ldh;
     int32_t *H = reinterpret_cast<int32_t *>(smem);                       /* bins ncoldb .. nb-1 */
     int32_t *C = r.cold + (size_t) blockIdx.x * (size_t) ncoldb * (size_t) ldh; /* bins 0 .. ncoldb-1, this row's scratch */
-    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nhot * (size_t) ldh * 4);
+    uint2 *queue = reinterpret_cast<uint2 *>(smem + (size_t) nhot * (size_t) ldh * 4) + (size_t) (tid >> 5) * GKM_IDX_QCAP; /* this warp's */
+    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES);
     uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
 
     const int ncol = (int) (bhi - blo);
@@ -297,8 +462,8 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
     __syncthreads();
 
-    if (r.ncold > 0) idx_probe<WEIGHTED, RANGE, true>(r, 0, r.ncold, xq, wq, nq, C, 0, ldh, blo, bhi);
-    idx_probe<WEIGHTED, RANGE, false>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi);
+    if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, C16>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi);
+    idx_probe_hot<WEIGHTED, RANGE, C16>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
     __syncthreads();
 
     /* epilogue: histogram -> normalised double, the reference's operation order */
@@ -340,7 +505,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
 unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted)
 {
     const int nhot = nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS;
-    size_t s = (size_t) nhot * (size_t) ldh * 4 + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
+    size_t s = (size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
     return (unsigned) ((s + 15) & ~(size_t) 15);
 }
 
@@ -352,7 +517,7 @@ size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows)
 
 int gkm_idx_max_cols(int nbins, int maxq, int weighted)
 {
-    const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - (long long) maxq * (weighted ? 5 : 4);
+    const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - GKM_IDX_QBYTES - (long long) maxq * (weighted ? 5 : 4);
     long long cols = budget / (4LL * (nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS));
     cols &= ~31LL;
     if (cols > (long long) GKM_IDX_MAX_COLS) cols = GKM_IDX_MAX_COLS & ~31;
@@ -364,9 +529,25 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
     const int rows = kp->row_end - kp->row_begin;
     if (rows <= 0 || ra->bhi <= ra->blo) return 0;
     const bool range = ra->blo != 0;
-    const void *fn = weighted ? (range ? (const void *) gkm_index_rows_kernel<true, true> : (const void *) gkm_index_rows_kernel<true, false>)
-                              : (range ? (const void *) gkm_index_rows_kernel<false, true> : (const void *) gkm_index_rows_kernel<false, false>);
     const unsigned smem = gkm_idx_row_smem(kp->nbins, ra->ldh, ra->maxq, weighted);
+    /* Two CTAs per SM where two full histogram rows of the block fit shared memory (blocks up to ~12 000 columns):
+     * that build is held to 32 registers, which the compact-slot code meets without spills (41.0 instead of 46.1 ms
+     * at 10k).  The decision is per block, not per launch: mixing the two builds inside one problem measured
+     * slower (28 288 sequences: 272 ms against 228 ms), and the 16-byte-slot code spills at 32 registers
+     * (wgkm at 10k: 70 ms against 49 ms), so the weighted types always run one CTA per SM. */
+    const bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted) + 1280u) <= 227u * 1024u;
+    const void *fn;
+    if (ra->fmt == GKM_IDX_FMT_C16) {
+        if (weighted) { gkm_set_error("compact index slots carry no weights"); return 1; }
+        fn = range ? (two ? (const void *) gkm_index_rows_kernel<false, true, true, 2> : (const void *) gkm_index_rows_kernel<false, true, true, 1>)
+                   : (two ? (const void *) gkm_index_rows_kernel<false, false, true, 2> : (const void *) gkm_index_rows_kernel<false, false, true, 1>);
+    } else if (weighted) {
+        fn = range ? (two ? (const void *) gkm_index_rows_kernel<true, true, false, 2> : (const void *) gkm_index_rows_kernel<true, true, false, 1>)
+                   : (two ? (const void *) gkm_index_rows_kernel<true, false, false, 2> : (const void *) gkm_index_rows_kernel<true, false, false, 1>);
+    } else {
+        fn = range ? (two ? (const void *) gkm_index_rows_kernel<false, true, false, 2> : (const void *) gkm_index_rows_kernel<false, true, false, 1>)
+                   : (two ? (const void *) gkm_index_rows_kernel<false, false, false, 2> : (const void *) gkm_index_rows_kernel<false, false, false, 1>);
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess) {
         void *args[] = { (void *) kp, (void *) ra };

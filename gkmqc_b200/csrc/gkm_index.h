@@ -43,6 +43,14 @@ extern "C" {
 #define GKM_IDX_COL_BITS 23
 #define GKM_IDX_COL_MASK 0x007FFFFFu  /* posting = column | weight << 23, bit 31 clear */
 #define GKM_IDX_MAX_COLS 0x007FFFFEu
+/* compact slots of the unit-weight kernel types (0..3): 8 bytes = four 16-bit columns {c0, c1, c2, c3}, 0xFFFF = none;
+ * five or more postings: {c0, c1, 0x80000000 | offset of columns 2.. in the overflow array (16-bit entries, lists
+ * aligned to 16 bytes and padded with 0xFFFF)}.  Columns stay below 0x8000, so bit 31 of the second word set and its
+ * upper half not 0xFFFF means "pointer".  Half the table (33.5 MB at L = 11) and 4 slots per 32-byte sector. */
+#define GKM_IDX_FMT_P32 0             /* 16-byte slots of 32-bit postings (column | weight << 23) */
+#define GKM_IDX_FMT_C16 1
+#define GKM_IDX_C16_NONE 0xFFFFu
+#define GKM_IDX_C16_MAX_COLS 0x7FFF
 #define GKM_IDX_HOT_BINS 2            /* bins d and d-1 (99 % of the hits) live in shared memory, the others in L2 */
 
 #if defined(__CUDACC__)

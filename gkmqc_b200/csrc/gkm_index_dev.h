@@ -11,8 +11,9 @@
 /* the index of one block of columns [cb, ce) on one GPU */
 struct gkm_idx_block {
     int cb, ce;
-    uint4 *tab;          /* 4^L slots of 16 bytes: postings 0..2, posting 3 or pointer */
-    uint32_t *ovf;       /* overflow lists (16-byte aligned, padded with end markers), <= 2P entries */
+    int fmt;             /* GKM_IDX_FMT_P32 (16-byte slots) or GKM_IDX_FMT_C16 (8-byte slots of 16-bit columns) */
+    void *tab;           /* 4^L slots */
+    uint32_t *ovf;       /* overflow lists (16-byte aligned, padded with end markers) */
     size_t tab_bytes, ovf_bytes; /* block sizes as handed out by the pool */
     int built;
 };
@@ -24,21 +25,25 @@ struct gkm_idx_build_args {
     size_t P;              /* postings of the block */
     void *scratch;         /* gkm_idx_scratch_bytes(P, L) bytes */
     size_t cub_bytes;
-    uint4 *tab; uint32_t *ovf;
+    int fmt;
+    void *tab; uint32_t *ovf;
 };
 
 struct gkm_idx_rowargs {
-    const uint4 *tab; const uint32_t *ovf; const uint32_t *deltas;
+    int fmt;
+    const void *tab; const uint32_t *ovf; const uint32_t *deltas;
     int ndelta;    /* masks in all */
     int ncold;     /* the first ncold masks belong to the cold bins (m <= d - 2) */
     int32_t *cold; /* [rows of the launch][cold bins][ldh] scratch in global memory, zeroed by the kernel */
     int cb;        /* first column of the index block */
     int blo, bhi;  /* wanted columns, relative to cb */
     int ldh;       /* histogram row stride in shared memory (>= bhi - blo) */
+    int blk_cols;  /* columns of the whole index block (decides the kernel build) */
     int maxq;      /* upper bound of query L-mers per row */
 };
 
-size_t gkm_idx_tab_bytes(int L);
+size_t gkm_idx_tab_bytes(int L, int fmt);
+size_t gkm_idx_ovf_bytes(size_t P, int fmt);
 size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out);
 int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st);
 /* most columns one block may hold so that the hot histogram rows + the query fit 227 KB of shared memory (0: none) */

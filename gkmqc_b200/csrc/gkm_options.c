@@ -21,6 +21,7 @@ static int g_chunk_mb = 64;
 static int g_tile_rows = 0;
 static int g_diag_flavor = -1;
 static int g_index_cols = 0;
+static int g_index_wide = 0;
 
 static int parse_kernel(const char *v, int *out)
 {
@@ -43,6 +44,7 @@ static void load_env(void)
     if ((v = getenv("GKM_CHUNK_MB")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 4096) g_chunk_mb = x; }
     if ((v = getenv("GKM_DIAG_FLAVOR")) != NULL) { int x = atoi(v); if (x >= -1 && x <= 7) g_diag_flavor = x; }
     if ((v = getenv("GKM_INDEX_COLS")) != NULL) { int x = atoi(v); if (x >= 32) g_index_cols = x & ~31; }
+    if ((v = getenv("GKM_INDEX_WIDE")) != NULL) g_index_wide = atoi(v) != 0;
     if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
 }
 
@@ -52,6 +54,7 @@ int gkm_opt_chunk_mb(void) { load_env(); return g_chunk_mb; }
 int gkm_opt_tile_rows(void) { load_env(); return g_tile_rows; }
 int gkm_opt_diag_flavor(void) { load_env(); return g_diag_flavor; }
 int gkm_opt_index_cols(void) { load_env(); return g_index_cols; }
+int gkm_opt_index_wide(void) { load_env(); return g_index_wide; }
 
 int gkmb200_set_option(const char *key, const char *value)
 {
@@ -80,6 +83,10 @@ int gkmb200_set_option(const char *key, const char *value)
     if (!strcmp(key, "index_cols")) { /* upper bound of the columns of one index block (0 = what fits shared memory) */
         if (x != 0 && x < 32) { gkm_set_error("index_cols must be 0 or >= 32"); return 1; }
         g_index_cols = x & ~31;
+        return 0;
+    }
+    if (!strcmp(key, "index_wide")) { /* 1: 16-byte slots even where the compact 8-byte ones would do (A/B, tests) */
+        g_index_wide = x != 0;
         return 0;
     }
     if (!strcmp(key, "tile_rows")) {

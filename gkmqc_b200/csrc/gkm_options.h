@@ -10,6 +10,7 @@ int gkm_opt_chunk_mb(void);
 int gkm_opt_tile_rows(void);
 int gkm_opt_diag_flavor(void);
 int gkm_opt_index_cols(void);
+int gkm_opt_index_wide(void);
 #ifdef __cplusplus
 }
 #endif

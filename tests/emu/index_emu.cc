@@ -31,8 +31,10 @@ static uint32_t window(const uint32_t *pl, int W, int lo, uint32_t mask)
 }
 
 struct emu_index {
+    int fmt; /* GKM_IDX_FMT_P32: 16-byte slots of 32-bit postings; GKM_IDX_FMT_C16: 8-byte slots of 16-bit columns */
     std::unordered_map<uint32_t, emu_slot> tab;
-    std::vector<uint32_t> ovf;
+    std::vector<uint32_t> ovf;     /* P32 */
+    std::vector<uint16_t> ovf16;   /* C16 */
 };
 
 /* index over the columns [cb, ce) */
@@ -54,6 +56,30 @@ static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
     }
     std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return (a >> 8) < (b >> 8); });
     size_t i = 0;
+    ix.fmt = (!p->weighted && ce - cb <= GKM_IDX_C16_MAX_COLS && !getenv("GKM_EMU_INDEX_WIDE")) ? GKM_IDX_FMT_C16 : GKM_IDX_FMT_P32;
+    while (ix.fmt == GKM_IDX_FMT_C16 && i < keys.size()) {
+        size_t e = i;
+        while (e < keys.size() && (keys[e] >> 32) == (keys[i] >> 32)) e++;
+        const size_t len = e - i;
+        uint16_t c[4] = { GKM_IDX_C16_NONE, GKM_IDX_C16_NONE, GKM_IDX_C16_NONE, GKM_IDX_C16_NONE };
+        emu_slot s;
+        if (len <= 4) {
+            for (size_t r = 0; r < len; r++) c[r] = (uint16_t) ((keys[i + r] >> 8) & 0x7FFFu);
+            s.v[0] = c[0] | ((uint32_t) c[1] << 16);
+            s.v[1] = c[2] | ((uint32_t) c[3] << 16);
+        } else {
+            for (size_t r = 0; r < 2; r++) c[r] = (uint16_t) ((keys[i + r] >> 8) & 0x7FFFu);
+            while (ix.ovf16.size() & 7) ix.ovf16.push_back(GKM_IDX_C16_NONE); /* lists start on 16 bytes */
+            s.v[0] = c[0] | ((uint32_t) c[1] << 16);
+            s.v[1] = GKM_IDX_PTR | (uint32_t) ix.ovf16.size();
+            for (size_t r = 2; r < len; r++) ix.ovf16.push_back((uint16_t) ((keys[i + r] >> 8) & 0x7FFFu));
+            ix.ovf16.push_back(GKM_IDX_C16_NONE);
+            while (ix.ovf16.size() & 7) ix.ovf16.push_back(GKM_IDX_C16_NONE);
+        }
+        s.v[2] = s.v[3] = 0;
+        ix.tab[(uint32_t) (keys[i] >> 32)] = s;
+        i = e;
+    }
     while (i < keys.size()) {
         size_t e = i;
         while (e < keys.size() && (keys[e] >> 32) == (keys[i] >> 32)) e++;
@@ -80,6 +106,11 @@ static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
     }
 }
 
+static inline void hit16(int32_t *H, int nb, int m, uint32_t b, uint32_t blo, uint32_t bhi)
+{
+    if (b < bhi && b >= blo) H[(size_t) (b - blo) * nb + m] += 1;
+}
+
 static inline void hit(int32_t *H, int nb, int m, uint32_t e, uint32_t blo, uint32_t bhi, int w)
 {
     const uint32_t b = e & GKM_IDX_COL_MASK;
@@ -102,6 +133,23 @@ static void probe_row(const gkmb200_problem *p, const emu_index &ix, const std::
             auto it = ix.tab.find(x ^ (dl & 0x0FFFFFFFu));
             if (it == ix.tab.end()) continue;
             const uint32_t *sl = it->second.v;
+            if (ix.fmt == GKM_IDX_FMT_C16) {
+                const uint32_t c1 = sl[0] >> 16, c3 = sl[1] >> 16;
+                hit16(H, nb, m, sl[0] & 0xFFFFu, blo, bhi);
+                hit16(H, nb, m, c1, blo, bhi);
+                if (!(sl[1] & GKM_IDX_PTR) || c3 == GKM_IDX_C16_NONE) {
+                    hit16(H, nb, m, sl[1] & 0xFFFFu, blo, bhi);
+                    hit16(H, nb, m, c3, blo, bhi);
+                } else if (c1 < bhi) {
+                    const uint16_t *q = ix.ovf16.data() + (sl[1] & ~GKM_IDX_PTR);
+                    for (;;) {
+                        for (int t = 0; t < 8; t++) hit16(H, nb, m, q[t], blo, bhi);
+                        if (q[7] >= bhi) break;
+                        q += 8;
+                    }
+                }
+                continue;
+            }
             hit(H, nb, m, sl[0], blo, bhi, w);
             hit(H, nb, m, sl[1], blo, bhi, w);
             hit(H, nb, m, sl[2], blo, bhi, w);

@@ -122,8 +122,9 @@ def test_seeded_against_oracle(kernel_type, L, k, d, length, ragged, variant):
         np.testing.assert_allclose(dv, Kr @ alpha + 0.25, rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize("kernel_type,L,k,d,cols", [(2, 11, 7, 3, 32), (4, 10, 6, 3, 64), (2, 8, 4, 4, 32), (4, 6, 5, 1, 32), (0, 9, 9, 0, 32)])
-def test_index_column_blocks(kernel_type, L, k, d, cols):
+@pytest.mark.parametrize("kernel_type,L,k,d,cols,wide", [(2, 11, 7, 3, 32, 0), (4, 10, 6, 3, 64, 0), (2, 8, 4, 4, 32, 0), (4, 6, 5, 1, 32, 0),
+                                                          (0, 9, 9, 0, 32, 0), (2, 8, 4, 4, 32, 1), (2, 11, 7, 3, 0, 1), (1, 7, 4, 3, 0, 0)])
+def test_index_column_blocks(kernel_type, L, k, d, cols, wide):
     """index variant with the columns cut into several index blocks (what a problem larger than one
     shared-memory histogram row gets), long posting lists (short L, repeats) and a column window that
     starts inside a block"""
@@ -137,6 +138,7 @@ def test_index_column_blocks(kernel_type, L, k, d, cols):
     o = pyoracle.Oracle(kernel_type, L, k, d, 50, 50.0, 0.7)
     capi.set_option("kernel", "index")
     capi.set_option("index_cols", str(cols))
+    capi.set_option("index_wide", str(wide))  # unit-weight types: compact 8-byte slots (0) or the 16-byte ones (1)
     try:
         with capi.Problem(kernel_type, L, k, d, 50, 50.0, 0.7) as P:
             for s in seqs:
@@ -154,6 +156,7 @@ def test_index_column_blocks(kernel_type, L, k, d, cols):
             np.testing.assert_allclose(dv, Kr[:, 40:100] @ alpha - 0.5, rtol=1e-9, atol=1e-12)
     finally:
         capi.set_option("index_cols", "0")
+        capi.set_option("index_wide", "0")
         capi.set_option("kernel", "auto")
 
 
