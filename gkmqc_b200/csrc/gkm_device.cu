@@ -105,6 +105,7 @@ struct gkm_image {
     /* "index" variant: one inverted index per block of blk_cols columns, built on first use */
     gkm_idx_block *blk;
     int nblk, blk_cols;
+    int part_lo, part_hi; /* the column range the blocks partition (that of the call that created them) */
 };
 
 struct gkm_devstate {
@@ -424,19 +425,28 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
 {
     const int L = p->param.L;
     if (ensure_deltas(g, L, p->param.d)) return 1;
+    /* The blocks partition the column range of the call that created them (the SVs of a scoring problem, all
+     * sequences of a kernel matrix); a later call for columns outside that range starts over. */
+    if (im->blk && (col_begin < im->part_lo || col_end > im->part_hi)) {
+        cudaStreamSynchronize(g->sc); cudaStreamSynchronize(g->sc2);
+        release_index(g, im);
+    }
     if (!im->blk) {
         const int cap = index_block_cap(p);
         if (cap <= 0) { gkm_set_error("index variant: sequences too long for shared memory"); return 1; }
-        const int nblk = (p->n + cap - 1) / cap;
-        int cols = (((p->n + nblk - 1) / nblk) + 31) & ~31;
+        const int span = col_end - col_begin;
+        const int nblk = (span + cap - 1) / cap;
+        int cols = (((span + nblk - 1) / nblk) + 31) & ~31;
         if (cols > cap) cols = cap;
         im->blk = (gkm_idx_block *) calloc((size_t) nblk, sizeof(gkm_idx_block));
         if (!im->blk) { gkm_set_error("out of memory"); return 1; }
         im->nblk = nblk;
         im->blk_cols = cols;
+        im->part_lo = col_begin;
+        im->part_hi = col_end;
         for (int k = 0; k < nblk; k++) {
-            im->blk[k].cb = k * cols;
-            im->blk[k].ce = (k + 1) * cols < p->n ? (k + 1) * cols : p->n;
+            im->blk[k].cb = col_begin + k * cols;
+            im->blk[k].ce = col_begin + (k + 1) * cols < col_end ? col_begin + (k + 1) * cols : col_end;
         }
     }
     for (int k = 0; k < im->nblk; k++) {
@@ -492,13 +502,10 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     if ((opt == GKM_KERNEL_AUTO || opt == GKM_KERNEL_INDEX) && nrows > 0 && ncols > 0 &&
         gkm_idx_supported(p->param.L, p->param.d, p->nbins)) {
         const int cap = index_block_cap(p);
-        const int nblk_all = cap > 0 ? (p->n + cap - 1) / cap : 0;
-        int ok = cap > 0 && p->n <= (long long) nblk_all * (long long) GKM_IDX_MAX_COLS;
+        int ok = cap > 0;
         int blocks = 0;
         if (ok) {
-            int cols = (((p->n + nblk_all - 1) / nblk_all) + 31) & ~31;
-            if (cols > cap) cols = cap;
-            blocks = (col0 + ncols - 1) / cols - col0 / cols + 1;
+            blocks = (ncols + cap - 1) / cap;
             /* at most 8 GiB of slot tables per GPU */
             if ((double) blocks * (double) gkm_idx_tab_bytes(p->param.L, p->weighted ? GKM_IDX_FMT_P32 : GKM_IDX_FMT_C16) > 8.0 * 1073741824.0) ok = 0;
         }
@@ -509,7 +516,7 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             const long long entries = (long long) nrows * (long long) ncols / (lower ? 2 : 1);
             /* lower: row a probes only the blocks that start below it */
             const int eff_blocks = lower ? (blocks + 1) / 2 : blocks;
-            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, nrows, nq, eff_blocks > 0 ? eff_blocks : 1, entries, 2.0 * nq * nq);
+            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks > 0 ? eff_blocks : 1, entries, 2.0 * nq * nq);
             const double cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
             ok = ci < cd;
             gkm_log(GKM_LOG_DEBUG, "kernel = auto: index %.2f ms vs diag %.2f ms (estimates)", ci, cd);

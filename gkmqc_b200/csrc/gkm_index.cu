@@ -535,7 +535,8 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
      * at 10k).  The decision is per block, not per launch: mixing the two builds inside one problem measured
      * slower (28 288 sequences: 272 ms against 228 ms), and the 16-byte-slot code spills at 32 registers
      * (wgkm at 10k: 70 ms against 49 ms), so the weighted types always run one CTA per SM. */
-    const bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted) + 1280u) <= 227u * 1024u;
+    bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted) + 1280u) <= 227u * 1024u;
+    { const char *e = getenv("GKM_IDX_MINB"); if (e) two = atoi(e) == 2; } /* A/B knob */
     const void *fn;
     if (ra->fmt == GKM_IDX_FMT_C16) {
         if (weighted) { gkm_set_error("compact index slots carry no weights"); return 1; }

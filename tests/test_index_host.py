@@ -22,7 +22,7 @@ def lib(product_lib):
     product_lib.gkm_idx_cold_count.restype = ctypes.c_longlong
     product_lib.gkm_idx_cold_count.argtypes = [ctypes.c_int, ctypes.c_int]
     product_lib.gkm_idx_cost_ms.restype = ctypes.c_double
-    product_lib.gkm_idx_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_int,
+    product_lib.gkm_idx_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_int,
                                             ctypes.c_longlong, ctypes.c_double]
     product_lib.gkm_diag_cost_ms.restype = ctypes.c_double
     product_lib.gkm_diag_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double]
@@ -86,12 +86,13 @@ def test_supported_and_cost_model(lib):
     nq, pairs = 290.0, 2.0 * 290 * 290
     # BASELINE configs[1]: the index wins by a wide margin; configs[0] (1 000 sequences): the bit-sliced kernel does
     big = 10000 * 9999 // 2
-    assert lib.gkm_idx_cost_ms(11, 3, 10000, nq, 1, big, pairs) < 0.5 * lib.gkm_diag_cost_ms(3, 0, big, pairs)
+    assert lib.gkm_idx_cost_ms(11, 3, 0, 10000, nq, 1, big, pairs) < 0.25 * lib.gkm_diag_cost_ms(3, 0, big, pairs)
+    assert 35 < lib.gkm_idx_cost_ms(11, 3, 0, 10000, nq, 1, big, pairs) < 50, "calibrated on the 41 ms of configs[1]"
     small = 1000 * 999 // 2
-    assert lib.gkm_idx_cost_ms(11, 3, 1000, nq, 1, small, pairs) > lib.gkm_diag_cost_ms(3, 0, small, pairs)
+    assert lib.gkm_idx_cost_ms(11, 3, 0, 1000, nq, 1, small, pairs) > lib.gkm_diag_cost_ms(3, 0, small, pairs)
     # L = 14, d = 4 on 20 000 sequences (the top of configs[2]): 91 771 masks per L-mer, the table leaves L2
     n20 = 20000 * 19999 // 2
-    assert lib.gkm_idx_cost_ms(14, 4, 20000, 287.0, 2, n20, 2.0 * 287 * 287) > lib.gkm_diag_cost_ms(4, 0, n20, 2.0 * 287 * 287)
+    assert lib.gkm_idx_cost_ms(14, 4, 0, 20000, 287.0, 2, n20, 2.0 * 287 * 287) > lib.gkm_diag_cost_ms(4, 0, n20, 2.0 * 287 * 287)
 
 
 @pytest.fixture(scope="module")
