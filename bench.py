@@ -155,8 +155,9 @@ def dist_barrier(dist):
         dist.barrier()
 
 
-def index_probe_counts(L, d):
-    """probes and distinct 32-byte sectors per query L-mer of the index variant, from the product's own mask list"""
+def index_probe_counts(L, d, slot_bytes):
+    """probes and distinct 32-byte sectors per query L-mer of the index variant, from the product's own mask list
+    (slot_bytes = 8: compact slots of the unit-weight kernel types, 16: slots with weights)"""
     from gkmqc_b200 import capi
     import ctypes
     lib = capi.load()
@@ -166,7 +167,7 @@ def index_probe_counts(L, d):
     nd = lib.gkm_idx_delta_count(L, d)
     a = np.zeros(nd, dtype=np.uint32)
     assert lib.gkm_idx_deltas(L, d, a.ctypes.data, nd) == nd
-    return int(nd), int(len(np.unique((a & 0x0FFFFFFF) >> 1)))   # two 16-byte slots per sector
+    return int(nd), int(len(np.unique((a & 0x0FFFFFFF) >> (2 if slot_bytes == 8 else 1))))   # 32-byte sector = 4 or 2 slots
 
 
 def measured_hbm():
@@ -343,17 +344,18 @@ def main():
     avg_launch_ms = ms_per_step / max(1, st["launches"])
     if variant == "index":
         peak_gather = capi.microbench("gather16")     # 1e9 random 16-byte gathers (one 32-byte sector each) per second
-        probes, sectors = index_probe_counts(L, D)
+        slot_bytes = 16 if KTYPE in (4, 5) else 8
+        probes, sectors = index_probe_counts(L, D, slot_bytes)
         nq = SEQLEN - L + 1
         my_rows = n / world                            # chunks of equal row counts, round-robin over the ranks
         sector_bytes = my_rows * nq * sectors * 32.0   # algorithmic: distinct sectors the probes of one pass must fetch
         achieved = sector_bytes / (ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "l2_sector", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
                     "frac": achieved / (peak_gather * 32.0), "traffic": traffic,
-                    "note": "index variant: every forward L-mer of a row probes %d slots of the L2-resident table (%d distinct 32-byte "
-                            "sectors); achieved = rows x %d L-mers x sectors x 32 B per pass / time; peak = random 16-byte gathers from a "
-                            "64 MB table measured in this run (x 32 B per sector). MEASURED_PEAKS.json hbm_gbs = %s for scale: the "
-                            "probes are served by L2, DRAM traffic is `traffic`" % (probes, sectors, nq, measured_hbm()),
+                    "note": "index variant: every forward L-mer of a row probes %d %d-byte slots of the L2-resident table (%d distinct "
+                            "32-byte sectors); achieved = rows x %d L-mers x sectors x 32 B per pass / time; peak = random 16-byte gathers "
+                            "from a 64 MB table measured in this run (x 32 B per sector). MEASURED_PEAKS.json hbm_gbs = %s for scale: "
+                            "the probes are served by L2, DRAM traffic is `traffic`" % (probes, slot_bytes, sectors, nq, measured_hbm()),
                     "probes_per_lmer": probes, "sectors_per_lmer": sectors, "peak_gather_gsectors": peak_gather,
                     "int_alu_equivalent": {"achieved_gops": int_alu_equiv, "peak_lop3_gops": peak_lop3, "ratio": int_alu_equiv / peak_lop3,
                                            "note": "what the canonical 5-op XOR/POPC form would need for the same entries/s (SURVEY.md 8d)"},

@@ -50,6 +50,9 @@ for k in ("dram_bytes_read", "dram_bytes_write"):
     if out[k] is not None:
         out[k] *= scale
 out["dram_bytes_per_launch"] = (out["dram_bytes_read"] or 0) + (out["dram_bytes_write"] or 0)
+su = rows[1][col["launch__shared_mem_per_block_dynamic"]].lower() if "launch__shared_mem_per_block_dynamic" in col else ""
+if out["dyn_smem_bytes_per_block"] is not None:
+    out["dyn_smem_bytes_per_block"] *= 1e3 if su.startswith("kbyte") else 1e6 if su.startswith("mbyte") else 1.0
 ms_unit = rows[1][col["gpu__time_duration.sum"]].lower()
 out["duration_ms"] = out["duration_ms"] * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(ms_unit, 1.0)
 print(json.dumps(out, indent=1))
