@@ -48,6 +48,15 @@ class gkmb200_stats(ctypes.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+class gkmb200_svm_task(ctypes.Structure):
+    _fields_ = [("train_off", ctypes.c_longlong), ("test_off", ctypes.c_longlong), ("ntrain", ctypes.c_int), ("ntest", ctypes.c_int)]
+
+
+class gkmb200_svm_fit(ctypes.Structure):
+    _fields_ = [("rho", ctypes.c_double), ("obj", ctypes.c_double), ("nu", ctypes.c_double),
+                ("n_iter", ctypes.c_int), ("n_sv", ctypes.c_int), ("reserved", ctypes.c_longlong)]
+
+
 class GkmError(RuntimeError):
     pass
 
@@ -105,6 +114,9 @@ def _declare(lib):
         ("gkmb200_get_stats", [P, ctypes.POINTER(gkmb200_stats)]),
         ("gkmb200_bench_lower_resident", [P, I, I, I, c_dbl_p]),
         ("gkmb200_microbench", [ctypes.c_char_p, c_dbl_p]),
+        ("gkmb200_svm_cv", [P, ctypes.c_void_p, ctypes.c_long, I, I, ctypes.POINTER(gkmb200_svm_task), c_int_p,
+                            ctypes.POINTER(ctypes.c_byte), c_int_p, ctypes.c_double, ctypes.c_double, I,
+                            c_dbl_p, ctypes.POINTER(gkmb200_svm_fit), c_dbl_p]),
         ("gkmb200_device_count", []),
         ("gkmb200_set_devices", [c_int_p, I]),
         ("gkmb200_set_option", [ctypes.c_char_p, ctypes.c_char_p]),
@@ -286,6 +298,56 @@ class Problem:
         ms = np.zeros(steps)
         _check(self.lib.gkmb200_bench_lower_resident(self.h, steps, warmup, int(flush_l2), ms.ctypes.data_as(c_dbl_p)), self.lib)
         return ms
+
+
+def svm_prepare_tasks(y, splits):
+    """(labels 0/1 per sequence, [(train ids, test ids), ...]) -> the flat arrays gkmb200_svm_cv takes.
+    Per fit the training ids are grouped by class, label 0 first, in their given order -- the order libsvm's
+    svm_group_classes (with sklearn's label sort) gives them -- and that first class is the sub-problem's +1."""
+    y = np.asarray(y)
+    tasks = (gkmb200_svm_task * len(splits))()
+    tr, ty, te = [], [], []
+    toff = eoff = 0
+    for t, (train, test) in enumerate(splits):
+        train = np.asarray(train, np.int32)
+        test = np.asarray(test, np.int32)
+        lab = y[train]
+        if not (np.any(lab == 0) and np.any(lab == 1)) or np.any((lab != 0) & (lab != 1)):
+            raise ValueError("fit %d: labels must be 0/1 with both classes present" % t)
+        order = np.concatenate((train[lab == 0], train[lab == 1]))
+        tr.append(order)
+        ty.append(np.where(y[order] == 0, 1, -1).astype(np.int8))
+        te.append(test)
+        tasks[t].train_off, tasks[t].test_off = toff, eoff
+        tasks[t].ntrain, tasks[t].ntest = len(order), len(test)
+        toff += len(order)
+        eoff += len(test)
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros(0), dt)
+    return tasks, cat(tr, np.int32), cat(ty, np.int8), cat(te, np.int32)
+
+
+def svm_cv(y, splits, kmat=None, problem=None, C=1.0, eps=1e-3, max_iter=-1, lib=None):
+    """cross-validated C-SVC on the GPU.  Either `kmat` (dense symmetric host matrix) or `problem`
+    (a capi.Problem whose kernel matrix is computed and kept on the device).  Returns (scores per split, fits, alphas):
+    scores are sklearn decision_function values of the test ids, alphas are in the grouped training order."""
+    lib = lib or (problem.lib if problem is not None else load())
+    tasks, tr, ty, te = svm_prepare_tasks(y, splits)
+    scores = np.zeros(len(te))
+    alpha = np.zeros(len(tr))
+    fits = (gkmb200_svm_fit * len(splits))()
+    if kmat is not None:
+        kmat = np.ascontiguousarray(kmat, np.float64)
+        n, kptr, ld, h = kmat.shape[0], kmat.ctypes.data, kmat.strides[0] // 8, None
+    else:
+        n, kptr, ld, h = problem.n, None, 0, problem.h
+    _check(lib.gkmb200_svm_cv(h, kptr, ld, n, len(splits), tasks, tr.ctypes.data_as(c_int_p),
+                              ty.ctypes.data_as(ctypes.POINTER(ctypes.c_byte)), te.ctypes.data_as(c_int_p),
+                              C, eps, max_iter, scores.ctypes.data_as(c_dbl_p), fits, alpha.ctypes.data_as(c_dbl_p)), lib)
+    out_s, out_a = [], []
+    for t in range(len(splits)):
+        out_s.append(scores[tasks[t].test_off: tasks[t].test_off + tasks[t].ntest])
+        out_a.append(alpha[tasks[t].train_off: tasks[t].train_off + tasks[t].ntrain])
+    return out_s, [dict(rho=f.rho, obj=f.obj, nu=f.nu, n_iter=f.n_iter, n_sv=f.n_sv) for f in fits], out_a
 
 
 def main_pywrapper(posfile, negfile, kernel_type=2, L=11, k=7, d=3, M=50, H=50.0, gamma=1.0,

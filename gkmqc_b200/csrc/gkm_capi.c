@@ -81,6 +81,13 @@ int gkmb200_bench_lower_resident(gkmb200_problem *p, int steps, int warmup, int 
 
 int gkmb200_microbench(const char *what, double *result) { return gkm_dev_microbench(what, result); }
 
+int gkmb200_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,
+                   const int *train_idx, const signed char *train_y, const int *test_idx,
+                   double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha)
+{
+    return gkm_dev_svm_cv(p, kmat, ld, n, ntasks, tasks, train_idx, train_y, test_idx, C, eps, max_iter, scores, fits, alpha);
+}
+
 /* ================================================================== */
 /* the operator: gkm_main_pywrapper (gkmkern_pylib.c:92-246)           */
 /* ================================================================== */

@@ -23,6 +23,7 @@
 #include "gkm_lmer_kernel.cuh"
 #include "gkm_mma_kernel.cuh"
 #include "gkm_index_dev.h"
+#include "gkm_svm.h"
 
 #define GKM_MAX_DEV 16
 #define GKM_NBUF 4 /* chunks in flight per GPU: kernels run ahead while the host scatters finished ones */
@@ -100,8 +101,9 @@ struct gkm_image {
     uint8_t *wend;
     double *sqnorm;
     size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes; /* block sizes as handed out by the pool */
-    double *full;       /* resident N x ldfull result (bench) */
+    double *full;       /* resident N x ldfull result (bench, svm consumer) */
     size_t full_ld;
+    int full_sym;       /* the resident matrix is complete and symmetric (unit diagonal) */
     /* "index" variant: one inverted index per block of blk_cols columns, built on first use */
     gkm_idx_block *blk;
     int nblk, blk_cols;
@@ -1012,6 +1014,90 @@ extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col
 }
 
 /* ------------------------------------------------------------------ */
+/* the consumer: cross-validated C-SVC on the resident matrix (8f/f4)   */
+/* ------------------------------------------------------------------ */
+/* one pass of the lower triangle into im->full on GPU 0, then mirrored: the matrix never leaves the device */
+static int resident_symmetric(gkmb200_problem *p)
+{
+    gkm_devstate *ds = p->dev;
+    gkm_gpu *g = &g_gpu[ds->dev[0]];
+    gkm_image *im = &ds->img[0];
+    const int n = p->n;
+    if (im->full && im->full_sym) return 0;
+    CK(cudaSetDevice(ds->dev[0]));
+    if (!im->full) {
+        im->full_ld = ((size_t) n + 15) & ~(size_t) 15;
+        CK(cudaMalloc(&im->full, im->full_ld * (size_t) n * sizeof(double)));
+    }
+    const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
+    const int maxc = n / 16 + 2;
+    gkm_chunk *chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
+    const int nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, 1),
+                                                      by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
+    if (nchunks < 0) { free(chunks); gkm_set_error("chunk planning failed"); return 1; }
+    int rc = 0, launches = 0;
+    for (int c = 0; !rc && c < nchunks; c++) {
+        gkm_kparams kp;
+        fill_kparams(p, im, &kp);
+        kp.mode = GKM_MODE_LOWER;
+        kp.row_begin = chunks[c].row_begin; kp.row_end = chunks[c].row_end;
+        kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
+        kp.row_base = 0; kp.col_base = 0;
+        kp.out = im->full; kp.ld = (long long) im->full_ld;
+        rc = launch_hist(p, im, g, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
+    }
+    free(chunks);
+    if (rc) return 1;
+    CK(cudaEventRecord(g->join, g->sc2));
+    CK(cudaStreamWaitEvent(g->sc, g->join, 0));
+    if (gkm_svm_symmetrize(im->full, (long long) im->full_ld, n, g->sc)) { gkm_set_error("CUDA: symmetrize kernel failed"); return 1; }
+    im->full_sym = 1;
+    p->stats.launches += launches + 1;
+    return 0;
+}
+
+extern "C" int gkm_dev_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,
+                              const int *train_idx, const signed char *train_y, const int *test_idx,
+                              double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha)
+{
+    if (ntasks < 0 || (ntasks > 0 && (!tasks || !train_idx || !train_y || !test_idx))) { gkm_set_error("null argument"); return 1; }
+    if (!(C > 0.0) || !(eps > 0.0)) { gkm_set_error("svm: C and eps must be positive"); return 1; }
+    pthread_mutex_lock(&g_lock);
+    int rc = 0;
+    const double t0 = now_ms();
+    if (!kmat) {
+        if (!p) { gkm_set_error("svm: neither a matrix nor a problem"); rc = 1; }
+        if (!rc && n != p->n) { gkm_set_error("svm: n = %d but the problem holds %d sequences", n, p->n); rc = 1; }
+        if (!rc) rc = upload_locked(p, 0);
+        if (!rc) rc = choose_variant(p, 0, p->n, 0, p->n, 1);
+        if (!rc) rc = resident_symmetric(p);
+        if (!rc) {
+            gkm_devstate *ds = p->dev;
+            gkm_gpu *g = &g_gpu[ds->dev[0]];
+            rc = gkm_svm_run(ds->img[0].full, (long long) ds->img[0].full_ld, n, ntasks, tasks, train_idx, train_y, test_idx,
+                             C, eps, max_iter, scores, fits, alpha, g->sc);
+            p->stats.launches += 3;
+            p->stats.wall_ms = now_ms() - t0;
+        }
+    } else {
+        if (n < 2 || ld < n) { gkm_set_error("svm: bad matrix shape"); rc = 1; }
+        if (!rc) rc = ensure_selected();
+        double *d_K = NULL;
+        if (!rc) {
+            gkm_gpu *g = &g_gpu[g_sel[0]];
+            rc = gpu_prepare(g, g_sel[0], 0, 0);
+            if (!rc && cudaMalloc(&d_K, sizeof(double) * (size_t) n * (size_t) n) != cudaSuccess) { gkm_set_error("CUDA: svm matrix: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+            if (!rc && cudaMemcpy2DAsync(d_K, sizeof(double) * (size_t) n, kmat, sizeof(double) * (size_t) ld, sizeof(double) * (size_t) n, (size_t) n,
+                                         cudaMemcpyHostToDevice, g->sc) != cudaSuccess) { gkm_set_error("CUDA: svm matrix upload: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+            if (!rc) rc = gkm_svm_run(d_K, (long long) n, n, ntasks, tasks, train_idx, train_y, test_idx, C, eps, max_iter, scores, fits, alpha, g->sc);
+            cudaFree(d_K);
+        }
+    }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* measurement                                                          */
 /* ------------------------------------------------------------------ */
 extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each)
@@ -1062,6 +1148,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
                 kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
                 kp.row_base = 0; kp.col_base = 0;
                 kp.out = im->full; kp.ld = (long long) im->full_ld;
+                im->full_sym = 0;
                 rc = launch_hist(p, im, g, kp, (launches & 1) ? g->sc2 : g->sc, &variant);
                 launches++;
                 entries += chunks[c].entries;

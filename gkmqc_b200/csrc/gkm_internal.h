@@ -89,6 +89,9 @@ int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col0, int ncol
                      const double *alpha, double bias, double *out);
 int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each);
 int gkm_dev_microbench(const char *what, double *result);
+int gkm_dev_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,
+                   const int *train_idx, const signed char *train_y, const int *test_idx,
+                   double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha);
 
 #ifdef __cplusplus
 }

@@ -3,8 +3,8 @@
 Same function name, same positional argument list and same return triple as the reference's driver, so the
 parity tests read like its own code path, but bound to gkmqc_b200/bin/gkmkern_pylib.so.  The reference's
 module itself works unchanged against this library; this mirror exists because the
-GPU box has no copy of the reference tree.  Cross-validation with sklearn's SVC (gkmsvm.py:104-176) consumes
-the path's output and is out of scope.
+GPU box has no copy of the reference tree.  ``crossValidate`` mirrors the consumer of the matrix
+(gkmsvm.py:104-176) with the GPU solver of SURVEY.md 8f/f4 in place of the multiprocessing pool of sklearn SVCs.
 """
 import logging
 import sys
@@ -30,3 +30,31 @@ def computeGkmKernel(args_gkm, max_seqs=MAX_SEQS):
     n = n_pseqs + n_nseqs
     kmat = padded[:n, :n]
     return np.maximum(kmat, kmat.T), n_pseqs, n_nseqs  # lower triangle -> symmetric (gkmsvm.py:96-97)
+
+
+def crossValidate(args_svm, _kmat, n_pseqs, n_nseqs, problem=None):
+    """args_svm = [regularization, precision, shrinking, cache_size, ncv, repeats, fast_estimation, random_seeds, p]
+    (gkmsvm.py:198-208).  Same splits as the reference (StratifiedKFold per repeat, gkmsvm.py:146-150), same
+    (mean AUC, std AUC) result; the 5 x 10 C-SVC fits run concurrently on the GPU through gkmb200_svm_cv.
+    _kmat = the symmetric host matrix, or None with `problem` given: the matrix then never leaves the device.
+    shrinking is accepted and ignored: the heuristic changes libsvm's path, not its optimum."""
+    from sklearn.metrics import roc_auc_score
+    from sklearn.model_selection import StratifiedKFold
+    regularization, precision, _shrinking, _cache_size, ncv, repeats, fast_estimation, random_seeds, _p = args_svm
+    if random_seeds < 0:
+        random_seeds = None
+    seqids = ["p%4d" % x for x in range(n_pseqs)] + ["n%4d" % x for x in range(n_nseqs)]
+    y = np.concatenate((np.repeat(1, n_pseqs), np.repeat(0, n_nseqs)))
+    if fast_estimation != 0:
+        raise NotImplementedError("fast_estimation is commented out in the reference as well (gkmsvm.py:160-174)")
+    splits = []
+    for _ in range(repeats):
+        kf = StratifiedKFold(n_splits=ncv, shuffle=True, random_state=random_seeds)
+        splits.extend(kf.split(seqids, y))
+    scores, fits, _ = capi.svm_cv(y, splits, kmat=_kmat, problem=problem, C=regularization, eps=precision)
+    aucs = []
+    for (_, test), s, f in zip(splits, scores, fits):
+        aucs.append(roc_auc_score(y[test], s))
+        logging.info("SVC training and validation; nu = %.3f, AUC = %.3f", f["nu"], aucs[-1])
+    logging.info("done cross-validation.")
+    return np.mean(aucs), np.std(aucs)

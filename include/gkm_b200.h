@@ -33,7 +33,7 @@ typedef struct gkmb200_stats {
     long long h2d_bytes;     /* bytes copied host->device by the last upload */
     long long d2h_bytes;     /* bytes copied device->host by the last compute call */
     int devices;             /* GPUs used */
-    int kernel_variant;      /* 1 = lmer (XOR/LOP3/POPC per pair), 2 = diag (bit-sliced diagonals), 3 = mma (tcgen05) */
+    int kernel_variant;      /* 1 = lmer (XOR/LOP3/POPC per pair), 2 = diag (bit-sliced diagonals), 3 = mma (tcgen05), 4 = index */
     int reserved[6];
 } gkmb200_stats;
 
@@ -42,7 +42,7 @@ const char *gkmb200_last_error(void);
 int gkmb200_abi_version(void);
 int gkmb200_device_count(void);                      /* visible CUDA devices of compute capability 10.x; 0 if none */
 int gkmb200_set_devices(const int *ids, int n);      /* default: env GKM_DEVICES ("0,1,.."), else all */
-int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag ; "max_L" = 12|16 ; "tile_rows", "chunk_mb" */
+int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag|mma|index ; "max_L" = 12|16 ; "tile_rows", "chunk_mb", "index_cols", "index_wide" */
 void gkmb200_set_verbosity(int level);               /* 0..4 like gkmOpt.verbosity */
 
 /* ---- host-only arithmetic of the path (no GPU needed) ---- */
@@ -77,6 +77,35 @@ int gkmb200_hist_block(gkmb200_problem *p, int row0, int nrows, int col0, int nc
 /* out[r-row0] = bias + sum_c alpha[c-col0] * K(r,c), reduced on the device */
 int gkmb200_decision_values(gkmb200_problem *p, int row0, int nrows, int col0, int ncols,
                             const double *alpha, double bias, double *out);
+
+/* ---- the consumer of the matrix: cross-validated C-SVC on the precomputed kernel ---- */
+/* One fit = one (train, test) split, like one call of _svm_train_proc in scripts/gkmsvm.py:104-122.
+ * train_idx / test_idx hold sequence ids; the training ids of a fit must be grouped by class, label 0 (the
+ * negatives) first -- the order libsvm gives them (svm_group_classes) -- and train_y must be +1 for that first
+ * class and -1 for the other (libsvm's sub-problem labels).  gkmqc_b200/driver.py prepares both from 0/1 labels. */
+typedef struct gkmb200_svm_task {
+    long long train_off, test_off; /* first entry of this fit in train_idx / train_y and in test_idx / scores */
+    int ntrain, ntest;
+} gkmb200_svm_task;
+
+typedef struct gkmb200_svm_fit {
+    double rho;    /* libsvm's rho of the sub-problem (sklearn's intercept_ = +rho after its sign flip) */
+    double obj;    /* dual objective value */
+    double nu;     /* sum(alpha) / ntrain, what gkmsvm.py:120 logs */
+    int n_iter;    /* SMO iterations */
+    int n_sv;      /* support vectors */
+    long long reserved;
+} gkmb200_svm_fit;
+
+/* Trains every fit with libsvm's SMO (C-SVC, second-order working-set selection, no shrinking; C, eps = SVC's C and
+ * tol; max_iter < 0: libsvm's own ceiling) on the GPU, all fits concurrently, and evaluates their test points:
+ * scores[test_off + r] = sklearn's decision_function value (positive = label 1).
+ * kmat != NULL: dense symmetric n x n host matrix with ld doubles per row (what computeGkmKernel returns).
+ * kmat == NULL: the kernel matrix of problem p is computed on the device and never leaves it (n = problem size).
+ * fits[ntasks] and alpha[sum of ntrain] (in training order) may be NULL. */
+int gkmb200_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,
+                   const int *train_idx, const signed char *train_y, const int *test_idx,
+                   double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha);
 
 /* ---- measurement ---- */
 int gkmb200_get_stats(const gkmb200_problem *p, gkmb200_stats *out);

@@ -1,0 +1,112 @@
+"""GPU tier for the consumer of the kernel matrix: the C-SVC cross-validation of
+scripts/gkmsvm.py:104-160 on the GPU against sklearn's SVC(kernel="precomputed") -- sklearn's bundled libsvm is the
+reference implementation of this piece (third-party; scikit-learn 1.9.0 in this image and on the GPU box).
+
+Bar: the GPU solver restates libsvm's SMO arithmetic (float-cached Q rows, tie rules, unfused updates), so the
+iterates coincide: same iteration count and support vectors, alpha and decision values to 1e-9 relative.  Should the
+paths ever part (they stop within eps = 1e-3 of the same optimum), the looser tier still holds: AUC within 2e-3."""
+import numpy as np
+import pytest
+
+from conftest import random_seqs
+from gkmqc_b200 import capi, driver
+
+pytestmark = pytest.mark.gpu
+
+SVC = pytest.importorskip("sklearn.svm").SVC
+from sklearn.metrics import roc_auc_score
+from sklearn.model_selection import StratifiedKFold
+
+
+@pytest.fixture(scope="module")
+def problem():
+    """two classes that differ by planted motifs, so that the SVM has something to learn"""
+    capi.load()
+    rng = np.random.default_rng(5)
+    npos = nneg = 300
+    seqs = random_seqs(npos + nneg, 200, seed=21)
+    motifs = ["GATAAGGCAT", "TTGACGTCAA", "CCCGCCCCTA"]
+    for i in range(npos):
+        s = list(seqs[i])
+        for m in motifs[: 1 + i % 3]:
+            p = int(rng.integers(0, 190))
+            mm = list(m)
+            if rng.random() < 0.5:
+                mm[int(rng.integers(0, 10))] = "ACGT"[int(rng.integers(0, 4))]
+            s[p:p + 10] = mm
+        seqs[i] = "".join(s)
+    P = capi.Problem(4, 10, 6, 3, 50, 50.0, 1.0)
+    P.add_many(seqs)
+    K = P.kernel_lower()
+    K = np.maximum(K, K.T)
+    y = np.concatenate((np.ones(npos, int), np.zeros(nneg, int)))
+    yield P, K, y
+    P.close()
+
+
+def sklearn_fit(K, y, train, test, C, eps):
+    sv = SVC(kernel="precomputed", C=C, tol=eps, shrinking=False, gamma=1.0, cache_size=500)
+    sv.fit(K[train][:, train], y[train])
+    return sv, sv.decision_function(K[test][:, train])
+
+
+@pytest.mark.parametrize("C,eps", [(1.0, 1e-3), (0.1, 1e-3), (10.0, 1e-4)])
+def test_fits_follow_libsvm(problem, C, eps):
+    P, K, y = problem
+    kf = StratifiedKFold(n_splits=5, shuffle=True, random_state=3)
+    splits = list(kf.split(np.zeros(len(y)), y))
+    scores, fits, alphas = capi.svm_cv(y, splits, kmat=K, C=C, eps=eps)
+    for (train, test), s, f, a in zip(splits, scores, fits, alphas):
+        sv, ref = sklearn_fit(K, y, train, test, C, eps)
+        # loose tier first: whatever the path, the optimum is the same within the stopping tolerance
+        assert abs(roc_auc_score(y[test], s) - roc_auc_score(y[test], ref)) < 2e-3
+        np.testing.assert_allclose(s, ref, atol=5 * eps * max(1.0, C))
+        # strict tier: same path
+        assert f["n_sv"] == len(sv.support_)
+        order = np.concatenate((train[y[train] == 0], train[y[train] == 1]))   # libsvm's grouping
+        sv_ids = order[a > 0]
+        assert np.array_equal(np.sort(sv_ids), np.sort(train[sv.support_]))
+        # dual_coef_ = alpha * y' with sklearn's sign flip: negative for label 0
+        coef = np.where(y[order] == 0, -a, a)[a > 0]
+        by_id = dict(zip(train[sv.support_], sv.dual_coef_[0]))
+        np.testing.assert_allclose(coef, [by_id[i] for i in sv_ids], rtol=1e-9, atol=1e-12)
+        assert f["rho"] == pytest.approx(sv.intercept_[0], rel=1e-9, abs=1e-12)
+        np.testing.assert_allclose(s, ref, rtol=1e-9, atol=1e-11)
+        assert f["nu"] == pytest.approx(np.sum(np.abs(sv.dual_coef_[0])) / len(train), rel=1e-9)
+
+
+def test_resident_matrix_equals_host_matrix(problem):
+    """kmat = NULL: the kernel matrix is computed on the device, mirrored there and consumed there"""
+    P, K, y = problem
+    kf = StratifiedKFold(n_splits=4, shuffle=True, random_state=11)
+    splits = list(kf.split(np.zeros(len(y)), y))
+    s_host, f_host, _ = capi.svm_cv(y, splits, kmat=K, C=1.0, eps=1e-3)
+    s_dev, f_dev, _ = capi.svm_cv(y, splits, problem=P, C=1.0, eps=1e-3)
+    for a, b in zip(s_host, s_dev):
+        assert np.array_equal(a, b)
+    assert [f["n_iter"] for f in f_host] == [f["n_iter"] for f in f_dev]
+
+
+def test_driver_crossValidate_matches_the_reference_flow(problem):
+    """gkmsvm.crossValidate (gkmsvm.py:126-176) restated with sklearn fits, against the driver mirror"""
+    P, K, y = problem
+    npos = int(y.sum())
+    args_svm = [1.0, 0.001, 0, 100, 5, 2, 0, 7, 4]
+    mean_gpu, std_gpu = driver.crossValidate(args_svm, K, npos, len(y) - npos)
+    aucs = []
+    for _ in range(2):
+        kf = StratifiedKFold(n_splits=5, shuffle=True, random_state=7)
+        for train, test in kf.split(np.zeros(len(y)), y):
+            _, ref = sklearn_fit(K, y, train, test, 1.0, 0.001)
+            aucs.append(roc_auc_score(y[test], ref))
+    assert mean_gpu == pytest.approx(np.mean(aucs), abs=1e-9)
+    assert std_gpu == pytest.approx(np.std(aucs), abs=1e-9)
+    assert 0.6 < mean_gpu <= 1.0
+
+
+def test_bad_arguments(problem):
+    P, K, y = problem
+    with pytest.raises(ValueError):
+        capi.svm_cv(y, [(np.arange(10), np.arange(10, 20))], kmat=K)   # one class only
+    with pytest.raises(capi.GkmError):
+        capi.svm_cv(y, [(np.arange(len(y)), np.arange(5))], kmat=K, C=-1.0)
