@@ -156,3 +156,20 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"pyoracle|gkm_oracle|oracle/|gkmo_|gkmref_", text):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_svm_task_preparation_follows_libsvm_grouping():
+    """host logic of the f4 consumer: per fit the training ids are grouped label 0 first (libsvm's svm_group_classes
+    with sklearn's label sort) and that class is the sub-problem's +1"""
+    import numpy as np
+    import pytest
+    from gkmqc_b200 import capi
+    y = np.array([1, 0, 1, 0, 0, 1, 1, 0])
+    splits = [(np.array([6, 1, 0, 3, 5]), np.array([2, 4, 7])), (np.array([7, 2, 4, 5]), np.array([0]))]
+    tasks, tr, ty, te = capi.svm_prepare_tasks(y, splits)
+    assert (tasks[0].train_off, tasks[0].test_off, tasks[0].ntrain, tasks[0].ntest) == (0, 0, 5, 3)
+    assert (tasks[1].train_off, tasks[1].test_off, tasks[1].ntrain, tasks[1].ntest) == (5, 3, 4, 1)
+    assert tr.tolist() == [1, 3, 6, 0, 5, 7, 4, 2, 5] and ty.tolist() == [1, 1, -1, -1, -1, 1, 1, -1, -1]
+    assert te.tolist() == [2, 4, 7, 0]
+    with pytest.raises(ValueError):
+        capi.svm_prepare_tasks(y, [(np.array([0, 2]), np.array([1]))])
