@@ -13,6 +13,8 @@
  */
 #include <cuda_runtime.h>
 #include <pthread.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -517,8 +519,8 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             const double nq = sum / (double) p->n;
             const long long entries = (long long) nrows * (long long) ncols / (lower ? 2 : 1);
             /* lower: row a probes only the blocks that start below it */
-            const int eff_blocks = lower ? (blocks + 1) / 2 : blocks;
-            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks > 0 ? eff_blocks : 1, entries, 2.0 * nq * nq);
+            const double eff_blocks = lower ? 0.5 * (double) (blocks + 1) : (double) blocks;
+            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks, entries, 2.0 * nq * nq);
             const double cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
             ok = ci < cd;
             gkm_log(GKM_LOG_DEBUG, "kernel = auto: index %.2f ms vs diag %.2f ms (estimates)", ci, cd);
@@ -839,6 +841,29 @@ static long long plan_budget(const gkmb200_problem *p, long long total_cells, in
     return want < cap ? want : cap;
 }
 
+/* The caller's matrix is fresh, never-touched memory (np.zeros of 15000 x 15000, gkmsvm.py:75): every 4 KB page
+ * the scatter writes first takes a page fault.  Where transparent huge pages are in "madvise" mode a hint on the
+ * destination span turns ~100 000 small faults of a 10k problem into a few hundred 2 MB ones.  A hint only: it
+ * changes no contents and no ownership; GKM_NO_THP=1 switches it off. */
+static void advise_hugepages(double **rows, int row0, int nrows, int col0, int ncols)
+{
+    if (nrows < 2 || ncols < 1) return;
+    uintptr_t lo = (uintptr_t) (rows[row0] + col0), hi = lo;
+    for (int r = row0; r < row0 + nrows; r++) {
+        const uintptr_t a = (uintptr_t) (rows[r] + col0), b = a + (uintptr_t) ncols * sizeof(double);
+        if (a < lo) lo = a;
+        if (b > hi) hi = b;
+    }
+    const uintptr_t page = (uintptr_t) sysconf(_SC_PAGESIZE);
+    lo = (lo + page - 1) & ~(page - 1);  /* inwards: only whole pages of the destination itself */
+    hi &= ~(page - 1);
+    if (hi <= lo || hi - lo > ((uintptr_t) 1 << 38) || hi - lo < ((uintptr_t) 4 << 20)) return;
+    /* rows far apart (not one array) would make the span meaningless: require it to be no larger than 4x the rows' own extent */
+    if ((double) (hi - lo) > 4.0 * (double) nrows * (double) ((uintptr_t) rows[row0 + 1] > (uintptr_t) rows[row0]
+                                                          ? (uintptr_t) rows[row0 + 1] - (uintptr_t) rows[row0] : (uintptr_t) ncols * 8)) return;
+    (void) madvise((void *) lo, (size_t) (hi - lo), MADV_HUGEPAGE);
+}
+
 extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower,
                                double *out, long ld, double **rows, int32_t *hist, int copy_threads)
 {
@@ -874,7 +899,9 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
                 if (gkm_chunk_owner(c, nchunks, p->shard_world) == p->shard_rank) owned[job.nowned++] = c;
             job.row0 = row0; job.col0 = col0; job.ncols = ncols; job.lower = lower;
             job.out = out; job.ld = ld; job.rows = rows; job.hist = hist;
-            job.copy_threads = copy_threads;
+            /* the host threads that scatter finished chunks are shared by the GPUs of the call */
+            job.copy_threads = copy_threads / ds->ndev > 1 ? copy_threads / ds->ndev : (ds->ndev > 1 ? 2 : copy_threads);
+            if (rows && !getenv("GKM_NO_THP")) advise_hugepages(rows, row0, nrows, col0, ncols);
             gkm_devthread dts[GKM_MAX_DEV];
             pthread_t th[GKM_MAX_DEV];
             int started[GKM_MAX_DEV];

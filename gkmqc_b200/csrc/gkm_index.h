@@ -89,7 +89,7 @@ long long gkm_idx_cold_count(int L, int d);
 int gkm_idx_supported(int L, int d, int nbins);
 
 /* rough cost model used by kernel = auto: estimated device milliseconds */
-double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, int col_blocks, long long entries,
+double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, double col_blocks, long long entries,
                        double mean_pairs_per_entry);
 double gkm_diag_cost_ms(int d, int weighted, long long entries, double mean_pairs_per_entry);
 

@@ -92,31 +92,32 @@ int gkm_idx_supported(int L, int d, int nbins)
     return nd > 0 && nd <= (64LL << 20); /* the mask list itself must stay small (256 MB) */
 }
 
-/* Device-time estimates, fitted to round-1 measurements on one B200 (L = 11, d = 3, 300 bp):
- *   10 000 rows x 1 block 41.0 ms, 14 144 x 1 block 72.2 ms, 28 288 x 2 blocks 228 ms  (compact slots)
- *   -> probes 8.7e11 /s + postings in range 4.1e11 /s, and never faster than 4e11 probes /s (the L1/L2 sector rate);
- *   16-byte slots (weighted types): 0.8 of that; tables that do not fit L2 (> 64 MB): probes at 1.5e11 /s;
- *   build ~1 ms per column block + 0.3 ms;
- *   diag  2.94e13 L-mer pairs /s (d <= 3), 2.3e13 (d = 4), ~1.2e13 (d <= 7), ~6e12 above; weighted types 0.6 of that. */
-double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, int col_blocks, long long entries,
+/* Device-time estimates, fitted to round-1 measurements on one B200 (300 bp):
+ *   L = 11, d = 3: 10 000 rows x 1 block 41.0 ms, 14 144 x 1 block 72.2 ms, 28 288 x 2 blocks 228 ms (compact slots)
+ *   -> probes 8.7e11 /s + postings in range 4.1e11 /s, and never faster than the sector rate of the slot probes:
+ *      4e11 /s while the table sits in L2 (<= 64 MB), 1.8e11 /s up to 256 MB (L = 12), 0.9e11 /s beyond (L >= 13);
+ *      checked against the 15 (L, d) of BASELINE configs[2] at 20 000 sequences (profiles/r1_config3_sweep_20k_index.*);
+ *   16-byte slots (weighted types): 0.8 of that;  build ~1 ms per column block + 0.3 ms + the table memset;
+ *   diag  2.94e13 L-mer pairs /s (d <= 3), 1.35e13 (d = 4), ~1.2e13 (d <= 7), ~6e12 above; weighted types 0.6 of that. */
+double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, double col_blocks, long long entries,
                        double mean_pairs_per_entry)
 {
     const double nd = (double) gkm_idx_delta_count(L, d);
     const double slots = pow(4.0, (double) L);
     const double slot_bytes = weighted ? 16.0 : 8.0;
-    const int in_l2 = slots * slot_bytes <= 64.0 * 1048576.0;
+    const double tab_mb = slots * slot_bytes / 1048576.0;
     const double scale = weighted ? 0.8 : 1.0;
-    const double probes = (double) rows * mean_query_lmers * nd * (double) col_blocks;
+    const double probes = (double) rows * mean_query_lmers * nd * col_blocks;
     const double hits = (double) entries * mean_pairs_per_entry * nd / slots; /* random sequences: P(distance <= d) = nd / 4^L */
     double t = probes / (8.7e11 * scale) + hits / (4.1e11 * scale);
-    const double floor_t = probes / ((in_l2 ? 4.0e11 : 1.5e11) * scale);
+    const double floor_t = probes / ((tab_mb <= 64.0 ? 4.0e11 : tab_mb <= 256.0 ? 1.8e11 : 0.9e11) * scale);
     if (t < floor_t) t = floor_t;
-    return 1e3 * t + 1.0 * (double) col_blocks + 0.3 + slots * slot_bytes / 3e12 * 1e3;
+    return 1e3 * t + 1.0 * col_blocks + 0.3 + slots * slot_bytes / 3e12 * 1e3;
 }
 
 double gkm_diag_cost_ms(int d, int weighted, long long entries, double mean_pairs_per_entry)
 {
-    double rate = (d <= 3) ? 2.94e13 : (d == 4) ? 2.3e13 : (d <= 7) ? 1.2e13 : 6e12;
+    double rate = (d <= 3) ? 2.94e13 : (d == 4) ? 1.35e13 : (d <= 7) ? 1.2e13 : 6e12;
     if (weighted) rate *= 0.6;
     return 1e3 * (double) entries * mean_pairs_per_entry / rate;
 }

@@ -22,7 +22,7 @@ def lib(product_lib):
     product_lib.gkm_idx_cold_count.restype = ctypes.c_longlong
     product_lib.gkm_idx_cold_count.argtypes = [ctypes.c_int, ctypes.c_int]
     product_lib.gkm_idx_cost_ms.restype = ctypes.c_double
-    product_lib.gkm_idx_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_int,
+    product_lib.gkm_idx_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double, ctypes.c_double,
                                             ctypes.c_longlong, ctypes.c_double]
     product_lib.gkm_diag_cost_ms.restype = ctypes.c_double
     product_lib.gkm_diag_cost_ms.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, ctypes.c_double]

@@ -8,13 +8,14 @@ import bench
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 kt = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 variants = sys.argv[3].split(",") if len(sys.argv) > 3 else ["index", "diag"]
+L, KK, D = (int(x) for x in sys.argv[4].split(",")) if len(sys.argv) > 4 else (11, 7, 3)
 capi.load()
 arr = bench.synth(n)
 seqs = [a.tobytes().decode() for a in arr]
 H = {}
 for v in variants:
     capi.set_option("kernel", v)
-    with capi.Problem(kt, 11, 7, 3, 50, 50.0, 1.0) as P:
+    with capi.Problem(kt, L, KK, D, 50, 50.0, 1.0) as P:
         P.add_many(seqs)
         t0 = time.time(); P.upload(); t1 = time.time()
         ms = P.bench_lower_resident(3, 2, flush_l2=True)

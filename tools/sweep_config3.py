@@ -37,7 +37,7 @@ def main():
     capi.load()
     if not pyoracle.have_ref():
         raise SystemExit("oracle/_ref is not present: build it where /root/reference exists")
-    out = {"n": n, "rows": rows, "triples": [], "timing": []}
+    out = {"n": n, "rows": rows, "triples": [], "timing": [], "GKM_KERNEL": os.environ.get("GKM_KERNEL", "auto")}
     nbad = 0
     for L in range(10, 15):
         t0 = time.time()
@@ -90,11 +90,12 @@ def main():
                 P.read(pos, neg)
                 ms = P.bench_lower_resident(1, 1, True)
                 rate = n * (n - 1) / 2 / ms.mean() / 1e3
-                out["timing"].append({"L": L, "d": d, "ms_per_pass": float(ms.mean()), "M_entries_per_s": rate})
-                print("timing L=%d d=%d: %.1f ms  %.1f M entries/s" % (L, d, ms.mean(), rate), flush=True)
+                variant = {1: "lmer", 2: "diag", 3: "mma", 4: "index"}.get(P.stats()["kernel_variant"], "?")
+                out["timing"].append({"L": L, "d": d, "ms_per_pass": float(ms.mean()), "M_entries_per_s": rate, "kernel": variant})
+                print("timing L=%d d=%d: %.1f ms  %.1f M entries/s (%s)" % (L, d, ms.mean(), rate, variant), flush=True)
     out["all_ok"] = nbad == 0
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "sweep_config3.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "sweep_config3_%s.json" % out["GKM_KERNEL"]), "w") as f:
         json.dump(out, f, indent=1)
     print("sweep: %d triples, %d failures" % (len(out["triples"]), nbad))
     sys.exit(1 if nbad else 0)
