@@ -65,7 +65,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(BIN_DIR, LIB_NAME)
+    # GKM_PYLIB: another build of the same library (kernel A/B runs, tools/ab_variants.sh); the product path is bin/
+    return os.environ.get("GKM_PYLIB") or os.path.join(BIN_DIR, LIB_NAME)
 
 
 def load(path=None):

@@ -769,6 +769,8 @@ static int dev_thread_body(gkm_devthread *dt)
     const int depth = job->hist ? 1 : GKM_NBUF;
     int inslot[GKM_NBUF];
     int head = 0, inflight = 0, rc = 0;
+    const double tb0 = now_ms();
+    double t_wait = 0.0, t_scatter = 0.0, t_issue = 0.0, t_lastsync = tb0;
     if (cudaEventRecord(g->span0, g->sc) != cudaSuccess) { gkm_set_error("CUDA: event record failed"); return 1; }
     while (!rc && inflight < depth) {
         const int nxt = __atomic_fetch_add(&job->next, 1, __ATOMIC_RELAXED);
@@ -778,9 +780,11 @@ static int dev_thread_body(gkm_devthread *dt)
         rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], s, d_hist);
         inflight++;
     }
+    t_issue += now_ms() - tb0;
     while (!rc && inflight > 0) {
         const int s = head % GKM_NBUF;
         const gkm_chunk *c = &job->chunks[job->owned[inslot[s]]];
+        const double tw0 = now_ms();
         if (cudaEventSynchronize(g->cdone[s]) != cudaSuccess) {
             gkm_set_error("CUDA: kernel or copy failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = 1;
@@ -789,7 +793,10 @@ static int dev_thread_body(gkm_devthread *dt)
         float ms = 0.f;
         /* device time of the call so far: first kernel start -> end of this chunk's kernel (chunks overlap) */
         if (cudaEventElapsedTime(&ms, g->span0, g->k1[s]) == cudaSuccess && ms > dt->kernel_ms) dt->kernel_ms = ms;
+        t_lastsync = now_ms();
+        t_wait += t_lastsync - tw0;
         if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[s]);
+        t_scatter += now_ms() - t_lastsync;
         if (job->hist) {
             const int width = c->col_end - c->col_begin, nb = p->nbins;
             const size_t cells = (size_t) (c->row_end - c->row_begin) * (size_t) width;
@@ -813,10 +820,14 @@ static int dev_thread_body(gkm_devthread *dt)
         if (nxt < job->nowned) {
             const int ns = (head + inflight) % GKM_NBUF;
             inslot[ns] = nxt;
+            const double ti0 = now_ms();
             rc = dev_issue(dt, g, im, &job->chunks[job->owned[nxt]], ns, d_hist);
+            t_issue += now_ms() - ti0;
             inflight++;
         }
     }
+    gkm_log(GKM_LOG_DEBUG, "GPU %d: %.2f ms in all: issue %.2f, waiting for chunks %.2f, scatter %.2f (after the last chunk arrived: %.2f)",
+            ds->dev[dt->slot], now_ms() - tb0, t_issue, t_wait, t_scatter, now_ms() - t_lastsync);
     if (rc) cudaDeviceSynchronize();
     if (d_hist) cudaFree(d_hist);
     free(h_hist);
@@ -839,6 +850,26 @@ static long long plan_budget(const gkmb200_problem *p, long long total_cells, in
     long long want = total_cells * 8 / (16LL * ndev * p->shard_world);
     if (want < (4LL << 20)) want = 4LL << 20;
     return want < cap ? want : cap;
+}
+
+/* Host threads that scatter finished chunks into the caller's rows.  The reference's `nthreads` (default 1 in
+ * bin/gkmqc.py:107,162) is its number of COMPUTE threads; here the only host work that scales with it is the copy-out,
+ * which at 10k is 100 000 first-touch page faults of the caller's fresh matrix: 72 / 54 / 50 ms per call with 4 / 8 /
+ * >= 12 threads on the 16-core GPU box (tools/e2e_ab.py), GPU-bound from 12 on.  So the request is a lower bound and
+ * the library uses the cores this process may run on (its affinity mask: cgroup- and slurm-aware), 16 at most.
+ * GKM_COPY_THREADS overrides. */
+#include <sched.h>
+extern "C" int gkm_copy_threads(int requested)
+{
+    const char *e = getenv("GKM_COPY_THREADS");
+    if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
+    int avail = 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
+    if (avail < 1) avail = (int) sysconf(_SC_NPROCESSORS_ONLN);
+    if (avail > 16) avail = 16;
+    return requested > avail ? (requested > 64 ? 64 : requested) : (avail < 1 ? 1 : avail);
 }
 
 /* The caller's matrix is fresh, never-touched memory (np.zeros of 15000 x 15000, gkmsvm.py:75): every 4 KB page
@@ -872,11 +903,20 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
         gkm_set_error("block [%d,+%d) x [%d,+%d) outside the problem (n=%d)", row0, nrows, col0, ncols, p->n);
         return 1;
     }
+    copy_threads = gkm_copy_threads(copy_threads);
+    if (p->shard_world > 1 && !getenv("GKM_COPY_THREADS")) { /* the ranks of one box share its cores */
+        copy_threads /= p->shard_world;
+        if (copy_threads < 2) copy_threads = 2;
+    }
     pthread_mutex_lock(&g_lock);
     const double t0 = now_ms();
     p->stats.launches = 0;
+    const char *ord = getenv("GKM_CHUNK_ORDER"); /* A/B knob: "asc" = rows in ascending order */
+    const int desc = lower && !(ord && ord[0] == 'a');
     int rc = upload_locked(p, 0);
+    const double t_up = now_ms();
     if (!rc) rc = choose_variant(p, row0, nrows, col0, ncols, lower);
+    const double t_var = now_ms();
     gkm_chunk *chunks = NULL;
     int *owned = NULL;
     if (!rc) {
@@ -895,8 +935,12 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
             gkm_job job;
             memset(&job, 0, sizeof(job));
             job.p = p; job.chunks = chunks; job.owned = owned;
-            for (int c = 0; c < nchunks; c++)
+            /* triangle: widest chunks first, so that the call ends on the chunk with the smallest copy and scatter
+             * (the last D2H + scatter cannot overlap anything; rows 0..591 are 2.8 MB, the last 592 rows 47 MB) */
+            for (int i = 0; i < nchunks; i++) {
+                const int c = desc ? nchunks - 1 - i : i;
                 if (gkm_chunk_owner(c, nchunks, p->shard_world) == p->shard_rank) owned[job.nowned++] = c;
+            }
             job.row0 = row0; job.col0 = col0; job.ncols = ncols; job.lower = lower;
             job.out = out; job.ld = ld; job.rows = rows; job.hist = hist;
             /* the host threads that scatter finished chunks are shared by the GPUs of the call */
@@ -931,6 +975,8 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
     free(chunks);
     free(owned);
     p->stats.wall_ms = now_ms() - t0;
+    gkm_log(GKM_LOG_DEBUG, "compute: pack+upload %.2f ms, variant+index %.2f ms, chunks %.2f ms (device span %.2f ms)",
+            t_up - t0, t_var - t_up, now_ms() - t_var, p->stats.kernel_ms);
     pthread_mutex_unlock(&g_lock);
     return rc;
 }

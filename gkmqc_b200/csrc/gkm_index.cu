@@ -3,7 +3,7 @@
  * Build (once per column block of a problem, a few ms):
  *   gkm_idx_keys_kernel   every valid L-mer window of both strands of the block's columns ->
  *                         64-bit key  code << 32 | column << 8 | weight
- *   cub radix sort        by (code, column)            [library call, set-up only]
+ *   cub radix sort        by code, stable: columns stay ascending   [library call, set-up only]
  *   gkm_idx_runs_kernel   run length of every distinct code; overflow demand of runs >= 5
  *   cub exclusive scan    overflow offsets             [library call, set-up only]
  *   gkm_idx_fill_kernel   slots {posting 0, 1, 2, posting 3 | pointer} and overflow lists
@@ -29,7 +29,12 @@
 #define GKM_IDX_UNROLL 4
 #endif
 #define GKM_IDX_QCAP 64 /* queued overflow walks per warp: < 32 waiting + <= 32 new */
-#define GKM_IDX_QBYTES ((GKM_IDX_THREADS / 32) * GKM_IDX_QCAP * 8)
+#define GKM_IDX_LQCAP 32 /* long lists waiting for a whole-warp walk, per warp */
+/* queue entry: (list, bin row, weight).  Compact slots: 4 bytes; 16-byte slots: 8 bytes.  The queues are kept small on
+ * purpose: at 10 000 columns two CTAs per SM need 2 x (80 KB histogram + queues + query) of shared memory, and
+ * every KB beyond 196 KB per SM moves the L1/shared split to its last step (28 KB of L1 instead of 60), which
+ * measured 4 % slower (the in-flight slot probes live in L1 lines): tools/ab_variants.sh, DESIGN.md 4.4. */
+#define GKM_IDX_QBYTES_FMT(c16) ((GKM_IDX_THREADS / 32) * (GKM_IDX_QCAP + GKM_IDX_LQCAP) * ((c16) ? 4 : 8) + (GKM_IDX_THREADS / 32) * 4)
 
 /* ------------------------------------------------------------------ */
 /* build                                                                */
@@ -104,8 +109,13 @@ gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int
     runlen[i] = len;
     /* overflow entries of a run of 5 or more: P32 keeps postings 3.. (32-bit entries, quads), C16 columns 2..
      * (16-bit entries, octets); both padded with at least one end marker */
-    if (fmt == GKM_IDX_FMT_C16) need[i] = (len >= 5) ? ((len - 2u + 8u) & ~7u) : 0u;
-    else need[i] = (len >= 5) ? ((len - 3u + 4u) & ~3u) : 0u;
+    if (fmt == GKM_IDX_FMT_C16) {
+        const uint32_t units = (len >= 5) ? GKM_IDX_C16_UNITS(len) : 0u;
+        need[i] = 8u * (units + (units >= GKM_IDX_LONG_UNITS ? 1u : 0u)); /* long lists carry a header unit */
+    } else {
+        const uint32_t units = (len >= 5) ? GKM_IDX_P32_UNITS(len) : 0u;
+        need[i] = 4u * (units + (units >= GKM_IDX_LONG_UNITS ? 1u : 0u));
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -132,15 +142,18 @@ gkm_idx_fill_kernel(const unsigned long long *__restrict__ keys, uint32_t P, con
     const uint32_t len = runlen[lb], r = i - lb;
     const uint32_t posting = gkm_idx_posting((uint32_t) (key >> 8) & GKM_IDX_COL_MASK, (uint32_t) key & 0xFFu);
     uint32_t *slot = reinterpret_cast<uint32_t *>(tab + code);
+    const uint32_t units = (len >= 5) ? GKM_IDX_P32_UNITS(len) : 0u;
+    const bool lng = units >= GKM_IDX_LONG_UNITS;
+    const uint32_t data = ovfofs[lb] + (lng ? 4u : 0u); /* behind the header unit */
     if (r < 3 || (r == 3 && len == 4)) {
         slot[r] = posting;
     } else {
-        ovf[ovfofs[lb] + r - 3] = posting;
+        ovf[data + r - 3] = posting;
     }
     if (r == 0 && len >= 5) {
-        slot[3] = GKM_IDX_PTR | ovfofs[lb];
-        const uint32_t end = (len - 3u + 4u) & ~3u; /* lists are read 16 bytes at a time */
-        for (uint32_t t = len - 3; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_EMPTY;
+        slot[3] = GKM_IDX_PTR | ovfofs[lb] | (lng ? GKM_IDX_LONG : 0u);
+        if (lng) { ovf[ovfofs[lb]] = units; ovf[ovfofs[lb] + 1] = 0; ovf[ovfofs[lb] + 2] = 0; ovf[ovfofs[lb] + 3] = 0; }
+        for (uint32_t t = len - 3; t < 4u * units; t++) ovf[data + t] = GKM_IDX_EMPTY; /* lists are read 16 bytes at a time */
     }
 }
 
@@ -170,19 +183,25 @@ gkm_idx_fill_c16_kernel(const unsigned long long *__restrict__ keys, uint32_t P,
     if (len <= 4) {
         slot[r] = col;
     } else {
+        const uint32_t units = GKM_IDX_C16_UNITS(len);
+        const bool lng = units >= GKM_IDX_LONG_UNITS;
+        const uint32_t data = ovfofs[lb] + (lng ? 8u : 0u); /* behind the header unit */
         if (r < 2) slot[r] = col;
-        else ovf[ovfofs[lb] + r - 2] = col;
+        else ovf[data + r - 2] = col;
         if (r == 0) {
-            reinterpret_cast<uint32_t *>(tab + code)[1] = GKM_IDX_PTR | ovfofs[lb];
-            const uint32_t end = (len - 2u + 8u) & ~7u;
-            for (uint32_t t = len - 2; t < end; t++) ovf[ovfofs[lb] + t] = GKM_IDX_C16_NONE;
+            reinterpret_cast<uint32_t *>(tab + code)[1] = GKM_IDX_PTR | ovfofs[lb] | (lng ? GKM_IDX_LONG : 0u);
+            if (lng) {
+                uint32_t *h = reinterpret_cast<uint32_t *>(ovf + ovfofs[lb]);
+                h[0] = units; h[1] = 0; h[2] = 0; h[3] = 0;
+            }
+            for (uint32_t t = len - 2; t < 8u * units; t++) ovf[data + t] = GKM_IDX_C16_NONE;
         }
     }
 }
 
 size_t gkm_idx_tab_bytes(int L, int fmt) { return ((size_t) 1 << (2 * L)) * (fmt == GKM_IDX_FMT_C16 ? sizeof(uint2) : sizeof(uint4)); }
 
-/* overflow demand is at most 2 entries per posting in either format */
+/* overflow demand is at most 2 entries per posting in either format (header unit of the long lists included) */
 size_t gkm_idx_ovf_bytes(size_t P, int fmt) { return (2 * P + 16) * (fmt == GKM_IDX_FMT_C16 ? 2 : 4); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
@@ -191,7 +210,7 @@ size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out)
 {
     size_t t1 = 0, t2 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, t1, (const unsigned long long *) nullptr, (unsigned long long *) nullptr,
-                                   (int) P, 8, 32 + 2 * L);
+                                   (int) P, 32, 32 + 2 * L);
     cub::DeviceScan::ExclusiveSum(nullptr, t2, (const uint32_t *) nullptr, (uint32_t *) nullptr, (int) P);
     const size_t cubb = align256(t1 > t2 ? t1 : t2);
     if (cub_bytes_out) *cub_bytes_out = cubb;
@@ -213,7 +232,9 @@ int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st)
     if ((e = cudaMemsetAsync(a->tab, 0xFF, gkm_idx_tab_bytes(a->L, a->fmt), st)) != cudaSuccess) goto fail;
     if (a->wend) gkm_idx_keys_kernel<true><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
     else gkm_idx_keys_kernel<false><<<(unsigned) (a->ce - a->cb), 128, 0, st>>>(a->planes, a->lens, a->wend, a->W, a->L, a->cb, a->offs, keys_a);
-    if ((e = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, (int) P, 8, 32 + 2 * a->L, st)) != cudaSuccess) goto fail;
+    /* the keys are generated in column order and the radix sort is stable: sorting by the code bits alone leaves
+     * every run in ascending column order (3 passes instead of 6 at L = 11) */
+    if ((e = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, (int) P, 32, 32 + 2 * a->L, st)) != cudaSuccess) goto fail;
     {
         const unsigned blocks = (unsigned) ((P + 255) / 256);
         gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, a->fmt, runlen, need);
@@ -308,26 +329,99 @@ __device__ __forceinline__ void idx_walk16(const uint32_t *__restrict__ ovf, uin
     }
 }
 
-/* one probe, walks included, for the phases that need no warp-level bookkeeping (cold bins) */
+/* A long list (GKM_IDX_LONG), walked by the whole warp: lane l takes the units l, l + 32, ...  Equal columns are
+ * adjacent in a list (a column with a repeat owns a run of postings): each lane folds the runs inside its unit
+ * before it touches the histogram, so a homopolymer costs one atomic per unit instead of eight on one address. */
 template <bool WEIGHTED, bool RANGE, bool C16>
-__device__ __forceinline__ void idx_probe_one(const gkm_idx_rowargs &r, uint32_t y, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+__device__ __forceinline__ void idx_walk_long(const uint32_t *__restrict__ ovf, uint32_t ofs, int32_t *Hm, uint32_t blo, uint32_t bhi, int w, int lane)
 {
-    if constexpr (C16) {
-        const uint32_t o = idx_slot16<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi);
-        if (o != ~0u) idx_walk16<RANGE>(r.ovf, o, Hm, blo, bhi);
-    } else {
-        const uint32_t o = idx_slot<WEIGHTED, RANGE>(__ldg(reinterpret_cast<const uint4 *>(r.tab) + y), Hm, blo, bhi, w);
-        if (o != ~0u) idx_walk<WEIGHTED, RANGE>(r.ovf, o, Hm, blo, bhi, w);
+    const uint4 *q = C16 ? reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(ovf) + ofs)
+                         : reinterpret_cast<const uint4 *>(ovf + ofs);
+    const uint32_t units = __ldg(q).x;
+    for (uint32_t u = (uint32_t) lane; u < units; u += 32u) {
+        const uint4 v = __ldg(q + 1 + u);
+        if constexpr (C16) {
+            uint32_t cur = v.x & 0xFFFFu;
+            if (cur >= bhi) break; /* sorted by column: nothing wanted in this unit or behind it */
+            int cnt = 1;
+            const uint32_t c[7] = { v.x >> 16, v.y & 0xFFFFu, v.y >> 16, v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16 };
+#pragma unroll
+            for (int t = 0; t < 7; t++) {
+                if (c[t] == cur) cnt++;
+                else { idx_red<RANGE>(Hm, cur, blo, bhi, cnt); cur = c[t]; cnt = 1; }
+            }
+            idx_red<RANGE>(Hm, cur, blo, bhi, cnt);
+        } else {
+            uint32_t cur = v.x & GKM_IDX_COL_MASK;
+            if (cur >= bhi) break;
+            int acc = WEIGHTED ? w * (int) (v.x >> GKM_IDX_COL_BITS) : 1;
+            const uint32_t e[3] = { v.y, v.z, v.w };
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const uint32_t col = e[t] & GKM_IDX_COL_MASK;
+                const int val = WEIGHTED ? w * (int) (e[t] >> GKM_IDX_COL_BITS) : 1;
+                if (col == cur) acc += val;
+                else { idx_red<RANGE>(Hm, cur, blo, bhi, acc); cur = col; acc = val; }
+            }
+            idx_red<RANGE>(Hm, cur, blo, bhi, acc);
+        }
     }
+}
+
+/* queue entries.  o = offset of the overflow list in entries (a multiple of 8 / 4) | GKM_IDX_LONG */
+template <bool C16> struct idx_qe;
+template <> struct idx_qe<true> {
+    typedef uint32_t type; /* offset / 8 : 27 | long : 1 | bin row : 4 */
+    static __device__ __forceinline__ type make(uint32_t o, int mrow, int) { return (o >> 3) | ((o & GKM_IDX_LONG) << 27) | ((uint32_t) mrow << 28); }
+    static __device__ __forceinline__ uint32_t ofs(type e) { return (e & 0x07FFFFFFu) << 3; }
+    static __device__ __forceinline__ bool lng(type e) { return (e >> 27) & 1u; }
+    static __device__ __forceinline__ int mrow(type e) { return (int) (e >> 28); }
+    static __device__ __forceinline__ int w(type) { return 1; }
+    static __device__ __forceinline__ type none() { return 0u; }
+};
+template <> struct idx_qe<false> {
+    typedef uint2 type; /* {offset | long, bin row | weight << 8} */
+    static __device__ __forceinline__ type make(uint32_t o, int mrow, int w) { return make_uint2(o, (uint32_t) mrow | ((uint32_t) w << 8)); }
+    static __device__ __forceinline__ uint32_t ofs(type e) { return e.x & ~GKM_IDX_LONG; }
+    static __device__ __forceinline__ bool lng(type e) { return e.x & GKM_IDX_LONG; }
+    static __device__ __forceinline__ int mrow(type e) { return (int) (e.y & 0xFFu); }
+    static __device__ __forceinline__ int w(type e) { return (int) (e.y >> 8); }
+    static __device__ __forceinline__ type none() { return make_uint2(0u, 0u); }
+};
+
+/* one list by the lane that owns the entry; a long one from behind its header unit */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_walk_own(const gkm_idx_rowargs &r, uint32_t ofs, bool lng, int32_t *He, uint32_t blo, uint32_t bhi, int w)
+{
+    if constexpr (C16) idx_walk16<RANGE>(r.ovf, ofs + (lng ? 8u : 0u), He, blo, bhi);
+    else idx_walk<WEIGHTED, RANGE>(r.ovf, ofs + (lng ? 4u : 0u), He, blo, bhi, w);
+}
+
+/* the long queue of a warp, one list after the other, each by all 32 lanes */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_long(const gkm_idx_rowargs &r, const typename idx_qe<C16>::type *lq, int lqn, int32_t *Hb, int ldh,
+                                         uint32_t blo, uint32_t bhi, int lane)
+{
+    typedef idx_qe<C16> QE;
+    __syncwarp();
+    for (int i = 0; i < lqn; i++) {
+        const typename QE::type e = lq[i];
+        idx_walk_long<WEIGHTED, RANGE, C16>(r.ovf, QE::ofs(e), Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e), lane);
+    }
+    __syncwarp();
 }
 
 /* Probes of the masks [t_begin, t_end) into the COLD bins (global scratch row C; m <= d - 2, ~1 % of the hits and
  * a handful of masks): tiles of <= 1024 masks; inside a tile a thread keeps its mask and walks the query L-mers.
- * A short tile is shared by several "phases" of threads that take interleaved query L-mers. */
+ * A short tile is shared by several "phases" of threads that take interleaved query L-mers.  Overflow lists are
+ * walked on the spot, except the long ones (these masks are where a repeat meets itself): a lane parks them in its
+ * warp's long queue (shared counter, the lanes are divergent here) and the warp walks them together at the end. */
 template <bool WEIGHTED, bool RANGE, bool C16>
 __device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
-                                               int nq, int32_t *C, int ldh, uint32_t blo, uint32_t bhi)
+                                               int nq, int32_t *C, int ldh, uint32_t blo, uint32_t bhi,
+                                               typename idx_qe<C16>::type *lq, int *lqcnt)
 {
+    typedef idx_qe<C16> QE;
     const int tid = (int) threadIdx.x;
     for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
         const int rem = min(GKM_IDX_THREADS, t_end - t0);
@@ -338,29 +432,67 @@ __device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_b
         if (ph >= nph || tt >= rem) continue;
         const uint32_t dl = r.deltas[t0 + tt];
         const uint32_t dx = dl & 0x0FFFFFFFu;
-        int32_t *Hm = C + (size_t) (dl >> 28) * (size_t) ldh;
-        for (int xi = ph; xi < nq; xi += nph)
-            idx_probe_one<WEIGHTED, RANGE, C16>(r, xq[xi] ^ dx, Hm, blo, bhi, WEIGHTED ? (int) wq[xi] : 1);
+        const int mrow = (int) (dl >> 28);
+        int32_t *Hm = C + (size_t) mrow * (size_t) ldh;
+        for (int xi = ph; xi < nq; xi += nph) {
+            const uint32_t y = xq[xi] ^ dx;
+            const int w = WEIGHTED ? (int) wq[xi] : 1;
+            uint32_t o;
+            if constexpr (C16) o = idx_slot16<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi);
+            else o = idx_slot<WEIGHTED, RANGE>(__ldg(reinterpret_cast<const uint4 *>(r.tab) + y), Hm, blo, bhi, w);
+            if (o == ~0u) continue;
+            if (o & GKM_IDX_LONG) {
+                const int pos = atomicAdd(lqcnt, 1);
+                if (pos < GKM_IDX_LQCAP) { lq[pos] = QE::make(o, mrow, w); continue; }
+            }
+            idx_walk_own<WEIGHTED, RANGE, C16>(r, o & ~GKM_IDX_LONG, o & GKM_IDX_LONG, Hm, blo, bhi, w);
+        }
     }
+    __syncwarp();
+    const int cnt = min(*lqcnt, GKM_IDX_LQCAP);
+    if (cnt) idx_long<WEIGHTED, RANGE, C16>(r, lq, cnt, C, ldh, blo, bhi, tid & 31);
 }
 
-/* Probes of the masks [t_begin, t_end) into the HOT bins (shared memory H; bin 0 of H holds m = mbase).
+/* the queued walks of a warp, one entry per lane that `have`s one.  Short lists: every lane walks its own.  Long
+ * lists are only MOVED here, to the warp's long queue lq[0 .. lqn): they are walked by all 32 lanes at the end of
+ * the probe iteration (idx_long), where the prefetched slots are dead -- walked here, inside the unrolled probe
+ * body, their registers cost the 32-register build spills of exactly those slots (ptxas -v / SASS).  Should the
+ * long queue be full, the list is walked like a short one: slow, but only reached by more than 32 long lists in
+ * one iteration. */
+template <bool WEIGHTED, bool RANGE, bool C16>
+__device__ __forceinline__ void idx_drain(const gkm_idx_rowargs &r, typename idx_qe<C16>::type e, bool have, int32_t *Hb, int ldh,
+                                          uint32_t blo, uint32_t bhi, typename idx_qe<C16>::type *lq, int &lqn, uint32_t lt)
+{
+    typedef idx_qe<C16> QE;
+    const bool lng = have && QE::lng(e);
+    const uint32_t lm = __ballot_sync(0xFFFFFFFFu, lng);
+    if (lm && lqn + __popc(lm) <= GKM_IDX_LQCAP) {
+        if (lng) lq[lqn + __popc(lm & lt)] = e;
+        lqn += __popc(lm);
+        have = have && !lng;
+    }
+    if (have) idx_walk_own<WEIGHTED, RANGE, C16>(r, QE::ofs(e), lng, Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e));
+}
+
+/* Probes of the masks [t_begin, t_end) into the HOT bins (shared memory H; bin row 0 of H holds m = mbase).
  * Same tiling as above, GKM_IDX_UNROLL independent slot loads in flight per thread.  Every lane of a warp runs the
  * same iterations (lanes without work probe with an empty column range), so that the overflow lists can be handled
  * at warp level: a lane that meets a list of five or more postings does NOT walk it on the spot -- one walking lane
  * would stall the other 31 behind a dependent load in divergent code, and nearly every warp probe has one -- but
  * pushes (list, bin row, weight) on the warp's queue in shared memory; whenever 32 walks are queued the warp runs
- * them together, one list per lane. */
+ * them together (idx_drain). */
 template <bool WEIGHTED, bool RANGE, bool C16>
 __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
-                                              int nq, int32_t *H, int mbase, int ldh, uint32_t blo, uint32_t bhi, uint2 *queue)
+                                              int nq, int32_t *H, int mbase, int ldh, uint32_t blo, uint32_t bhi,
+                                              typename idx_qe<C16>::type *queue)
 {
+    typedef idx_qe<C16> QE;
     const int tid = (int) threadIdx.x, lane = tid & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const uint4 *__restrict__ tab = reinterpret_cast<const uint4 *>(r.tab);
     const uint2 *__restrict__ tab16 = reinterpret_cast<const uint2 *>(r.tab);
-    const uint32_t h0 = (uint32_t) __cvta_generic_to_shared(H);
-    int qn = 0; /* queued walks of this warp (warp-uniform) */
+    typename QE::type *lq = queue + GKM_IDX_QCAP; /* long queue of this warp */
+    int qn = 0, lqn = 0;                          /* queued walks of this warp (warp-uniform) */
     for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
         const int rem = min(GKM_IDX_THREADS, t_end - t0);
         int T = (rem + 31) & ~31;
@@ -396,29 +528,22 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
                 else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bh[u], w[u]);
                 const uint32_t mk = __ballot_sync(0xFFFFFFFFu, o != ~0u);
                 if (mk) {
-                    if (o != ~0u) queue[qn + __popc(mk & lt)] = make_uint2(o, (uint32_t) mrow | ((uint32_t) w[u] << 8));
+                    if (o != ~0u) queue[qn + __popc(mk & lt)] = QE::make(o, mrow, w[u]);
                     qn += __popc(mk);
                     if (qn >= 32) {
                         __syncwarp();
-                        const uint2 e = queue[qn - 32 + lane];
-                        int32_t *He = H + (size_t) (e.y & 0xFFu) * (size_t) ldh;
-                        if constexpr (C16) idx_walk16<RANGE>(r.ovf, e.x, He, blo, bhi);
-                        else idx_walk<WEIGHTED, RANGE>(r.ovf, e.x, He, blo, bhi, (int) (e.y >> 8));
+                        idx_drain<WEIGHTED, RANGE, C16>(r, queue[qn - 32 + lane], true, H, ldh, blo, bhi, lq, lqn, lt);
                         qn -= 32;
                         __syncwarp();
                     }
                 }
             }
+            if (lqn) { idx_long<WEIGHTED, RANGE, C16>(r, lq, lqn, H, ldh, blo, bhi, lane); lqn = 0; }
         }
     }
     __syncwarp();
-    if (lane < qn) {
-        const uint2 e = queue[lane];
-        int32_t *He = H + (size_t) (e.y & 0xFFu) * (size_t) ldh;
-        if constexpr (C16) idx_walk16<RANGE>(r.ovf, e.x, He, blo, bhi);
-        else idx_walk<WEIGHTED, RANGE>(r.ovf, e.x, He, blo, bhi, (int) (e.y >> 8));
-    }
-    (void) h0;
+    idx_drain<WEIGHTED, RANGE, C16>(r, lane < qn ? queue[lane] : QE::none(), lane < qn, H, ldh, blo, bhi, lq, lqn, lt);
+    if (lqn) idx_long<WEIGHTED, RANGE, C16>(r, lq, lqn, H, ldh, blo, bhi, lane);
 }
 
 template <bool WEIGHTED, bool RANGE, bool C16, int MINB>
@@ -441,8 +566,11 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     const int ldh = r.ldh;
     int32_t *H = reinterpret_cast<int32_t *>(smem);                       /* bins ncoldb .. nb-1 */
     int32_t *C = r.cold + (size_t) blockIdx.x * (size_t) ncoldb * (size_t) ldh; /* bins 0 .. ncoldb-1, this row's scratch */
-    uint2 *queue = reinterpret_cast<uint2 *>(smem + (size_t) nhot * (size_t) ldh * 4) + (size_t) (tid >> 5) * GKM_IDX_QCAP; /* this warp's */
-    uint32_t *xq = reinterpret_cast<uint32_t *>(smem + (size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES);
+    typedef typename idx_qe<C16>::type qe_t;
+    unsigned char *qbase = smem + (size_t) nhot * (size_t) ldh * 4;
+    qe_t *queue = reinterpret_cast<qe_t *>(qbase) + (size_t) (tid >> 5) * (GKM_IDX_QCAP + GKM_IDX_LQCAP); /* this warp's */
+    int *lqcnt = reinterpret_cast<int *>(qbase + GKM_IDX_QBYTES_FMT(C16)) - GKM_IDX_THREADS / 32 + (tid >> 5); /* cold phase only */
+    uint32_t *xq = reinterpret_cast<uint32_t *>(qbase + GKM_IDX_QBYTES_FMT(C16));
     uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
 
     const int ncol = (int) (bhi - blo);
@@ -450,6 +578,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
         for (int i = tid; i < ncol; i += GKM_IDX_THREADS) H[m * ldh + i] = 0;
     for (int m = 0; m < ncoldb; m++)
         for (int i = tid; i < ncol; i += GKM_IDX_THREADS) __stcg(C + (size_t) m * ldh + i, 0);
+    if ((tid & 31) == 0) *lqcnt = 0;
     /* forward L-mers of the query (window ending at e, L-1 <= e < len) */
     const int len = p.lens[a], nq = len - L + 1;
     {
@@ -462,7 +591,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
     __syncthreads();
 
-    if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, C16>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi);
+    if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, C16>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi, queue + GKM_IDX_QCAP, lqcnt);
     idx_probe_hot<WEIGHTED, RANGE, C16>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
     __syncthreads();
 
@@ -502,10 +631,10 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
 }
 
-unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted)
+unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted, int c16)
 {
     const int nhot = nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS;
-    size_t s = (size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
+    size_t s = (size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES_FMT(c16) + (size_t) maxq * 4 + (weighted ? (size_t) maxq : 0);
     return (unsigned) ((s + 15) & ~(size_t) 15);
 }
 
@@ -517,7 +646,7 @@ size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows)
 
 int gkm_idx_max_cols(int nbins, int maxq, int weighted)
 {
-    const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - GKM_IDX_QBYTES - (long long) maxq * (weighted ? 5 : 4);
+    const long long budget = 227LL * 1024 - 1024 /* static reduction buffer and slack */ - GKM_IDX_QBYTES_FMT(0) - (long long) maxq * (weighted ? 5 : 4);
     long long cols = budget / (4LL * (nbins < GKM_IDX_HOT_BINS ? nbins : GKM_IDX_HOT_BINS));
     cols &= ~31LL;
     if (cols > (long long) GKM_IDX_MAX_COLS) cols = GKM_IDX_MAX_COLS & ~31;
@@ -529,13 +658,14 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
     const int rows = kp->row_end - kp->row_begin;
     if (rows <= 0 || ra->bhi <= ra->blo) return 0;
     const bool range = ra->blo != 0;
-    const unsigned smem = gkm_idx_row_smem(kp->nbins, ra->ldh, ra->maxq, weighted);
+    const int c16 = ra->fmt == GKM_IDX_FMT_C16;
+    const unsigned smem = gkm_idx_row_smem(kp->nbins, ra->ldh, ra->maxq, weighted, c16);
     /* Two CTAs per SM where two full histogram rows of the block fit shared memory (blocks up to ~12 000 columns):
      * that build is held to 32 registers, which the compact-slot code meets without spills (41.0 instead of 46.1 ms
      * at 10k).  The decision is per block, not per launch: mixing the two builds inside one problem measured
      * slower (28 288 sequences: 272 ms against 228 ms), and the 16-byte-slot code spills at 32 registers
      * (wgkm at 10k: 70 ms against 49 ms), so the weighted types always run one CTA per SM. */
-    bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted) + 1280u) <= 227u * 1024u;
+    bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted, c16) + 1280u) <= 227u * 1024u;
     { const char *e = getenv("GKM_IDX_MINB"); if (e) two = atoi(e) == 2; } /* A/B knob */
     const void *fn;
     if (ra->fmt == GKM_IDX_FMT_C16) {

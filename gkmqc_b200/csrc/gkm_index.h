@@ -51,6 +51,16 @@ extern "C" {
 #define GKM_IDX_FMT_C16 1
 #define GKM_IDX_C16_NONE 0xFFFFu
 #define GKM_IDX_C16_MAX_COLS 0x7FFF
+/* long lists (repeats, homopolymers): an overflow list of GKM_IDX_LONG_UNITS or more 16-byte units is not walked by
+ * the lane that met it (one dependent load per unit: a 20 000-posting poly-A list cost that lane ~1 ms, and every
+ * third random row meets it) but by its whole warp, a unit per lane.  Such a list starts with a 16-byte header
+ * {number of units, 0, 0, 0} and its slot pointer carries GKM_IDX_LONG (lists are 16-byte aligned, so the low
+ * bits of the offset are free). */
+#define GKM_IDX_LONG 1u
+#define GKM_IDX_LONG_UNITS 8u
+/* units (16 bytes = 8 columns / 4 postings) of the overflow part of a list of `len` postings, end marker included */
+#define GKM_IDX_C16_UNITS(len) ((((len) - 2u + 8u) & ~7u) >> 3)
+#define GKM_IDX_P32_UNITS(len) ((((len) - 3u + 4u) & ~3u) >> 2)
 #define GKM_IDX_HOT_BINS 2            /* bins d and d-1 (99 % of the hits) live in shared memory, the others in L2 */
 
 #if defined(__CUDACC__)

@@ -48,7 +48,7 @@ size_t gkm_idx_scratch_bytes(size_t P, int L, size_t *cub_bytes_out);
 int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st);
 /* most columns one block may hold so that the hot histogram rows + the query fit 227 KB of shared memory (0: none) */
 int gkm_idx_max_cols(int nbins, int maxq, int weighted);
-unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted);
+unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted, int c16);
 /* bytes of cold-bin scratch a launch of `rows` rows needs */
 size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows);
 /* rows [kp->row_begin, kp->row_end) against the wanted columns of one block; outputs as in gkm_kparams */

@@ -67,7 +67,9 @@ int gkmb200_problem_upload(gkmb200_problem *p);
 int gkmb200_problem_sqnorm(gkmb200_problem *p, double *out);                 /* n values */
 
 /* ---- the kernel ---- */
-/* triangular matrix into caller rows: rows[a][j] = K(a,j) for j<a, rows[a][a] = 1 (gkmkern_pylib.c:169-221) */
+/* triangular matrix into caller rows: rows[a][j] = K(a,j) for j<a, rows[a][a] = 1 (gkmkern_pylib.c:169-221).
+ * copy_threads is a lower bound on the host threads that scatter finished chunks into the rows: the library uses
+ * the cores of its affinity mask, 16 at most (env GKM_COPY_THREADS overrides; gkm_device.cu:gkm_copy_threads) */
 int gkmb200_kernel_lower(gkmb200_problem *p, double **rows, int copy_threads);
 /* dense block: out[(r-row0)*ld + (c-col0)] = K(r,c).  lower != 0: only c < r is written (and r == c gets 1.0).
  * With the SVs at ids [0,nSV) this is gkmkernel_kernelfunc_batch_all(a, 0, nSV) for a whole batch of rows. */

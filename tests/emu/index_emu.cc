@@ -5,7 +5,7 @@
  *   keys   -> every valid window of both strands, coded by gkm_idx_code()         (gkm_idx_keys_kernel)
  *   sort   -> by (code, column)                                                    (cub radix sort)
  *   slots  -> {posting 0, 1, 2, posting 3 | pointer}, overflow lists padded to     (gkm_idx_runs_kernel,
- *             quads with end markers                                                gkm_idx_fill_kernel)
+ *             quads with end markers; long lists with a header unit and a flag      gkm_idx_fill_kernel)
  *   probes -> x ^ mask for every mask of gkm_idx_deltas(), postings walked with    (gkm_index_rows_kernel,
  *             the same sorted-list / end-marker rules                               idx_slot)
  * so that the code layout, the mask list, the slot encoding and the walk rules are checked against
@@ -72,6 +72,12 @@ static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
             while (ix.ovf16.size() & 7) ix.ovf16.push_back(GKM_IDX_C16_NONE); /* lists start on 16 bytes */
             s.v[0] = c[0] | ((uint32_t) c[1] << 16);
             s.v[1] = GKM_IDX_PTR | (uint32_t) ix.ovf16.size();
+            const uint32_t units = GKM_IDX_C16_UNITS((uint32_t) len);
+            if (units >= GKM_IDX_LONG_UNITS) { /* long list: header unit {units, 0, 0, 0}, flag in the pointer */
+                s.v[1] |= GKM_IDX_LONG;
+                ix.ovf16.push_back((uint16_t) (units & 0xFFFFu)); ix.ovf16.push_back((uint16_t) (units >> 16));
+                for (int t = 0; t < 6; t++) ix.ovf16.push_back(0);
+            }
             for (size_t r = 2; r < len; r++) ix.ovf16.push_back((uint16_t) ((keys[i + r] >> 8) & 0x7FFFu));
             ix.ovf16.push_back(GKM_IDX_C16_NONE);
             while (ix.ovf16.size() & 7) ix.ovf16.push_back(GKM_IDX_C16_NONE);
@@ -93,6 +99,11 @@ static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
                 if (r == 3) {
                     while (ix.ovf.size() & 3) ix.ovf.push_back(GKM_IDX_EMPTY); /* lists start on 16 bytes */
                     s.v[3] = GKM_IDX_PTR | (uint32_t) ix.ovf.size();
+                    const uint32_t units = GKM_IDX_P32_UNITS((uint32_t) len);
+                    if (units >= GKM_IDX_LONG_UNITS) {
+                        s.v[3] |= GKM_IDX_LONG;
+                        ix.ovf.push_back(units); ix.ovf.push_back(0); ix.ovf.push_back(0); ix.ovf.push_back(0);
+                    }
                 }
                 ix.ovf.push_back(posting);
             }
@@ -140,6 +151,16 @@ static void probe_row(const gkmb200_problem *p, const emu_index &ix, const std::
                 if (!(sl[1] & GKM_IDX_PTR) || c3 == GKM_IDX_C16_NONE) {
                     hit16(H, nb, m, sl[1] & 0xFFFFu, blo, bhi);
                     hit16(H, nb, m, c3, blo, bhi);
+                } else if (c1 < bhi && (sl[1] & GKM_IDX_LONG)) {
+                    /* long list (idx_walk_long): `units` units behind the header; a unit whose first column is
+                     * behind the range ends the walk of the lane that owns it -- every later unit is behind it too */
+                    const uint16_t *q = ix.ovf16.data() + (sl[1] & ~(GKM_IDX_PTR | GKM_IDX_LONG));
+                    const uint32_t units = q[0] | ((uint32_t) q[1] << 16);
+                    for (uint32_t u = 0; u < units; u++) {
+                        const uint16_t *v = q + 8 + 8 * (size_t) u;
+                        if (v[0] >= bhi) continue;
+                        for (int t = 0; t < 8; t++) hit16(H, nb, m, v[t], blo, bhi);
+                    }
                 } else if (c1 < bhi) {
                     const uint16_t *q = ix.ovf16.data() + (sl[1] & ~GKM_IDX_PTR);
                     for (;;) {
@@ -154,6 +175,15 @@ static void probe_row(const gkmb200_problem *p, const emu_index &ix, const std::
             hit(H, nb, m, sl[1], blo, bhi, w);
             hit(H, nb, m, sl[2], blo, bhi, w);
             if (!(sl[3] & GKM_IDX_PTR)) hit(H, nb, m, sl[3], blo, bhi, w);
+            else if (sl[3] != GKM_IDX_EMPTY && (sl[2] & GKM_IDX_COL_MASK) < bhi && (sl[3] & GKM_IDX_LONG)) {
+                const uint32_t *q = ix.ovf.data() + (sl[3] & ~(GKM_IDX_PTR | GKM_IDX_LONG));
+                const uint32_t units = q[0];
+                for (uint32_t u = 0; u < units; u++) {
+                    const uint32_t *v = q + 4 + 4 * (size_t) u;
+                    if ((v[0] & GKM_IDX_COL_MASK) >= bhi) continue;
+                    for (int t = 0; t < 4; t++) hit(H, nb, m, v[t], blo, bhi, w);
+                }
+            }
             else if (sl[3] != GKM_IDX_EMPTY && (sl[2] & GKM_IDX_COL_MASK) < bhi) {
                 const uint32_t *q = ix.ovf.data() + (sl[3] & ~GKM_IDX_PTR);
                 for (;;) {

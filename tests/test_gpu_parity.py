@@ -123,7 +123,10 @@ def test_seeded_against_oracle(kernel_type, L, k, d, length, ragged, variant):
 
 
 @pytest.mark.parametrize("kernel_type,L,k,d,cols,wide", [(2, 11, 7, 3, 32, 0), (4, 10, 6, 3, 64, 0), (2, 8, 4, 4, 32, 0), (4, 6, 5, 1, 32, 0),
-                                                          (0, 9, 9, 0, 32, 0), (2, 8, 4, 4, 32, 1), (2, 11, 7, 3, 0, 1), (1, 7, 4, 3, 0, 0)])
+                                                          (0, 9, 9, 0, 32, 0), (2, 8, 4, 4, 32, 1), (2, 11, 7, 3, 0, 1), (1, 7, 4, 3, 0, 0),
+                                                          # nearly every slot holds a LONG list (whole-warp walks, and more than 32 of
+                                                          # them per probe iteration: the long queue overflows into per-lane walks)
+                                                          (4, 5, 4, 1, 0, 0), (2, 4, 3, 1, 0, 0), (2, 4, 3, 1, 64, 0), (2, 5, 3, 2, 0, 1)])
 def test_index_column_blocks(kernel_type, L, k, d, cols, wide):
     """index variant with the columns cut into several index blocks (what a problem larger than one
     shared-memory histogram row gets), long posting lists (short L, repeats) and a column window that
@@ -157,6 +160,36 @@ def test_index_column_blocks(kernel_type, L, k, d, cols, wide):
     finally:
         capi.set_option("index_cols", "0")
         capi.set_option("index_wide", "0")
+        capi.set_option("kernel", "auto")
+
+
+@pytest.mark.parametrize("kernel_type", [2, 4])
+def test_nonuniform_index_vs_bitsliced(kernel_type):
+    """genome-like inputs (poly-A tracts, dinucleotide repeats, a repeat family, exact duplicates,
+    AT-rich composition) put thousands of postings into a few slots.  The index kernel (neighbour enumeration, long
+    lists walked by whole warps) and the bit-sliced kernel (dense diagonals) are independent constructions: their
+    integer histograms and kernel doubles must agree bit for bit."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("nonuniform", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "nonuniform.py"))
+    nu = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nu)
+    n, L, k, d = 1500, 11, 7, 3
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    try:
+        for name, x in nu.workloads(n, seed=99).items():
+            if name in ("uniform", "at_rich"):
+                continue
+            seqs = [acgt[r].tobytes().decode() for r in x]
+            out = {}
+            for v in ("index", "diag"):
+                capi.set_option("kernel", v)
+                with capi.Problem(kernel_type, L, k, d, 50, 50.0, 1.0) as P:
+                    P.add_many(seqs)
+                    out[v] = (P.hist_block(n - 200, 200, 0, n - 200), P.kernel_block(n - 200, 200, 0, n - 200), P.stats()["kernel_variant"])
+            assert out["index"][2] == 4 and out["diag"][2] == 2
+            assert np.array_equal(out["index"][0], out["diag"][0]), name
+            assert np.array_equal(out["index"][1], out["diag"][1]), name
+    finally:
         capi.set_option("kernel", "auto")
 
 

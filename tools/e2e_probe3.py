@@ -12,7 +12,7 @@ capi.load()
 for it in range(10):
     kmat = np.zeros((n, n))
     t0 = time.perf_counter()
-    ret, kmat, a, b = capi.main_pywrapper(pos, neg, kernel_type=2, L=11, k=7, d=3, nthreads=8, verbosity=2, kmat=kmat)
+    ret, kmat, a, b = capi.main_pywrapper(pos, neg, kernel_type=2, L=11, k=7, d=3, nthreads=8, verbosity=int(os.environ.get("V","2")), kmat=kmat)
     t1 = time.perf_counter()
     sys.stdout.flush()
     print("CALL %d: %.1f ms" % (it, 1e3 * (t1 - t0)), flush=True)
