@@ -299,7 +299,7 @@ def main():
         dist_barrier(dist)
         t0 = time.perf_counter()
         # nthreads is gkmQC's own default (bin/gkmqc.py:107,162: 1); the library sizes its copy-out threads by the host's cores
-        ret, kmat, npos, nneg = capi.main_pywrapper(pos, neg, kernel_type=KTYPE, L=L, k=K, d=D, nthreads=1, verbosity=0, kmat=kmat)
+        ret, kmat, npos, nneg = capi.main_pywrapper(pos, neg, kernel_type=KTYPE, L=L, k=K, d=D, nthreads=1, verbosity=int(os.environ.get("GKM_BENCH_V", "0")), kmat=kmat)
         t1 = time.perf_counter()
         if ret != 0:
             raise SystemExit("gkm_main_pywrapper failed: " + capi.last_error())

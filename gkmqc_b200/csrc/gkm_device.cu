@@ -253,6 +253,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
         ra.cb = b->cb; ra.blo = lo - b->cb; ra.bhi = hi - b->cb;
         ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
         ra.blk_cols = b->ce - b->cb;
+        ra.nblk = im->nblk;
         ra.maxq = 32 * p->Wa;
         ra.ncold = g->ncold;
         {   /* cold-bin scratch of this stream, grown on demand (the stream is drained before a block is replaced) */
@@ -391,6 +392,7 @@ static int index_block_cap(const gkmb200_problem *p)
      * overflow walks cost more than probing a second block does (measured: 6.0 us per row at 14k columns in one
      * block, 10.9 us at 20k in one block against 7.5 us in two) */
     if (cap > 16384) cap = 16384;
+    if (p->weighted && cap > GKM_IDX_W20_MAX_COLS) cap = GKM_IDX_W20_MAX_COLS; /* 14-bit columns of the compact weighted slots */
     const int opt = gkm_opt_index_cols();
     if (opt > 0 && opt < cap) cap = opt;
     return cap;
@@ -467,7 +469,14 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
         void *scratch = NULL, *d_offs = NULL;
         size_t scratch_got = 0, offs_got = 0;
         /* unit-weight kernel types get the compact 16-bit slots (a block never holds more than 16384 columns) */
-        b->fmt = (!p->weighted && nc <= GKM_IDX_C16_MAX_COLS && !gkm_opt_index_wide()) ? GKM_IDX_FMT_C16 : GKM_IDX_FMT_P32;
+        b->fmt = GKM_IDX_FMT_P32;
+        if (!gkm_opt_index_wide()) {
+            if (!p->weighted && nc <= GKM_IDX_C16_MAX_COLS) b->fmt = GKM_IDX_FMT_C16;
+            /* weighted types: 8-byte slots of three 20-bit postings where weights, columns and the overflow offsets fit
+             * (worst case 4/3 overflow entries per posting + padding) */
+            if (p->weighted && nc <= GKM_IDX_W20_MAX_COLS && p->param.M <= GKM_IDX_W20_MAX_WEIGHT &&
+                (4 * P) / 3 + 64 < 4 * (size_t) GKM_IDX_W20_MAX_UNITS) b->fmt = GKM_IDX_FMT_W20;
+        }
         int rc = pool_alloc(g, (void **) &b->tab, &b->tab_bytes, gkm_idx_tab_bytes(L, b->fmt)) ||
                  pool_alloc(g, (void **) &b->ovf, &b->ovf_bytes, gkm_idx_ovf_bytes(P, b->fmt)) ||
                  pool_alloc(g, &scratch, &scratch_got, sbytes) ||
@@ -684,24 +693,88 @@ static void *scatter_worker(void *arg)
     return NULL;
 }
 
-static void scatter_chunk(const gkm_job *job, const gkm_chunk *c, const double *src)
-{
-    int nt = job->copy_threads;
-    if (nt < 1) nt = 1;
-    if (nt > 64) nt = 64;
-    if (nt > c->row_end - c->row_begin) nt = c->row_end - c->row_begin;
+/* The scatter team of one device thread: created once per compute call and joined before it returns (no thread of
+ * the library outlives gkm_main_pywrapper).  One pthread_create per helper and CHUNK was 0.5 ms of
+ * pure overhead per chunk with 16 threads (25-35 chunks per call: a third of the time spent "scattering"). */
+struct gkm_team {
+    pthread_mutex_t mu;
+    pthread_cond_t work, done;
+    int nthreads;          /* helpers + the device thread itself */
+    int gen, pending, quit;
+    gkm_scatter task;      /* job, chunk, source of the generation in progress (t is per helper) */
     pthread_t th[64];
-    gkm_scatter sc[64];
     int started[64];
-    for (int t = 0; t < nt; t++) {
-        sc[t].job = job; sc[t].c = c; sc[t].src = src; sc[t].t = t; sc[t].nt = nt;
-        started[t] = 0;
-        if (t > 0) started[t] = (pthread_create(&th[t], NULL, scatter_worker, &sc[t]) == 0);
+    struct gkm_team_arg { gkm_team *team; int t; } arg[64];
+};
+
+static void *team_worker(void *a)
+{
+    gkm_team *tm = ((gkm_team::gkm_team_arg *) a)->team;
+    const int t = ((gkm_team::gkm_team_arg *) a)->t;
+    int seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&tm->mu);
+        while (tm->gen == seen && !tm->quit) pthread_cond_wait(&tm->work, &tm->mu);
+        if (tm->quit) { pthread_mutex_unlock(&tm->mu); return NULL; }
+        seen = tm->gen;
+        gkm_scatter sc = tm->task;
+        pthread_mutex_unlock(&tm->mu);
+        sc.t = t;
+        if (t < sc.nt) scatter_worker(&sc);
+        pthread_mutex_lock(&tm->mu);
+        if (--tm->pending == 0) pthread_cond_signal(&tm->done);
+        pthread_mutex_unlock(&tm->mu);
     }
-    scatter_worker(&sc[0]);
-    for (int t = 1; t < nt; t++) {
-        if (started[t]) pthread_join(th[t], NULL);
-        else scatter_worker(&sc[t]); /* like the reference: run the share inline if the thread could not start */
+}
+
+static void team_start(gkm_team *tm, int nthreads)
+{
+    memset(tm, 0, sizeof(*tm));
+    pthread_mutex_init(&tm->mu, NULL);
+    pthread_cond_init(&tm->work, NULL);
+    pthread_cond_init(&tm->done, NULL);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    tm->nthreads = 1;
+    for (int t = 1; t < nthreads; t++) {
+        tm->arg[t].team = tm; tm->arg[t].t = tm->nthreads;
+        tm->started[t] = (pthread_create(&tm->th[t], NULL, team_worker, &tm->arg[t]) == 0);
+        if (tm->started[t]) tm->nthreads++; /* like the reference: a thread that cannot start just is not there */
+    }
+}
+
+static void team_stop(gkm_team *tm)
+{
+    pthread_mutex_lock(&tm->mu);
+    tm->quit = 1;
+    pthread_cond_broadcast(&tm->work);
+    pthread_mutex_unlock(&tm->mu);
+    for (int t = 1; t < 64; t++) if (tm->started[t]) pthread_join(tm->th[t], NULL);
+    pthread_cond_destroy(&tm->work);
+    pthread_cond_destroy(&tm->done);
+    pthread_mutex_destroy(&tm->mu);
+}
+
+static void scatter_chunk(gkm_team *tm, const gkm_job *job, const gkm_chunk *c, const double *src)
+{
+    int nt = tm->nthreads;
+    if (nt > c->row_end - c->row_begin) nt = c->row_end - c->row_begin;
+    if (nt < 1) nt = 1;
+    gkm_scatter sc;
+    sc.job = job; sc.c = c; sc.src = src; sc.t = 0; sc.nt = nt;
+    if (nt > 1) {
+        pthread_mutex_lock(&tm->mu);
+        tm->task = sc;
+        tm->pending = tm->nthreads - 1;
+        tm->gen++;
+        pthread_cond_broadcast(&tm->work);
+        pthread_mutex_unlock(&tm->mu);
+    }
+    scatter_worker(&sc);
+    if (nt > 1) {
+        pthread_mutex_lock(&tm->mu);
+        while (tm->pending > 0) pthread_cond_wait(&tm->done, &tm->mu);
+        pthread_mutex_unlock(&tm->mu);
     }
 }
 
@@ -742,7 +815,7 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     return 0;
 }
 
-static int dev_thread_body(gkm_devthread *dt)
+static int dev_thread_run(gkm_devthread *dt, gkm_team *team_p)
 {
     gkm_job *job = dt->job;
     gkmb200_problem *p = job->p;
@@ -757,6 +830,7 @@ static int dev_thread_body(gkm_devthread *dt)
         if (cells * 4 * (size_t) p->nbins > maxhist) maxhist = cells * 4 * (size_t) p->nbins;
     }
     if (gpu_prepare(g, ds->dev[dt->slot], maxbytes, maxbytes)) return 1;
+    gkm_team &team = *team_p;
     int32_t *d_hist = NULL, *h_hist = NULL;
     if (job->hist) {
         CK(cudaMalloc(&d_hist, maxhist ? maxhist : 4));
@@ -795,7 +869,7 @@ static int dev_thread_body(gkm_devthread *dt)
         if (cudaEventElapsedTime(&ms, g->span0, g->k1[s]) == cudaSuccess && ms > dt->kernel_ms) dt->kernel_ms = ms;
         t_lastsync = now_ms();
         t_wait += t_lastsync - tw0;
-        if (job->out || job->rows) scatter_chunk(job, c, (const double *) g->h_stage[s]);
+        if (job->out || job->rows) scatter_chunk(&team, job, c, (const double *) g->h_stage[s]);
         t_scatter += now_ms() - t_lastsync;
         if (job->hist) {
             const int width = c->col_end - c->col_begin, nb = p->nbins;
@@ -831,6 +905,15 @@ static int dev_thread_body(gkm_devthread *dt)
     if (rc) cudaDeviceSynchronize();
     if (d_hist) cudaFree(d_hist);
     free(h_hist);
+    return rc;
+}
+
+static int dev_thread_body(gkm_devthread *dt)
+{
+    gkm_team team;
+    team_start(&team, (dt->job->out || dt->job->rows) ? dt->job->copy_threads : 1);
+    const int rc = dev_thread_run(dt, &team);
+    team_stop(&team);
     return rc;
 }
 

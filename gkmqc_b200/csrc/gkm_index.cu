@@ -30,6 +30,16 @@
 #endif
 #define GKM_IDX_QCAP 64 /* queued overflow walks per warp: < 32 waiting + <= 32 new */
 #define GKM_IDX_LQCAP 32 /* long lists waiting for a whole-warp walk, per warp */
+/* Problems of several column blocks run two CTAs per SM only while both fit the 196 KB step of the L1/shared split
+ * (blocks up to ~10 700 columns): beyond it L1 shrinks to 28 KB, and the two-CTA build then measured 2x SLOWER than
+ * one CTA per SM (50k x 50k, 4 blocks of 12 512 columns: 1 300-1 590 ms against 704 ms).  A single block profits from
+ * two CTAs up to the 227 KB limit (12 000 columns: 54.9 against 59.6 ms). */
+#ifndef GKM_IDX_TWO_SMEM
+#define GKM_IDX_TWO_SMEM (196u * 1024u)
+#endif
+#ifndef GKM_IDX_W20_TWO
+#define GKM_IDX_W20_TWO 1 /* weighted compact slots: two CTAs per SM where the histogram rows fit (A/B: 0) */
+#endif
 /* queue entry: (list, bin row, weight).  Compact slots: 4 bytes; 16-byte slots: 8 bytes.  The queues are kept small on
  * purpose: at 10 000 columns two CTAs per SM need 2 x (80 KB histogram + queues + query) of shared memory, and
  * every KB beyond 196 KB per SM moves the L1/shared split to its last step (28 KB of L1 instead of 60), which
@@ -112,6 +122,9 @@ gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int
     if (fmt == GKM_IDX_FMT_C16) {
         const uint32_t units = (len >= 5) ? GKM_IDX_C16_UNITS(len) : 0u;
         need[i] = 8u * (units + (units >= GKM_IDX_LONG_UNITS ? 1u : 0u)); /* long lists carry a header unit */
+    } else if (fmt == GKM_IDX_FMT_W20) {
+        const uint32_t units = (len >= 4) ? GKM_IDX_W20_UNITS(len) : 0u;
+        need[i] = 4u * (units + (units >= GKM_IDX_LONG_UNITS ? 1u : 0u));
     } else {
         const uint32_t units = (len >= 5) ? GKM_IDX_P32_UNITS(len) : 0u;
         need[i] = 4u * (units + (units >= GKM_IDX_LONG_UNITS ? 1u : 0u));
@@ -199,7 +212,54 @@ gkm_idx_fill_c16_kernel(const unsigned long long *__restrict__ keys, uint32_t P,
     }
 }
 
-size_t gkm_idx_tab_bytes(int L, int fmt) { return ((size_t) 1 << (2 * L)) * (fmt == GKM_IDX_FMT_C16 ? sizeof(uint2) : sizeof(uint4)); }
+/* W20: the three 20-bit fields of a slot are written by three different threads into two shared 32-bit words that
+ * start as all ones: each thread ANDs its own bits in */
+__global__ void __launch_bounds__(256)
+gkm_idx_fill_w20_kernel(const unsigned long long *__restrict__ keys, uint32_t P, const uint32_t *__restrict__ runlen,
+                        const uint32_t *__restrict__ ovfofs, uint2 *__restrict__ tab, uint32_t *__restrict__ ovf)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const unsigned long long key = keys[i];
+    const uint32_t code = (uint32_t) (key >> 32);
+    uint32_t lb = i;
+    if (runlen[i] == 0) {
+        uint32_t hi = i, lo = 0, step = 1;
+        for (;;) {
+            if (hi < step) { lo = 0; break; }
+            const uint32_t probe = hi - step;
+            if ((uint32_t) (keys[probe] >> 32) != code) { lo = probe + 1; break; }
+            hi = probe;
+            step <<= 1;
+        }
+        lb = idx_lower(keys, lo, hi, code);
+    }
+    const uint32_t len = runlen[lb], r = i - lb;
+    const uint32_t col = (uint32_t) (key >> 8) & GKM_IDX_W20_COL_MASK, wt = (uint32_t) key & 0xFFu;
+    const uint32_t p20 = col | (wt << GKM_IDX_W20_COL_BITS);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(tab + code);
+    const uint32_t units = (len >= 4) ? GKM_IDX_W20_UNITS(len) : 0u;
+    const bool lng = units >= GKM_IDX_LONG_UNITS;
+    const uint32_t data = ovfofs[lb] + (lng ? 4u : 0u); /* behind the header unit */
+    if (r == 0) {
+        atomicAnd(slot, p20 | ~0xFFFFFu);
+        if (len <= 3) atomicAnd(slot + 1, ~GKM_IDX_PTR);
+        else {
+            atomicAnd(slot + 1, GKM_IDX_PTR | ((ovfofs[lb] >> 2) << 9) | (lng ? (GKM_IDX_LONG << 8) : 0u) | 0xFFu);
+            if (lng) { ovf[ovfofs[lb]] = units; ovf[ovfofs[lb] + 1] = 0; ovf[ovfofs[lb] + 2] = 0; ovf[ovfofs[lb] + 3] = 0; }
+            for (uint32_t t = len - 2; t < 4u * units; t++) ovf[data + t] = GKM_IDX_EMPTY;
+        }
+    } else if (r == 1) {
+        atomicAnd(slot, (p20 << 20) | 0xFFFFFu);
+        atomicAnd(slot + 1, (p20 >> 12) | ~0xFFu);
+    } else if (len == 3) {
+        atomicAnd(slot + 1, (p20 << 8) | ~(0xFFFFFu << 8));
+    } else {
+        ovf[data + r - 2] = gkm_idx_posting(col, wt);
+    }
+}
+
+size_t gkm_idx_tab_bytes(int L, int fmt) { return ((size_t) 1 << (2 * L)) * (fmt == GKM_IDX_FMT_P32 ? sizeof(uint4) : sizeof(uint2)); }
 
 /* overflow demand is at most 2 entries per posting in either format (header unit of the long lists included) */
 size_t gkm_idx_ovf_bytes(size_t P, int fmt) { return (2 * P + 16) * (fmt == GKM_IDX_FMT_C16 ? 2 : 4); }
@@ -242,6 +302,7 @@ int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st)
         cub_bytes = a->cub_bytes;
         if ((e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, need, ovfofs, (int) P, st)) != cudaSuccess) goto fail;
         if (a->fmt == GKM_IDX_FMT_C16) gkm_idx_fill_c16_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, (uint2 *) a->tab, (uint16_t *) a->ovf);
+        else if (a->fmt == GKM_IDX_FMT_W20) gkm_idx_fill_w20_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, (uint2 *) a->tab, a->ovf);
         else gkm_idx_fill_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, runlen, ovfofs, (uint4 *) a->tab, a->ovf);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) goto fail;
@@ -329,12 +390,33 @@ __device__ __forceinline__ void idx_walk16(const uint32_t *__restrict__ ovf, uin
     }
 }
 
+/* ---- compact slots with weights (GKM_IDX_FMT_W20): three 20-bit postings (column : 14 | weight : 6) in 8 bytes ----
+ * x = p0 | p1 << 20, y = p1 >> 12 | p2 << 8 | flags << 28.  Four or more postings: p0 and p1 inline, y bit 31 set, y bits
+ * 9..30 = offset of postings 2.. in the overflow array in 16-byte units (entries there are the 32-bit postings of the
+ * P32 format: the walks are shared), y bit 8 = GKM_IDX_LONG.  A column field of all ones (0x3FFF: blocks hold at most
+ * 16 352 columns) fails the range test; an empty slot is all ones and is told from a pointer by its first column. */
+template <bool RANGE>
+__device__ __forceinline__ uint32_t idx_slot20(const uint2 sl, int32_t *Hm, uint32_t blo, uint32_t bhi, int w)
+{
+    const uint32_t p0 = sl.x & 0xFFFFFu, p1 = (sl.x >> 20) | ((sl.y & 0xFFu) << 12);
+    const uint32_t c0 = p0 & GKM_IDX_W20_COL_MASK, c1 = p1 & GKM_IDX_W20_COL_MASK;
+    idx_red<RANGE>(Hm, c0, blo, bhi, w * (int) (p0 >> GKM_IDX_W20_COL_BITS));
+    idx_red<RANGE>(Hm, c1, blo, bhi, w * (int) (p1 >> GKM_IDX_W20_COL_BITS));
+    if (!(sl.y & GKM_IDX_PTR) || c0 == GKM_IDX_W20_COL_MASK) {
+        const uint32_t p2 = (sl.y >> 8) & 0xFFFFFu;
+        idx_red<RANGE>(Hm, p2 & GKM_IDX_W20_COL_MASK, blo, bhi, w * (int) (p2 >> GKM_IDX_W20_COL_BITS));
+        return ~0u;
+    }
+    return (c1 < bhi) ? ((((sl.y >> 9) & 0x3FFFFFu) << 2) | ((sl.y >> 8) & GKM_IDX_LONG)) : ~0u;
+}
+
 /* A long list (GKM_IDX_LONG), walked by the whole warp: lane l takes the units l, l + 32, ...  Equal columns are
  * adjacent in a list (a column with a repeat owns a run of postings): each lane folds the runs inside its unit
  * before it touches the histogram, so a homopolymer costs one atomic per unit instead of eight on one address. */
-template <bool WEIGHTED, bool RANGE, bool C16>
+template <bool WEIGHTED, bool RANGE, int FMT>
 __device__ __forceinline__ void idx_walk_long(const uint32_t *__restrict__ ovf, uint32_t ofs, int32_t *Hm, uint32_t blo, uint32_t bhi, int w, int lane)
 {
+    constexpr bool C16 = FMT == GKM_IDX_FMT_C16;
     const uint4 *q = C16 ? reinterpret_cast<const uint4 *>(reinterpret_cast<const uint16_t *>(ovf) + ofs)
                          : reinterpret_cast<const uint4 *>(ovf + ofs);
     const uint32_t units = __ldg(q).x;
@@ -390,23 +472,23 @@ template <> struct idx_qe<false> {
 };
 
 /* one list by the lane that owns the entry; a long one from behind its header unit */
-template <bool WEIGHTED, bool RANGE, bool C16>
+template <bool WEIGHTED, bool RANGE, int FMT>
 __device__ __forceinline__ void idx_walk_own(const gkm_idx_rowargs &r, uint32_t ofs, bool lng, int32_t *He, uint32_t blo, uint32_t bhi, int w)
 {
-    if constexpr (C16) idx_walk16<RANGE>(r.ovf, ofs + (lng ? 8u : 0u), He, blo, bhi);
+    if constexpr (FMT == GKM_IDX_FMT_C16) idx_walk16<RANGE>(r.ovf, ofs + (lng ? 8u : 0u), He, blo, bhi);
     else idx_walk<WEIGHTED, RANGE>(r.ovf, ofs + (lng ? 4u : 0u), He, blo, bhi, w);
 }
 
 /* the long queue of a warp, one list after the other, each by all 32 lanes */
-template <bool WEIGHTED, bool RANGE, bool C16>
-__device__ __forceinline__ void idx_long(const gkm_idx_rowargs &r, const typename idx_qe<C16>::type *lq, int lqn, int32_t *Hb, int ldh,
+template <bool WEIGHTED, bool RANGE, int FMT>
+__device__ __forceinline__ void idx_long(const gkm_idx_rowargs &r, const typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *lq, int lqn, int32_t *Hb, int ldh,
                                          uint32_t blo, uint32_t bhi, int lane)
 {
-    typedef idx_qe<C16> QE;
+    typedef idx_qe<FMT == GKM_IDX_FMT_C16> QE;
     __syncwarp();
     for (int i = 0; i < lqn; i++) {
         const typename QE::type e = lq[i];
-        idx_walk_long<WEIGHTED, RANGE, C16>(r.ovf, QE::ofs(e), Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e), lane);
+        idx_walk_long<WEIGHTED, RANGE, FMT>(r.ovf, QE::ofs(e), Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e), lane);
     }
     __syncwarp();
 }
@@ -416,12 +498,12 @@ __device__ __forceinline__ void idx_long(const gkm_idx_rowargs &r, const typenam
  * A short tile is shared by several "phases" of threads that take interleaved query L-mers.  Overflow lists are
  * walked on the spot, except the long ones (these masks are where a repeat meets itself): a lane parks them in its
  * warp's long queue (shared counter, the lanes are divergent here) and the warp walks them together at the end. */
-template <bool WEIGHTED, bool RANGE, bool C16>
+template <bool WEIGHTED, bool RANGE, int FMT>
 __device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
                                                int nq, int32_t *C, int ldh, uint32_t blo, uint32_t bhi,
-                                               typename idx_qe<C16>::type *lq, int *lqcnt)
+                                               typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *lq, int *lqcnt)
 {
-    typedef idx_qe<C16> QE;
+    typedef idx_qe<FMT == GKM_IDX_FMT_C16> QE;
     const int tid = (int) threadIdx.x;
     for (int t0 = t_begin; t0 < t_end; t0 += GKM_IDX_THREADS) {
         const int rem = min(GKM_IDX_THREADS, t_end - t0);
@@ -438,19 +520,20 @@ __device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_b
             const uint32_t y = xq[xi] ^ dx;
             const int w = WEIGHTED ? (int) wq[xi] : 1;
             uint32_t o;
-            if constexpr (C16) o = idx_slot16<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi);
+            if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi);
+            else if constexpr (FMT == GKM_IDX_FMT_W20) o = idx_slot20<RANGE>(__ldg(reinterpret_cast<const uint2 *>(r.tab) + y), Hm, blo, bhi, w);
             else o = idx_slot<WEIGHTED, RANGE>(__ldg(reinterpret_cast<const uint4 *>(r.tab) + y), Hm, blo, bhi, w);
             if (o == ~0u) continue;
             if (o & GKM_IDX_LONG) {
                 const int pos = atomicAdd(lqcnt, 1);
                 if (pos < GKM_IDX_LQCAP) { lq[pos] = QE::make(o, mrow, w); continue; }
             }
-            idx_walk_own<WEIGHTED, RANGE, C16>(r, o & ~GKM_IDX_LONG, o & GKM_IDX_LONG, Hm, blo, bhi, w);
+            idx_walk_own<WEIGHTED, RANGE, FMT>(r, o & ~GKM_IDX_LONG, o & GKM_IDX_LONG, Hm, blo, bhi, w);
         }
     }
     __syncwarp();
     const int cnt = min(*lqcnt, GKM_IDX_LQCAP);
-    if (cnt) idx_long<WEIGHTED, RANGE, C16>(r, lq, cnt, C, ldh, blo, bhi, tid & 31);
+    if (cnt) idx_long<WEIGHTED, RANGE, FMT>(r, lq, cnt, C, ldh, blo, bhi, tid & 31);
 }
 
 /* the queued walks of a warp, one entry per lane that `have`s one.  Short lists: every lane walks its own.  Long
@@ -459,11 +542,11 @@ __device__ __forceinline__ void idx_probe_cold(const gkm_idx_rowargs &r, int t_b
  * body, their registers cost the 32-register build spills of exactly those slots (ptxas -v / SASS).  Should the
  * long queue be full, the list is walked like a short one: slow, but only reached by more than 32 long lists in
  * one iteration. */
-template <bool WEIGHTED, bool RANGE, bool C16>
-__device__ __forceinline__ void idx_drain(const gkm_idx_rowargs &r, typename idx_qe<C16>::type e, bool have, int32_t *Hb, int ldh,
-                                          uint32_t blo, uint32_t bhi, typename idx_qe<C16>::type *lq, int &lqn, uint32_t lt)
+template <bool WEIGHTED, bool RANGE, int FMT>
+__device__ __forceinline__ void idx_drain(const gkm_idx_rowargs &r, typename idx_qe<FMT == GKM_IDX_FMT_C16>::type e, bool have, int32_t *Hb, int ldh,
+                                          uint32_t blo, uint32_t bhi, typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *lq, int &lqn, uint32_t lt)
 {
-    typedef idx_qe<C16> QE;
+    typedef idx_qe<FMT == GKM_IDX_FMT_C16> QE;
     const bool lng = have && QE::lng(e);
     const uint32_t lm = __ballot_sync(0xFFFFFFFFu, lng);
     if (lm && lqn + __popc(lm) <= GKM_IDX_LQCAP) {
@@ -471,22 +554,22 @@ __device__ __forceinline__ void idx_drain(const gkm_idx_rowargs &r, typename idx
         lqn += __popc(lm);
         have = have && !lng;
     }
-    if (have) idx_walk_own<WEIGHTED, RANGE, C16>(r, QE::ofs(e), lng, Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e));
+    if (have) idx_walk_own<WEIGHTED, RANGE, FMT>(r, QE::ofs(e), lng, Hb + (size_t) QE::mrow(e) * (size_t) ldh, blo, bhi, QE::w(e));
 }
 
 /* Probes of the masks [t_begin, t_end) into the HOT bins (shared memory H; bin row 0 of H holds m = mbase).
- * Same tiling as above, GKM_IDX_UNROLL independent slot loads in flight per thread.  Every lane of a warp runs the
+ * Same tiling as above, UNR independent slot loads in flight per thread.  Every lane of a warp runs the
  * same iterations (lanes without work probe with an empty column range), so that the overflow lists can be handled
  * at warp level: a lane that meets a list of five or more postings does NOT walk it on the spot -- one walking lane
  * would stall the other 31 behind a dependent load in divergent code, and nearly every warp probe has one -- but
  * pushes (list, bin row, weight) on the warp's queue in shared memory; whenever 32 walks are queued the warp runs
  * them together (idx_drain). */
-template <bool WEIGHTED, bool RANGE, bool C16>
+template <bool WEIGHTED, bool RANGE, int FMT, int UNR>
 __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
                                               int nq, int32_t *H, int mbase, int ldh, uint32_t blo, uint32_t bhi,
-                                              typename idx_qe<C16>::type *queue)
+                                              typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *queue)
 {
-    typedef idx_qe<C16> QE;
+    typedef idx_qe<FMT == GKM_IDX_FMT_C16> QE;
     const int tid = (int) threadIdx.x, lane = tid & 31;
     const uint32_t lt = (1u << lane) - 1u;
     const uint4 *__restrict__ tab = reinterpret_cast<const uint4 *>(r.tab);
@@ -507,24 +590,25 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
         int32_t *Hm = H + (size_t) mrow * (size_t) ldh;
         const uint32_t bhi_l = lane_ok ? bhi : 0u; /* a lane without a mask never hits */
         const int n_it = (nq + nph - 1) / nph;     /* the same for every lane */
-        for (int it = 0; it < n_it; it += GKM_IDX_UNROLL) {
-            uint32_t bh[GKM_IDX_UNROLL];
-            int w[GKM_IDX_UNROLL];
-            uint4 sl[GKM_IDX_UNROLL];
-            uint2 sc[GKM_IDX_UNROLL];
+        for (int it = 0; it < n_it; it += UNR) {
+            uint32_t bh[UNR];
+            int w[UNR];
+            uint4 sl[UNR];
+            uint2 sc[UNR];
 #pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+            for (int u = 0; u < UNR; u++) {
                 const int xi = ph + (it + u) * nph;
                 const bool ok = (it + u < n_it) && xi < nq;
                 const uint32_t y = (ok ? xq[xi] : 0u) ^ dx;
                 bh[u] = ok ? bhi_l : 0u;
                 w[u] = (WEIGHTED && ok) ? (int) wq[xi] : 1;
-                if constexpr (C16) sc[u] = __ldg(tab16 + y); else sl[u] = __ldg(tab + y);
+                if constexpr (FMT != GKM_IDX_FMT_P32) sc[u] = __ldg(tab16 + y); else sl[u] = __ldg(tab + y);
             }
 #pragma unroll
-            for (int u = 0; u < GKM_IDX_UNROLL; u++) {
+            for (int u = 0; u < UNR; u++) {
                 uint32_t o;
-                if constexpr (C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bh[u]);
+                if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bh[u]);
+                else if constexpr (FMT == GKM_IDX_FMT_W20) o = idx_slot20<RANGE>(sc[u], Hm, blo, bh[u], w[u]);
                 else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bh[u], w[u]);
                 const uint32_t mk = __ballot_sync(0xFFFFFFFFu, o != ~0u);
                 if (mk) {
@@ -532,21 +616,21 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
                     qn += __popc(mk);
                     if (qn >= 32) {
                         __syncwarp();
-                        idx_drain<WEIGHTED, RANGE, C16>(r, queue[qn - 32 + lane], true, H, ldh, blo, bhi, lq, lqn, lt);
+                        idx_drain<WEIGHTED, RANGE, FMT>(r, queue[qn - 32 + lane], true, H, ldh, blo, bhi, lq, lqn, lt);
                         qn -= 32;
                         __syncwarp();
                     }
                 }
             }
-            if (lqn) { idx_long<WEIGHTED, RANGE, C16>(r, lq, lqn, H, ldh, blo, bhi, lane); lqn = 0; }
+            if (lqn) { idx_long<WEIGHTED, RANGE, FMT>(r, lq, lqn, H, ldh, blo, bhi, lane); lqn = 0; }
         }
     }
     __syncwarp();
-    idx_drain<WEIGHTED, RANGE, C16>(r, lane < qn ? queue[lane] : QE::none(), lane < qn, H, ldh, blo, bhi, lq, lqn, lt);
-    if (lqn) idx_long<WEIGHTED, RANGE, C16>(r, lq, lqn, H, ldh, blo, bhi, lane);
+    idx_drain<WEIGHTED, RANGE, FMT>(r, lane < qn ? queue[lane] : QE::none(), lane < qn, H, ldh, blo, bhi, lq, lqn, lt);
+    if (lqn) idx_long<WEIGHTED, RANGE, FMT>(r, lq, lqn, H, ldh, blo, bhi, lane);
 }
 
-template <bool WEIGHTED, bool RANGE, bool C16, int MINB>
+template <bool WEIGHTED, bool RANGE, int FMT, int MINB>
 __global__ void __launch_bounds__(GKM_IDX_THREADS, MINB)
 gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gkm_idx_rowargs r)
 {
@@ -566,11 +650,11 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     const int ldh = r.ldh;
     int32_t *H = reinterpret_cast<int32_t *>(smem);                       /* bins ncoldb .. nb-1 */
     int32_t *C = r.cold + (size_t) blockIdx.x * (size_t) ncoldb * (size_t) ldh; /* bins 0 .. ncoldb-1, this row's scratch */
-    typedef typename idx_qe<C16>::type qe_t;
+    typedef typename idx_qe<FMT == GKM_IDX_FMT_C16>::type qe_t;
     unsigned char *qbase = smem + (size_t) nhot * (size_t) ldh * 4;
     qe_t *queue = reinterpret_cast<qe_t *>(qbase) + (size_t) (tid >> 5) * (GKM_IDX_QCAP + GKM_IDX_LQCAP); /* this warp's */
-    int *lqcnt = reinterpret_cast<int *>(qbase + GKM_IDX_QBYTES_FMT(C16)) - GKM_IDX_THREADS / 32 + (tid >> 5); /* cold phase only */
-    uint32_t *xq = reinterpret_cast<uint32_t *>(qbase + GKM_IDX_QBYTES_FMT(C16));
+    int *lqcnt = reinterpret_cast<int *>(qbase + GKM_IDX_QBYTES_FMT(FMT == GKM_IDX_FMT_C16)) - GKM_IDX_THREADS / 32 + (tid >> 5); /* cold phase only */
+    uint32_t *xq = reinterpret_cast<uint32_t *>(qbase + GKM_IDX_QBYTES_FMT(FMT == GKM_IDX_FMT_C16));
     uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
 
     const int ncol = (int) (bhi - blo);
@@ -591,8 +675,11 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     }
     __syncthreads();
 
-    if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, C16>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi, queue + GKM_IDX_QCAP, lqcnt);
-    idx_probe_hot<WEIGHTED, RANGE, C16>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
+    if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, FMT>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi, queue + GKM_IDX_QCAP, lqcnt);
+    /* weighted types at two CTAs per SM: two loads in flight per thread instead of four (the same number per SM as one
+     * CTA with four) keep the 32-register build nearly spill-free: wgkm at 10k 50.7 -> 47.8 ms (tools/wgkm_ab.py) */
+    constexpr int UNR = (WEIGHTED && MINB == 2) ? 2 : GKM_IDX_UNROLL;
+    idx_probe_hot<WEIGHTED, RANGE, FMT, UNR>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
     __syncthreads();
 
     /* epilogue: histogram -> normalised double, the reference's operation order */
@@ -664,21 +751,19 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
      * that build is held to 32 registers, which the compact-slot code meets without spills (41.0 instead of 46.1 ms
      * at 10k).  The decision is per block, not per launch: mixing the two builds inside one problem measured
      * slower (28 288 sequences: 272 ms against 228 ms), and the 16-byte-slot code spills at 32 registers
-     * (wgkm at 10k: 70 ms against 49 ms), so the weighted types always run one CTA per SM. */
-    bool two = !weighted && 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted, c16) + 1280u) <= 227u * 1024u;
+     * (wgkm at 10k: 70 ms against 49 ms), so that format always runs one CTA per SM. */
+    const unsigned pair = 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted, c16) + 1280u);
+    bool two = ra->fmt != GKM_IDX_FMT_P32 && (!weighted || GKM_IDX_W20_TWO) && pair <= (ra->nblk > 1 ? GKM_IDX_TWO_SMEM : 227u * 1024u);
     { const char *e = getenv("GKM_IDX_MINB"); if (e) two = atoi(e) == 2; } /* A/B knob */
+    if ((ra->fmt == GKM_IDX_FMT_C16 && weighted) || (ra->fmt == GKM_IDX_FMT_W20 && !weighted)) { gkm_set_error("index slot format does not match the kernel type"); return 1; }
     const void *fn;
-    if (ra->fmt == GKM_IDX_FMT_C16) {
-        if (weighted) { gkm_set_error("compact index slots carry no weights"); return 1; }
-        fn = range ? (two ? (const void *) gkm_index_rows_kernel<false, true, true, 2> : (const void *) gkm_index_rows_kernel<false, true, true, 1>)
-                   : (two ? (const void *) gkm_index_rows_kernel<false, false, true, 2> : (const void *) gkm_index_rows_kernel<false, false, true, 1>);
-    } else if (weighted) {
-        fn = range ? (two ? (const void *) gkm_index_rows_kernel<true, true, false, 2> : (const void *) gkm_index_rows_kernel<true, true, false, 1>)
-                   : (two ? (const void *) gkm_index_rows_kernel<true, false, false, 2> : (const void *) gkm_index_rows_kernel<true, false, false, 1>);
-    } else {
-        fn = range ? (two ? (const void *) gkm_index_rows_kernel<false, true, false, 2> : (const void *) gkm_index_rows_kernel<false, true, false, 1>)
-                   : (two ? (const void *) gkm_index_rows_kernel<false, false, false, 2> : (const void *) gkm_index_rows_kernel<false, false, false, 1>);
-    }
+#define GKM_IDX_PICK(W, F) (range ? (two ? (const void *) gkm_index_rows_kernel<W, true, F, 2> : (const void *) gkm_index_rows_kernel<W, true, F, 1>) \
+                                  : (two ? (const void *) gkm_index_rows_kernel<W, false, F, 2> : (const void *) gkm_index_rows_kernel<W, false, F, 1>))
+    if (ra->fmt == GKM_IDX_FMT_C16) fn = GKM_IDX_PICK(false, GKM_IDX_FMT_C16);
+    else if (ra->fmt == GKM_IDX_FMT_W20) fn = GKM_IDX_PICK(true, GKM_IDX_FMT_W20);
+    else if (weighted) fn = GKM_IDX_PICK(true, GKM_IDX_FMT_P32);
+    else fn = GKM_IDX_PICK(false, GKM_IDX_FMT_P32);
+#undef GKM_IDX_PICK
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess) {
         void *args[] = { (void *) kp, (void *) ra };

@@ -51,6 +51,17 @@ extern "C" {
 #define GKM_IDX_FMT_C16 1
 #define GKM_IDX_C16_NONE 0xFFFFu
 #define GKM_IDX_C16_MAX_COLS 0x7FFF
+/* compact slots of the weighted kernel types (4, 5): 8 bytes = three 20-bit postings (column : 14 | weight : 6) + 4 flag
+ * bits; four or more postings: two inline + pointer to 32-bit postings (the P32 entry format) in the overflow array.
+ * Needs weights <= 63 (M <= 63; gkmQC's default is 50), <= 16 352 columns per block and < 2^22 overflow units;
+ * otherwise the 16-byte slots are used.  Same table size and sector density as C16 (gkm_index.cu: idx_slot20). */
+#define GKM_IDX_FMT_W20 2
+#define GKM_IDX_W20_COL_BITS 14
+#define GKM_IDX_W20_COL_MASK 0x3FFFu
+#define GKM_IDX_W20_MAX_COLS 16352
+#define GKM_IDX_W20_MAX_WEIGHT 63
+#define GKM_IDX_W20_MAX_UNITS (1u << 22)
+#define GKM_IDX_W20_UNITS(len) ((((len) - 2u + 4u) & ~3u) >> 2)
 /* long lists (repeats, homopolymers): an overflow list of GKM_IDX_LONG_UNITS or more 16-byte units is not walked by
  * the lane that met it (one dependent load per unit: a 20 000-posting poly-A list cost that lane ~1 ms, and every
  * third random row meets it) but by its whole warp, a unit per lane.  Such a list starts with a 16-byte header

@@ -39,6 +39,7 @@ struct gkm_idx_rowargs {
     int blo, bhi;  /* wanted columns, relative to cb */
     int ldh;       /* histogram row stride in shared memory (>= bhi - blo) */
     int blk_cols;  /* columns of the whole index block (decides the kernel build) */
+    int nblk;      /* column blocks of the problem (ditto) */
     int maxq;      /* upper bound of query L-mers per row */
 };
 

@@ -97,7 +97,7 @@ int gkm_idx_supported(int L, int d, int nbins)
  *   -> probes 8.7e11 /s + postings in range 4.1e11 /s, and never faster than the sector rate of the slot probes:
  *      4e11 /s while the table sits in L2 (<= 64 MB), 1.8e11 /s up to 256 MB (L = 12), 0.9e11 /s beyond (L >= 13);
  *      checked against the 15 (L, d) of BASELINE configs[2] at 20 000 sequences (profiles/r1_config3_sweep_20k_index.*);
- *   16-byte slots (weighted types): 0.8 of that;  build ~1 ms per column block + 0.3 ms + the table memset;
+ *   weighted types (compact 20-bit postings, two loads in flight): 0.86 of that;  build ~1 ms per column block + 0.3 ms + the table memset;
  *   diag  2.94e13 L-mer pairs /s (d <= 3), 1.35e13 (d = 4), ~1.2e13 (d <= 7), ~6e12 above; weighted types 0.6 of that. */
 double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, double col_blocks, long long entries,
                        double mean_pairs_per_entry)
@@ -106,7 +106,7 @@ double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_q
     const double slots = pow(4.0, (double) L);
     const double slot_bytes = weighted ? 16.0 : 8.0;
     const double tab_mb = slots * slot_bytes / 1048576.0;
-    const double scale = weighted ? 0.8 : 1.0;
+    const double scale = weighted ? 0.86 : 1.0;
     const double probes = (double) rows * mean_query_lmers * nd * col_blocks;
     const double hits = (double) entries * mean_pairs_per_entry * nd / slots; /* random sequences: P(distance <= d) = nd / 4^L */
     double t = probes / (8.7e11 * scale) + hits / (4.1e11 * scale);

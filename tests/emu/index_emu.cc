@@ -56,7 +56,39 @@ static void build_index(const gkmb200_problem *p, int cb, int ce, emu_index &ix)
     }
     std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return (a >> 8) < (b >> 8); });
     size_t i = 0;
-    ix.fmt = (!p->weighted && ce - cb <= GKM_IDX_C16_MAX_COLS && !getenv("GKM_EMU_INDEX_WIDE")) ? GKM_IDX_FMT_C16 : GKM_IDX_FMT_P32;
+    ix.fmt = GKM_IDX_FMT_P32;
+    if (!getenv("GKM_EMU_INDEX_WIDE")) {
+        if (!p->weighted && ce - cb <= GKM_IDX_C16_MAX_COLS) ix.fmt = GKM_IDX_FMT_C16;
+        if (p->weighted && ce - cb <= GKM_IDX_W20_MAX_COLS && p->param.M <= GKM_IDX_W20_MAX_WEIGHT) ix.fmt = GKM_IDX_FMT_W20;
+    }
+    /* W20: x = p0 | p1 << 20, y = p1 >> 12 | p2 << 8 | flags; >= 4 postings: y = p1 >> 12 | long << 8 | units offset << 9 | PTR,
+     * overflow entries are P32 postings starting with posting 2 */
+    while (ix.fmt == GKM_IDX_FMT_W20 && i < keys.size()) {
+        size_t e = i;
+        while (e < keys.size() && (keys[e] >> 32) == (keys[i] >> 32)) e++;
+        const size_t len = e - i;
+        uint32_t p20[3] = { 0xFFFFFu, 0xFFFFFu, 0xFFFFFu };
+        for (size_t r = 0; r < len && r < 3; r++)
+            p20[r] = ((uint32_t) (keys[i + r] >> 8) & GKM_IDX_W20_COL_MASK) | (((uint32_t) keys[i + r] & 0xFFu) << GKM_IDX_W20_COL_BITS);
+        emu_slot s;
+        s.v[0] = p20[0] | (p20[1] << 20);
+        if (len <= 3) {
+            s.v[1] = (p20[1] >> 12) | (p20[2] << 8) | (0x7u << 28); /* flag bits other than PTR stay as the memset left them */
+        } else {
+            while (ix.ovf.size() & 3) ix.ovf.push_back(GKM_IDX_EMPTY);
+            const uint32_t units = GKM_IDX_W20_UNITS((uint32_t) len);
+            const uint32_t lng = units >= GKM_IDX_LONG_UNITS ? 1u : 0u;
+            s.v[1] = (p20[1] >> 12) | (lng << 8) | ((uint32_t) (ix.ovf.size() >> 2) << 9) | GKM_IDX_PTR;
+            if (lng) { ix.ovf.push_back(units); ix.ovf.push_back(0); ix.ovf.push_back(0); ix.ovf.push_back(0); }
+            for (size_t r = 2; r < len; r++)
+                ix.ovf.push_back(gkm_idx_posting((uint32_t) (keys[i + r] >> 8) & GKM_IDX_COL_MASK, (uint32_t) keys[i + r] & 0xFFu));
+            ix.ovf.push_back(GKM_IDX_EMPTY);
+            while (ix.ovf.size() & 3) ix.ovf.push_back(GKM_IDX_EMPTY);
+        }
+        s.v[2] = s.v[3] = 0;
+        ix.tab[(uint32_t) (keys[i] >> 32)] = s;
+        i = e;
+    }
     while (ix.fmt == GKM_IDX_FMT_C16 && i < keys.size()) {
         size_t e = i;
         while (e < keys.size() && (keys[e] >> 32) == (keys[i] >> 32)) e++;
@@ -167,6 +199,33 @@ static void probe_row(const gkmb200_problem *p, const emu_index &ix, const std::
                         for (int t = 0; t < 8; t++) hit16(H, nb, m, q[t], blo, bhi);
                         if (q[7] >= bhi) break;
                         q += 8;
+                    }
+                }
+                continue;
+            }
+            if (ix.fmt == GKM_IDX_FMT_W20) {
+                const uint32_t p0 = sl[0] & 0xFFFFFu, p1 = (sl[0] >> 20) | ((sl[1] & 0xFFu) << 12);
+                const uint32_t c0 = p0 & GKM_IDX_W20_COL_MASK, c1 = p1 & GKM_IDX_W20_COL_MASK;
+                if (c0 < bhi && c0 >= blo) H[(size_t) (c0 - blo) * nb + m] += w * (int) (p0 >> GKM_IDX_W20_COL_BITS);
+                if (c1 < bhi && c1 >= blo) H[(size_t) (c1 - blo) * nb + m] += w * (int) (p1 >> GKM_IDX_W20_COL_BITS);
+                if (!(sl[1] & GKM_IDX_PTR) || c0 == GKM_IDX_W20_COL_MASK) {
+                    const uint32_t p2 = (sl[1] >> 8) & 0xFFFFFu, c2 = p2 & GKM_IDX_W20_COL_MASK;
+                    if (c2 < bhi && c2 >= blo) H[(size_t) (c2 - blo) * nb + m] += w * (int) (p2 >> GKM_IDX_W20_COL_BITS);
+                } else if (c1 < bhi) {
+                    const uint32_t *q = ix.ovf.data() + (((sl[1] >> 9) & 0x3FFFFFu) << 2);
+                    if ((sl[1] >> 8) & GKM_IDX_LONG) {
+                        const uint32_t units = q[0];
+                        for (uint32_t u = 0; u < units; u++) {
+                            const uint32_t *v = q + 4 + 4 * (size_t) u;
+                            if ((v[0] & GKM_IDX_COL_MASK) >= bhi) continue;
+                            for (int t = 0; t < 4; t++) hit(H, nb, m, v[t], blo, bhi, w);
+                        }
+                    } else {
+                        for (;;) {
+                            for (int t = 0; t < 4; t++) hit(H, nb, m, q[t], blo, bhi, w);
+                            if ((q[3] & GKM_IDX_COL_MASK) >= bhi) break;
+                            q += 4;
+                        }
                     }
                 }
                 continue;

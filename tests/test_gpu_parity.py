@@ -126,7 +126,9 @@ def test_seeded_against_oracle(kernel_type, L, k, d, length, ragged, variant):
                                                           (0, 9, 9, 0, 32, 0), (2, 8, 4, 4, 32, 1), (2, 11, 7, 3, 0, 1), (1, 7, 4, 3, 0, 0),
                                                           # nearly every slot holds a LONG list (whole-warp walks, and more than 32 of
                                                           # them per probe iteration: the long queue overflows into per-lane walks)
-                                                          (4, 5, 4, 1, 0, 0), (2, 4, 3, 1, 0, 0), (2, 4, 3, 1, 64, 0), (2, 5, 3, 2, 0, 1)])
+                                                          (4, 5, 4, 1, 0, 0), (2, 4, 3, 1, 0, 0), (2, 4, 3, 1, 64, 0), (2, 5, 3, 2, 0, 1),
+                                                          # weighted types: compact 20-bit postings (wide = 0) and the 16-byte slots (1)
+                                                          (4, 5, 4, 1, 0, 1), (4, 10, 6, 3, 64, 1), (5, 11, 7, 3, 0, 0), (5, 11, 7, 3, 0, 1), (4, 7, 5, 2, 32, 0)])
 def test_index_column_blocks(kernel_type, L, k, d, cols, wide):
     """index variant with the columns cut into several index blocks (what a problem larger than one
     shared-memory histogram row gets), long posting lists (short L, repeats) and a column window that
@@ -141,7 +143,7 @@ def test_index_column_blocks(kernel_type, L, k, d, cols, wide):
     o = pyoracle.Oracle(kernel_type, L, k, d, 50, 50.0, 0.7)
     capi.set_option("kernel", "index")
     capi.set_option("index_cols", str(cols))
-    capi.set_option("index_wide", str(wide))  # unit-weight types: compact 8-byte slots (0) or the 16-byte ones (1)
+    capi.set_option("index_wide", str(wide))  # compact 8-byte slots (0: C16 / W20 by kernel type) or the 16-byte ones (1)
     try:
         with capi.Problem(kernel_type, L, k, d, 50, 50.0, 0.7) as P:
             for s in seqs:

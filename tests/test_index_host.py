@@ -133,9 +133,7 @@ def test_emulated_index_long_lists_and_ranges(kernel_type, L, d, wide, emu, monk
     """few distinct L-mers (short L, repeats): posting lists far beyond the four inline slots, so the overflow
     walk, its end markers and the column-range cut are exercised; plus a rectangular block with col0 > 0"""
     if wide:
-        if kernel_type in (4, 5):
-            pytest.skip("the weighted types always use the 16-byte slots")
-        monkeypatch.setenv("GKM_EMU_INDEX_WIDE", "1")  # 16-byte slots for a unit-weight type too
+        monkeypatch.setenv("GKM_EMU_INDEX_WIDE", "1")  # 16-byte slots instead of the compact ones (C16 / W20)
     seqs = random_seqs(40, 90, seed=17 * L + d, ragged=True)
     seqs = [s if len(s) >= L else s + "ACGT" * 4 for s in seqs]
     seqs[7] = seqs[6]
