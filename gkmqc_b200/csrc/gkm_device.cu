@@ -324,6 +324,8 @@ static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g
     }
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     dim3 grid((unsigned) ((cols + kp.TB - 1) / kp.TB), (unsigned) ((rows + kp.TA - 1) / kp.TA), 1);
+    /* the diagonal: one CTA per row tile (it finds its own column tile), where the tile shapes allow it */
+    if (kp.mode == GKM_MODE_DIAG && variant == GKM_KERNEL_DIAG && kp.TB % kp.TA == 0 && kp.row_begin == kp.col_begin) grid.x = 1;
     if (grid.y > 65535u) { gkm_set_error("chunk has too many row tiles"); return 1; }
     void *args[] = { &kp };
     CK(cudaLaunchKernel(fn, grid, dim3(256, 1, 1), args, smem, st));
@@ -619,9 +621,13 @@ static int upload_locked(gkmb200_problem *p, int need_host)
         fill_kparams(p, im, &kp);
         kp.mode = GKM_MODE_DIAG;
         kp.sqnorm_out = im->sqnorm;
-        for (int r = 0; r < p->n; r += 1024) {
+        /* the bit-sliced kernel covers the diagonal with one column of CTAs, 8 rows each: one launch for up to
+         * 131 070 rows (grid.y <= 65 535 row tiles of at least 2 rows; it was 10 launches of 32 x 128 CTAs at 10k,
+         * 1.8 ms of device time) */
+        const int step = (pick_variant(p, GKM_MODE_DIAG) == GKM_KERNEL_DIAG) ? 131070 : 1024;
+        for (int r = 0; r < p->n; r += step) {
             kp.row_begin = kp.col_begin = kp.row_base = kp.col_base = r;
-            kp.row_end = kp.col_end = (r + 1024 < p->n) ? r + 1024 : p->n;
+            kp.row_end = kp.col_end = (r + step < p->n) ? r + step : p->n;
             if (launch_hist(p, im, g, kp, g->sc, NULL)) return 1;
             p->stats.launches++;
         }

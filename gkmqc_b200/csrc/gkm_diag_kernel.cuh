@@ -98,7 +98,10 @@ gkm_diag_kernel(const __grid_constant__ gkm_kparams p)
 
     const int tid = threadIdx.x;
     const int row0 = p.row_begin + (int) blockIdx.y * TA;
-    const int col0 = p.col_begin + (int) blockIdx.x * TB;
+    /* sqnorm (GKM_MODE_DIAG) launches ONE column of CTAs: each takes the column tile that holds its rows' diagonal
+     * (TB is a multiple of TA, so a row tile never straddles two column tiles) */
+    const int col0 = (p.mode == GKM_MODE_DIAG && gridDim.x == 1) ? p.col_begin + ((row0 - p.col_begin) / TB) * TB
+                                                                 : p.col_begin + (int) blockIdx.x * TB;
     const int row_last = min(row0 + TA, p.row_end) - 1;
     const int col_last = min(col0 + TB, p.col_end) - 1;
     if (p.mode == GKM_MODE_LOWER && col0 > row_last) return;           /* tile entirely above the diagonal */
