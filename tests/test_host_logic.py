@@ -173,3 +173,45 @@ def test_svm_task_preparation_follows_libsvm_grouping():
     assert te.tolist() == [2, 4, 7, 0]
     with pytest.raises(ValueError):
         capi.svm_prepare_tasks(y, [(np.array([0, 2]), np.array([1]))])
+
+
+def test_copy_threads_policy(monkeypatch):
+    """the reference's nthreads (default 1 in bin/gkmqc.py) is only a lower bound on the copy-out threads: the library
+    takes the cores of its affinity mask, 16 at most; GKM_COPY_THREADS overrides (gkm_device.cu:gkm_copy_threads)"""
+    import ctypes
+    lib = capi.load()
+    lib.gkm_copy_threads.restype = ctypes.c_int
+    lib.gkm_copy_threads.argtypes = [ctypes.c_int]
+    monkeypatch.delenv("GKM_COPY_THREADS", raising=False)
+    avail = min(16, len(os.sched_getaffinity(0)))
+    assert lib.gkm_copy_threads(1) == avail
+    assert lib.gkm_copy_threads(avail + 3) == avail + 3
+    assert lib.gkm_copy_threads(1000) == 64
+    monkeypatch.setenv("GKM_COPY_THREADS", "5")
+    assert lib.gkm_copy_threads(1) == 5 and lib.gkm_copy_threads(32) == 5
+
+
+def test_two_file_read_equals_two_sequential_reads(tmp_path):
+    """gkmb200_problem_read parses the negatives on a helper thread and appends them: ids, order and codes must be
+    those of two sequential reads (positives 0..n_pos-1, negatives behind: libgkm.c:1316-1333)"""
+    seqs = random_seqs(301, 90, seed=5, ragged=True)
+    seqs = [s if len(s) >= 11 else s + "ACGTACGTACG" for s in seqs]
+    pos, neg = tmp_path / "p.fa", tmp_path / "n.fa"
+    pos.write_text("".join(">p%d\n%s\n" % (i, s) for i, s in enumerate(seqs[:120])))
+    neg.write_text("".join(">n%d\r\n%s\r\n" % (i, s.lower()) for i, s in enumerate(seqs[120:])))
+    a = capi.Problem(2, 11, 7, 3)
+    b = capi.Problem(2, 11, 7, 3)
+    try:
+        assert a.read(str(pos), str(neg)) == 120
+        assert b.read_fasta(str(pos)) == 120 and b.read_fasta(str(neg)) == 181
+        assert a.n == b.n == 301
+        for i in (0, 1, 119, 120, 121, 200, 300):
+            assert a.seqlen(i) == b.seqlen(i) == len(seqs[i])
+            fa, ra = a.codes(i)
+            fb, rb = b.codes(i)
+            assert np.array_equal(fa, fb) and np.array_equal(ra, rb)
+        with pytest.raises(capi.GkmError):
+            capi.Problem(2, 11, 7, 3).read(str(pos), str(tmp_path / "missing.fa"))
+    finally:
+        a.close()
+        b.close()
