@@ -598,7 +598,7 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 const int xi = ph + (it + u) * nph;
-                const bool ok = (it + u < n_it) && xi < nq;
+                const bool ok = xi < nq; /* implies it + u < n_it */
                 const uint32_t y = (ok ? xq[xi] : 0u) ^ dx;
                 bh[u] = ok ? bhi_l : 0u;
                 w[u] = (WEIGHTED && ok) ? (int) wq[xi] : 1;
