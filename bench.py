@@ -400,6 +400,8 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_rate(pos, neg, n, 15.0, os.cpu_count() or 1)
+        one = cpu_reference_rate(pos, neg, n, 5.0, 1)   # the 1-thread figure beside the all-cores one
+        cpu["single_thread"] = {"value": one["value"], "unit": one["unit"], "kind": one["kind"], "sample": one["sample"]}
 
     print(json.dumps({
         "metric": "gkm kernel entries/sec (300bp, l=11 k=7 d=3)", "value": value, "unit": "entries/s",
