@@ -98,7 +98,7 @@ int gkm_idx_supported(int L, int d, int nbins)
  *      4e11 /s while the table sits in L2 (<= 64 MB), 1.8e11 /s up to 256 MB (L = 12), 0.9e11 /s beyond (L >= 13);
  *      checked against the 15 (L, d) of BASELINE configs[2] at 20 000 sequences (profiles/r1_config3_sweep_20k_index.*);
  *   weighted types (compact 20-bit postings, two loads in flight): 0.86 of that;  build ~1 ms per column block + 0.3 ms + the table memset;
- *   diag  2.94e13 L-mer pairs /s (d <= 3), 1.35e13 (d = 4), ~1.2e13 (d <= 7), ~6e12 above; weighted types 0.6 of that. */
+ *   diag  2.94e13 L-mer pairs /s (d <= 3), 2.06e13 (d = 4: 1.6 s per 20k pass in profiles/r1_v9_config3_sweep_20k_auto.log), ~1.2e13 (d <= 7), ~6e12 above; weighted types 0.6 of that. */
 double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_query_lmers, double col_blocks, long long entries,
                        double mean_pairs_per_entry)
 {
@@ -117,7 +117,7 @@ double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_q
 
 double gkm_diag_cost_ms(int d, int weighted, long long entries, double mean_pairs_per_entry)
 {
-    double rate = (d <= 3) ? 2.94e13 : (d == 4) ? 1.35e13 : (d <= 7) ? 1.2e13 : 6e12;
+    double rate = (d <= 3) ? 2.94e13 : (d == 4) ? 2.06e13 : (d <= 7) ? 1.2e13 : 6e12;
     if (weighted) rate *= 0.6;
     return 1e3 * (double) entries * mean_pairs_per_entry / rate;
 }
