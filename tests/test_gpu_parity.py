@@ -195,6 +195,30 @@ def test_nonuniform_index_vs_bitsliced(kernel_type):
         capi.set_option("kernel", "auto")
 
 
+def test_sqnorm_beyond_one_launch():
+    """sqnorm is the diagonal of the kernel, computed by one column of CTAs per launch of at most 131 070 rows: more
+    rows than that take several launches.  Copies of the same sequences on both sides of the boundary must get the
+    same value, and the values must be the oracle's."""
+    base = random_seqs(300, 60, seed=77, ragged=True)
+    base = [s if len(s) >= 11 else s + "ACGTACGTACG" for s in base]
+    reps = 131070 // len(base) + 2
+    seqs = (base * reps)[:131070 + 450]
+    o = pyoracle.Oracle(4, 11, 7, 3)
+    for s in base:
+        o.add(s)
+    want = o.sqnorm() if hasattr(o, "sqnorm") else None
+    with capi.Problem(4, 11, 7, 3) as P:
+        P.add_many(seqs)
+        sq = P.sqnorm()
+    assert len(sq) == len(seqs)
+    per = np.asarray(sq[:len(base)])
+    for start in range(0, len(seqs), len(base)):
+        part = np.asarray(sq[start:start + len(base)])
+        assert np.array_equal(part, per[:len(part)]), start
+    if want is not None:
+        assert np.array_equal(per, np.asarray(want))
+
+
 def test_edge_cases(variant):
     L, k, d = 11, 7, 3
     seqs = ["ACGTACGTACG",               # exactly one L-mer
