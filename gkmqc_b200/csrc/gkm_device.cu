@@ -250,6 +250,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
         if (!b->built) { gkm_set_error("index block %d is not built", k); return 1; }
         gkm_idx_rowargs ra;
         ra.fmt = b->fmt; ra.tab = b->tab; ra.ovf = b->ovf; ra.deltas = g->d_deltas; ra.ndelta = g->ndelta;
+        ra.nslots = 1u << (2 * p->param.L);
         ra.cb = b->cb; ra.blo = lo - b->cb; ra.bhi = hi - b->cb;
         ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
         ra.blk_cols = b->ce - b->cb;

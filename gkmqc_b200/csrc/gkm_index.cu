@@ -259,7 +259,8 @@ gkm_idx_fill_w20_kernel(const unsigned long long *__restrict__ keys, uint32_t P,
     }
 }
 
-size_t gkm_idx_tab_bytes(int L, int fmt) { return ((size_t) 1 << (2 * L)) * (fmt == GKM_IDX_FMT_P32 ? sizeof(uint4) : sizeof(uint2)); }
+/* 4^L slots and one spare, always empty: where the probes of lanes that ran out of query L-mers go */
+size_t gkm_idx_tab_bytes(int L, int fmt) { return (((size_t) 1 << (2 * L)) + 1) * (fmt == GKM_IDX_FMT_P32 ? sizeof(uint4) : sizeof(uint2)); }
 
 /* overflow demand is at most 2 entries per posting in either format (header unit of the long lists included) */
 size_t gkm_idx_ovf_bytes(size_t P, int fmt) { return (2 * P + 16) * (fmt == GKM_IDX_FMT_C16 ? 2 : 4); }
@@ -591,7 +592,6 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
         const uint32_t bhi_l = lane_ok ? bhi : 0u; /* a lane without a mask never hits */
         const int n_it = (nq + nph - 1) / nph;     /* the same for every lane */
         for (int it = 0; it < n_it; it += UNR) {
-            uint32_t bh[UNR];
             int w[UNR];
             uint4 sl[UNR];
             uint2 sc[UNR];
@@ -599,17 +599,17 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
             for (int u = 0; u < UNR; u++) {
                 const int xi = ph + (it + u) * nph;
                 const bool ok = xi < nq; /* implies it + u < n_it */
-                const uint32_t y = (ok ? xq[xi] : 0u) ^ dx;
-                bh[u] = ok ? bhi_l : 0u;
+                /* a probe past the last L-mer reads the spare slot behind the table: always empty, never a hit */
+                const uint32_t y = ok ? (xq[xi] ^ dx) : r.nslots;
                 w[u] = (WEIGHTED && ok) ? (int) wq[xi] : 1;
                 if constexpr (FMT != GKM_IDX_FMT_P32) sc[u] = __ldg(tab16 + y); else sl[u] = __ldg(tab + y);
             }
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 uint32_t o;
-                if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bh[u]);
-                else if constexpr (FMT == GKM_IDX_FMT_W20) o = idx_slot20<RANGE>(sc[u], Hm, blo, bh[u], w[u]);
-                else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bh[u], w[u]);
+                if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bhi_l);
+                else if constexpr (FMT == GKM_IDX_FMT_W20) o = idx_slot20<RANGE>(sc[u], Hm, blo, bhi_l, w[u]);
+                else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bhi_l, w[u]);
                 const uint32_t mk = __ballot_sync(0xFFFFFFFFu, o != ~0u);
                 if (mk) {
                     if (o != ~0u) queue[qn + __popc(mk & lt)] = QE::make(o, mrow, w[u]);

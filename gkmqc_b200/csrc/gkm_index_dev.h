@@ -32,6 +32,7 @@ struct gkm_idx_build_args {
 struct gkm_idx_rowargs {
     int fmt;
     const void *tab; const uint32_t *ovf; const uint32_t *deltas;
+    uint32_t nslots; /* 4^L: index of the spare, always empty slot behind the table */
     int ndelta;    /* masks in all */
     int ncold;     /* the first ncold masks belong to the cold bins (m <= d - 2) */
     int32_t *cold; /* [rows of the launch][cold bins][ldh] scratch in global memory, zeroed by the kernel */
