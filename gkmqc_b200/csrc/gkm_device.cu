@@ -256,6 +256,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
         ra.ldh = (ra.bhi - ra.blo + 31) & ~31;
         ra.blk_cols = b->ce - b->cb;
         ra.nblk = im->nblk;
+        ra.skew = b->skew;
         ra.maxq = 32 * p->Wa;
         ra.ncold = g->ncold;
         {   /* cold-bin scratch of this stream, grown on demand (the stream is drained before a block is replaced) */
@@ -495,6 +496,7 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
             a.W = p->Wmax; a.L = L; a.cb = b->cb; a.ce = b->ce;
             a.offs = (const uint32_t *) d_offs; a.P = P; a.scratch = scratch; a.cub_bytes = cub_bytes;
             a.fmt = b->fmt; a.tab = b->tab; a.ovf = b->ovf;
+            b->sumsq = 0; a.h_sumsq = &b->sumsq;
             rc = gkm_idx_build(&a, g->sc);
         }
         /* pageable source and recycled scratch: wait for the build before letting go of them */
@@ -503,6 +505,8 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
         pool_free(g, scratch, scratch_got);
         pool_free(g, d_offs, offs_got);
         if (rc) return 1;
+        b->skew = (double) b->sumsq / (double) (P ? P : 1);
+        gkm_log(GKM_LOG_DEBUG, "index block %d: %zu postings, sum len^2 / postings = %.2f", k, P, b->skew);
         b->built = 1;
         p->stats.launches += 5;
     }

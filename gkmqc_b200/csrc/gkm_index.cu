@@ -37,6 +37,7 @@
 #ifndef GKM_IDX_TWO_SMEM
 #define GKM_IDX_TWO_SMEM (196u * 1024u)
 #endif
+#define GKM_IDX_SKEW_ONE_CTA 16.0 /* sum len^2 / P of the block: 2.4 on uniform 10k x 300 bp, 3 on AT-rich, > 100 with 10 % poly-A */
 #ifndef GKM_IDX_W20_TWO
 #define GKM_IDX_W20_TWO 1 /* weighted compact slots: two CTAs per SM where the histogram rows fit (A/B: 0) */
 #endif
@@ -98,13 +99,13 @@ __device__ __forceinline__ uint32_t idx_lower(const unsigned long long *keys, ui
 }
 
 __global__ void __launch_bounds__(256)
-gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int fmt, uint32_t *__restrict__ runlen, uint32_t *__restrict__ need)
+gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int fmt, uint32_t *__restrict__ runlen, uint32_t *__restrict__ need,
+                    unsigned long long *__restrict__ sumsq)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const uint32_t code = (uint32_t) (keys[i] >> 32);
     uint32_t len = 0;
-    if (i == 0 || (uint32_t) (keys[i - 1] >> 32) != code) {
+    const uint32_t code = (i < P) ? (uint32_t) (keys[i] >> 32) : 0u;
+    if (i < P && (i == 0 || (uint32_t) (keys[i - 1] >> 32) != code)) {
         /* gallop, then bisect: runs are short (mean 1.4 at 10k x 300 bp) but homopolymers make long ones */
         uint32_t lo = i + 1, hi = P, step = 1; /* [i, lo) holds `code`; keys[hi] does not (or hi == P) */
         for (;;) {
@@ -116,6 +117,14 @@ gkm_idx_runs_kernel(const unsigned long long *__restrict__ keys, uint32_t P, int
         }
         len = idx_upper(keys, lo, hi, code) - i;
     }
+    {   /* sum of squared list lengths of the block: its ratio to P tells uniform input (1 + postings per slot) from
+         * input with repeats (one list of 20 000 postings outweighs everything else); one atomic per warp */
+        unsigned long long sq = (unsigned long long) len * (unsigned long long) len;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_down_sync(0xFFFFFFFFu, sq, o);
+        if ((threadIdx.x & 31u) == 0u && sq) atomicAdd(sumsq, sq);
+    }
+    if (i >= P) return;
     runlen[i] = len;
     /* overflow entries of a run of 5 or more: P32 keeps postings 3.. (32-bit entries, quads), C16 columns 2..
      * (16-bit entries, octets); both padded with at least one end marker */
@@ -298,7 +307,10 @@ int gkm_idx_build(const gkm_idx_build_args *a, cudaStream_t st)
     if ((e = cub::DeviceRadixSort::SortKeys(cub_tmp, cub_bytes, keys_a, keys_b, (int) P, 32, 32 + 2 * a->L, st)) != cudaSuccess) goto fail;
     {
         const unsigned blocks = (unsigned) ((P + 255) / 256);
-        gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, a->fmt, runlen, need);
+        unsigned long long *sumsq = (unsigned long long *) ((unsigned char *) cub_tmp + a->cub_bytes); /* in the slack behind the cub area */
+        if ((e = cudaMemsetAsync(sumsq, 0, sizeof(*sumsq), st)) != cudaSuccess) goto fail;
+        gkm_idx_runs_kernel<<<blocks, 256, 0, st>>>(keys_b, (uint32_t) P, a->fmt, runlen, need, sumsq);
+        if (a->h_sumsq && (e = cudaMemcpyAsync(a->h_sumsq, sumsq, sizeof(*sumsq), cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto fail;
         uint32_t *ovfofs = (uint32_t *) keys_a; /* the unsorted keys are dead now */
         cub_bytes = a->cub_bytes;
         if ((e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, need, ovfofs, (int) P, st)) != cudaSuccess) goto fail;
@@ -754,6 +766,9 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
      * (wgkm at 10k: 70 ms against 49 ms), so that format always runs one CTA per SM. */
     const unsigned pair = 2u * (gkm_idx_row_smem(kp->nbins, (ra->blk_cols + 31) & ~31, ra->maxq, weighted, c16) + 1280u);
     bool two = ra->fmt != GKM_IDX_FMT_P32 && (!weighted || GKM_IDX_W20_TWO) && pair <= (ra->nblk > 1 ? GKM_IDX_TWO_SMEM : 227u * 1024u);
+    /* weighted types on input with repeats (long-tailed rows): one CTA per SM (everything-mixed workload of
+     * tools/nonuniform.py: 80 against 95 ms; uniform input: 50.4 against 47.4 ms the other way round) */
+    if (weighted && ra->skew > GKM_IDX_SKEW_ONE_CTA) two = false;
     { const char *e = getenv("GKM_IDX_MINB"); if (e) two = atoi(e) == 2; } /* A/B knob */
     if ((ra->fmt == GKM_IDX_FMT_C16 && weighted) || (ra->fmt == GKM_IDX_FMT_W20 && !weighted)) { gkm_set_error("index slot format does not match the kernel type"); return 1; }
     const void *fn;

@@ -15,6 +15,8 @@ struct gkm_idx_block {
     void *tab;           /* 4^L slots */
     uint32_t *ovf;       /* overflow lists (16-byte aligned, padded with end markers) */
     size_t tab_bytes, ovf_bytes; /* block sizes as handed out by the pool */
+    unsigned long long sumsq;    /* sum of squared posting-list lengths (gkm_idx_runs_kernel) */
+    double skew;                 /* sumsq / postings: ~1 + postings per slot on uniform input, far more with repeats */
     int built;
 };
 
@@ -27,6 +29,7 @@ struct gkm_idx_build_args {
     size_t cub_bytes;
     int fmt;
     void *tab; uint32_t *ovf;
+    unsigned long long *h_sumsq; /* host, optional: sum of squared list lengths, valid once the stream has drained */
 };
 
 struct gkm_idx_rowargs {
@@ -41,6 +44,7 @@ struct gkm_idx_rowargs {
     int ldh;       /* histogram row stride in shared memory (>= bhi - blo) */
     int blk_cols;  /* columns of the whole index block (decides the kernel build) */
     int nblk;      /* column blocks of the problem (ditto) */
+    double skew;   /* of the block (ditto, weighted types) */
     int maxq;      /* upper bound of query L-mers per row */
 };
 
