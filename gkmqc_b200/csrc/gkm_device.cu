@@ -520,6 +520,7 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     gkm_devstate *ds = p->dev;
     const int opt = gkm_opt_kernel();
     int v = base_variant(p);
+    double ci = 0.0, cd = 0.0; /* estimates of kernel = auto */
     if ((opt == GKM_KERNEL_AUTO || opt == GKM_KERNEL_INDEX) && nrows > 0 && ncols > 0 &&
         gkm_idx_supported(p->param.L, p->param.d, p->nbins)) {
         const int cap = index_block_cap(p);
@@ -537,8 +538,8 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             const long long entries = (long long) nrows * (long long) ncols / (lower ? 2 : 1);
             /* lower: row a probes only the blocks that start below it */
             const double eff_blocks = lower ? 0.5 * (double) (blocks + 1) : (double) blocks;
-            const double ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks, entries, 2.0 * nq * nq);
-            const double cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
+            ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks, entries, 2.0 * nq * nq);
+            cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
             ok = ci < cd;
             gkm_log(GKM_LOG_DEBUG, "kernel = auto: index %.2f ms vs diag %.2f ms (estimates)", ci, cd);
         }
@@ -551,6 +552,21 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             if (ensure_index(p, g, &ds->img[i], col0, col0 + ncols)) return 1;
             CK(cudaEventRecord(g->join, g->sc));
             CK(cudaStreamWaitEvent(g->sc2, g->join, 0));
+        }
+        /* kernel = auto, second look: the cost model above assumes random sequences.  The index build knows better:
+         * a list of l postings is met by ~l/2 query L-mers of the same problem, l^2/4 exact-match hits in the lower
+         * triangle.  Low-complexity input (thousands of poly-A sequences) makes that term seconds; the bit-sliced
+         * kernel does not care what the sequences are. */
+        if (opt == GKM_KERNEL_AUTO && lower && row0 == col0 && nrows == ncols) {
+            const gkm_image *im = &ds->img[0];
+            double sumsq = 0.0;
+            for (int k = 0; k < im->nblk; k++)
+                if (im->blk[k].built && im->blk[k].ce > col0 && im->blk[k].cb < col0 + ncols) sumsq += (double) im->blk[k].sumsq;
+            const double extra = 1e3 * 0.25 * sumsq / 4.1e11;
+            if (ci + extra > cd) {
+                gkm_log(GKM_LOG_DEBUG, "kernel = auto: long posting lists add ~%.1f ms to the index estimate (%.1f ms): bit-sliced kernel (%.1f ms)", extra, ci, cd);
+                v = base_variant(p);
+            }
         }
     }
     (void) row0;

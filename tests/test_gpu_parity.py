@@ -195,6 +195,30 @@ def test_nonuniform_index_vs_bitsliced(kernel_type):
         capi.set_option("kernel", "auto")
 
 
+def test_auto_leaves_the_index_on_low_complexity_input():
+    """kernel = auto looks at the posting lists the index build produced: half of the sequences being poly-A makes the
+    exact-match term of the index kernel larger than the whole bit-sliced pass, so auto runs the bit-sliced kernel --
+    and both give the same integers"""
+    n, L, k, d = 3000, 11, 7, 3
+    rng = np.random.default_rng(8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = [acgt[r].tobytes().decode() for r in rng.integers(0, 4, size=(n, 300))]
+    for i in range(0, n, 2):
+        seqs[i] = "A" * 300 if (i // 2) % 2 == 0 else "T" * 150 + "A" * 150
+    out = {}
+    try:
+        for v in ("auto", "index"):
+            capi.set_option("kernel", v)
+            with capi.Problem(2, L, k, d) as P:
+                P.add_many(seqs)
+                K = P.kernel_lower()
+                out[v] = (K[n - 40:, :], P.stats()["kernel_variant"])
+    finally:
+        capi.set_option("kernel", "auto")
+    assert out["index"][1] == 4 and out["auto"][1] == 2
+    assert np.array_equal(out["auto"][0], out["index"][0])
+
+
 def test_sqnorm_beyond_one_launch():
     """sqnorm is the diagonal of the kernel, computed by one column of CTAs per launch of at most 131 070 rows: more
     rows than that take several launches.  Copies of the same sequences on both sides of the boundary must get the
