@@ -215,3 +215,23 @@ def test_two_file_read_equals_two_sequential_reads(tmp_path):
     finally:
         a.close()
         b.close()
+
+
+def test_base_coding_of_every_byte_value():
+    """A,C,G,T in either case -> 1..4 (gkm_data.seq codes); every other byte counts as A like the reference does
+    (libgkm.c:864-875).  All 256 byte values, at every position of the 16-byte vector path and of the scalar tail."""
+    lib = capi.load()
+    lib.gkmb200_set_verbosity(0)   # the warnings about the 248 other bytes are not the point here
+    want = {ord("A"): 1, ord("a"): 1, ord("C"): 2, ord("c"): 2, ord("G"): 3, ord("g"): 3, ord("T"): 4, ord("t"): 4}
+    P = capi.Problem(2, 11, 7, 3)
+    try:
+        for shift in (0, 5, 16):
+            raw = bytes((b + shift) & 0xFF for b in range(256)) + bytes(range(37))   # 293 bytes: 18 vectors + 5 tail bytes
+            i = P.add(raw)
+            fwd, rc = P.codes(i)
+            exp = np.array([want.get(b, 1) for b in raw], np.uint8)
+            assert np.array_equal(fwd, exp)
+            assert np.array_equal(rc, (5 - exp)[::-1])
+    finally:
+        P.close()
+        lib.gkmb200_set_verbosity(2)
