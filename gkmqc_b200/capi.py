@@ -41,7 +41,8 @@ class gkmb200_stats(ctypes.Structure):
         ("kernel_ms", ctypes.c_double), ("wall_ms", ctypes.c_double), ("upload_ms", ctypes.c_double),
         ("launches", ctypes.c_longlong), ("entries", ctypes.c_longlong), ("lmer_pairs", ctypes.c_longlong),
         ("h2d_bytes", ctypes.c_longlong), ("d2h_bytes", ctypes.c_longlong),
-        ("devices", ctypes.c_int), ("kernel_variant", ctypes.c_int), ("reserved", ctypes.c_int * 6),
+        ("devices", ctypes.c_int), ("kernel_variant", ctypes.c_int), ("shard_rank", ctypes.c_int), ("shard_world", ctypes.c_int),
+        ("copy_threads", ctypes.c_int), ("thp_chunks", ctypes.c_int), ("scatter_ms", ctypes.c_float), ("wait_ms", ctypes.c_float),
     )
 
     def as_dict(self):
@@ -101,6 +102,8 @@ def _declare(lib):
     lib.gkmb200_problem_read.argtypes = [P, ctypes.c_char_p, ctypes.c_char_p]
     lib.gkmb200_problem_size.argtypes = [P]
     lib.gkmb200_problem_seqlen.argtypes = [P, I]
+    lib.gkmb200_problem_sid.argtypes = [P, I]
+    lib.gkmb200_problem_sid.restype = ctypes.c_char_p
     lib.gkmb200_problem_codes.argtypes = [P, I, c_u8_p, c_u8_p]
     lib.gkmb200_problem_get_weights.argtypes = [P, c_dbl_p]
     lib.gkmb200_problem_set_shard.argtypes = [P, I, I]
@@ -239,6 +242,9 @@ class Problem:
 
     def seqlen(self, i):
         return self.lib.gkmb200_problem_seqlen(self.h, i)
+
+    def sid(self, i):
+        return self.lib.gkmb200_problem_sid(self.h, i)
 
     def codes(self, i):
         n = self.seqlen(i)

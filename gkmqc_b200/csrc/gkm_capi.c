@@ -134,6 +134,9 @@ int gkm_main_pywrapper(gkmOpt *opts, double **kmat, int *kmat_size)
 
     gkmb200_problem *p = gkmb200_problem_new(&param);
     if (!p) return 1;
+    gkm_problem_shard_from_env(p); /* one process per GPU: this call fills only the chunks of its rank */
+    if (p->shard_world > 1)
+        gkm_log(GKM_LOG_WARN, "GKM_SHARD=%d/%d: this process computes only its own chunks of the matrix", p->shard_rank, p->shard_world);
     int rc = 1;
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
@@ -168,6 +171,8 @@ int gkm_main_pywrapper(gkmOpt *opts, double **kmat, int *kmat_size)
 typedef struct gkm_shadow {
     gkmb200_problem *prob; /* device-resident image of prob_svm_data */
     int dirty;
+    gkm_data **read_x;     /* the objects gkmkernel_read_problems made `prob` from, in image order */
+    int read_n;
 } gkm_shadow;
 
 static gkm_shadow *shadow_of(gkm_kernel *kernel) { return (gkm_shadow *) (void *) kernel->prob_kmertree; }
@@ -207,7 +212,7 @@ void gkmkernel_destroy(gkm_kernel *kernel)
 {
     if (!kernel) return;
     gkm_shadow *sh = shadow_of(kernel);
-    if (sh) { gkmb200_problem_free(sh->prob); free(sh); }
+    if (sh) { gkmb200_problem_free(sh->prob); free(sh->read_x); free(sh); }
     free(kernel->prob_svm_data);
     free(kernel->prob_gkmkernel_index);
     free(kernel->prob_libsvm_index);
@@ -222,39 +227,34 @@ static char *dup_string(const char *s)
     return r;
 }
 
-/* a gkm_data laid out like the reference's (libgkm.c:841-938); sqnorm comes from the GPU */
-gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seqid)
+/* the arrays of a gkm_data from base codes 0..3 (libgkm.c:864-932): seq, seq_rc (codes 1..4), seq_string, wt, wt_rc
+ * and the leaf index of every L-mer in the reference's 4-ary tree (libgkm.c:891-908: base-4 digits 0..3).
+ * Returns 1 when an allocation failed (the caller deletes the object). */
+static int fill_object(gkm_data *d, const gkm_parameter *pa, const uint8_t *code, int len, const char *text, const char *sid, int seqid)
 {
-    if (!kernel || !seq) return NULL;
-    const gkm_parameter *pa = kernel->param;
-    const int len = (int) strlen(seq);
+    static const char letters[4] = { 'A', 'C', 'G', 'T' };
     const int nk = len - pa->L + 1;
-    if (nk < 1) { gkm_set_error("sequence %s is shorter than L", sid ? sid : "?"); return NULL; }
-    gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
-    if (!d) return NULL;
     d->sid = sid ? dup_string(sid) : NULL;
     d->seqid = seqid;
     d->seqlen = len;
-    d->seq_string = dup_string(seq);
+    d->seq_string = (char *) malloc((size_t) len + 1);
     d->seq = (u_int8_t *) malloc((size_t) len);
     d->seq_rc = (u_int8_t *) malloc((size_t) len);
     d->wt = (u_int8_t *) malloc((size_t) nk);
     d->wt_rc = (u_int8_t *) malloc((size_t) nk);
     d->kmerids = (int *) malloc(sizeof(int) * (size_t) nk);
     d->kmerids_rc = (int *) malloc(sizeof(int) * (size_t) nk);
-
-    /* one-sequence problem: coding, and sqnorm = sqrt(Kraw(x,x)) on the device */
-    gkmb200_problem *one = gkmb200_problem_new(pa);
-    if (!one || gkmb200_problem_add(one, seq, len) < 0 || gkmb200_problem_codes(one, 0, d->seq, d->seq_rc) ||
-        gkm_dev_upload(one)) {
-        gkmb200_problem_free(one);
-        gkmkernel_delete_object(d);
-        return NULL;
+    if ((sid && !d->sid) || !d->seq_string || !d->seq || !d->seq_rc || !d->wt || !d->wt_rc || !d->kmerids || !d->kmerids_rc) {
+        gkm_set_error("out of memory");
+        return 1;
     }
-    d->sqnorm = one->sqnorm[0];
-    gkmb200_problem_free(one);
+    for (int j = 0; j < len; j++) {
+        d->seq[j] = (u_int8_t) (code[j] + 1);
+        d->seq_rc[j] = (u_int8_t) (4 - code[len - 1 - j]);
+        d->seq_string[j] = text ? text[j] : letters[code[j]]; /* the reference keeps the caller's spelling (strcpy) */
+    }
+    d->seq_string[len] = '\0';
     gkm_calc_posweights(nk, pa->kernel_type, pa->M, pa->H, d->wt, d->wt_rc);
-    /* leaf index of each L-mer in the reference's 4-ary tree (libgkm.c:891-908): base-4 digits 0..3 */
     u_int8_t *strands[2] = { d->seq, d->seq_rc };
     int *ids[2] = { d->kmerids, d->kmerids_rc };
     for (int s = 0; s < 2; s++)
@@ -263,6 +263,36 @@ gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seq
             for (int i = 0; i < pa->L; i++) v = v * 4 + (strands[s][i + j] - 1);
             ids[s][j] = v;
         }
+    return 0;
+}
+
+/* a gkm_data laid out like the reference's (libgkm.c:841-938); sqnorm comes from the GPU.
+ * The reference bounds the length only in read_fasta_file (2047 bases, libgkm.c:1294-1299); the engine holds at
+ * most GKM_MAX_BASES per sequence, so a longer string handed to this function directly is cut there as well
+ * (with the warning the reader would have given) and seqlen / seq_string describe what is actually used. */
+gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seqid)
+{
+    if (!kernel || !seq) return NULL;
+    const gkm_parameter *pa = kernel->param;
+    size_t full = strlen(seq);
+    if (full > GKM_MAX_BASES) {
+        gkm_log(GKM_LOG_WARN, "maximum sequence length allowed is %d. The first %d nucleotides of %s will only be used",
+                GKM_MAX_BASES, GKM_MAX_BASES, sid ? sid : "?");
+        full = GKM_MAX_BASES;
+    }
+    const int len = (int) full;
+    if (len - pa->L + 1 < 1) { gkm_set_error("sequence %s is shorter than L", sid ? sid : "?"); return NULL; }
+    gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
+    if (!d) return NULL;
+    /* one-sequence problem: coding, and sqnorm = sqrt(Kraw(x,x)) on the device */
+    gkmb200_problem *one = gkmb200_problem_new(pa);
+    if (!one || gkmb200_problem_add(one, seq, len) < 0 || fill_object(d, pa, one->code[0], len, seq, sid, seqid) || gkm_dev_upload(one)) {
+        gkmb200_problem_free(one);
+        gkmkernel_delete_object(d);
+        return NULL;
+    }
+    d->sqnorm = one->sqnorm[0];
+    gkmb200_problem_free(one);
     gkm_log(GKM_LOG_TRACE, "%d's sqnorm is %f", seqid, d->sqnorm);
     return d;
 }
@@ -284,6 +314,18 @@ void gkmkernel_delete_object(gkm_data *d)
     free(d);
 }
 
+/* one caller-held object -> one sequence of an engine problem.  The object may come from anywhere (the ABI lets
+ * callers build gkm_data themselves): its length is checked against what the engine holds, its arrays against NULL. */
+static int add_object(gkmb200_problem *prob, const gkm_data *x, int i)
+{
+    static const char letters[4] = { 'A', 'C', 'G', 'T' };
+    char buf[GKM_MAX_BASES + 1];
+    if (!x || !x->seq) { gkm_set_error("object %d is null or was freed with gkmkernel_free_object", i); return 1; }
+    if (x->seqlen < 1 || x->seqlen > GKM_MAX_BASES) { gkm_set_error("object %d has %d bases; the engine holds 1..%d", i, x->seqlen, GKM_MAX_BASES); return 1; }
+    for (int j = 0; j < x->seqlen; j++) buf[j] = letters[(x->seq[j] - 1) & 3];
+    return gkmb200_problem_add(prob, buf, x->seqlen) < 0;
+}
+
 /* rebuild the device image from prob_svm_data (order = current gkmkernel index order) */
 static int shadow_sync(gkm_kernel *kernel)
 {
@@ -293,16 +335,8 @@ static int shadow_sync(gkm_kernel *kernel)
     gkmb200_problem_free(sh->prob);
     sh->prob = gkmb200_problem_new(kernel->param);
     if (!sh->prob) return 1;
-    static const char letters[4] = { 'A', 'C', 'G', 'T' };
-    char *buf = (char *) malloc(MAX_SEQ_LENGTH);
-    if (!buf) return 1;
-    for (int i = 0; i < kernel->prob_num; i++) {
-        const gkm_data *x = kernel->prob_svm_data[i];
-        if (!x->seq) { gkm_set_error("object %d was freed with gkmkernel_free_object", i); free(buf); return 1; }
-        for (int j = 0; j < x->seqlen; j++) buf[j] = letters[(x->seq[j] - 1) & 3];
-        if (gkmb200_problem_add(sh->prob, buf, x->seqlen) < 0) { free(buf); return 1; }
-    }
-    free(buf);
+    for (int i = 0; i < kernel->prob_num; i++)
+        if (add_object(sh->prob, kernel->prob_svm_data[i], i)) return 1;
     sh->dirty = 0;
     return gkm_dev_upload(sh->prob);
 }
@@ -321,7 +355,12 @@ void gkmkernel_build_tree(gkm_kernel *kernel, gkm_data **x, int n)
     kernel->prob_num = n;
     for (int i = 0; i < n; i++) { kernel->prob_gkmkernel_index[i] = i; kernel->prob_libsvm_index[i] = i; }
     gkm_shadow *sh = shadow_of(kernel);
-    if (sh) sh->dirty = 1;
+    if (sh) {
+        /* the image gkmkernel_read_problems uploaded serves as it is when the tree is built over exactly its objects */
+        const int same = sh->prob && sh->read_x && sh->read_n == n && n > 0 && memcmp(sh->read_x, x, sizeof(gkm_data *) * (size_t) n) == 0;
+        sh->dirty = !same;
+        free(sh->read_x); sh->read_x = NULL; sh->read_n = 0;
+    }
     if (n > 0 && shadow_sync(kernel)) gkm_log(GKM_LOG_ERROR, "gkmkernel_build_tree: %s", gkmb200_last_error());
 }
 
@@ -344,18 +383,13 @@ double *gkmkernel_kernelfunc_batch(gkm_kernel *kernel, int a, const gkm_data **d
     if (!kernel || !res || n < 0) return res;
     for (int i = 0; i < n; i++) res[i] = 0;
     if (n == 0 || a < 0 || a >= kernel->prob_num) return res;
-    static const char letters[4] = { 'A', 'C', 'G', 'T' };
+    if (!db_array) return res;
     gkmb200_problem *tmp = gkmb200_problem_new(kernel->param);
-    char *buf = (char *) malloc(MAX_SEQ_LENGTH);
-    int ok = tmp && buf;
-    for (int i = 0; ok && i <= n; i++) { /* db_array[0..n-1] then the query */
-        const gkm_data *x = (i < n) ? db_array[i] : kernel->prob_svm_data[a];
-        for (int j = 0; j < x->seqlen; j++) buf[j] = letters[(x->seq[j] - 1) & 3];
-        ok = gkmb200_problem_add(tmp, buf, x->seqlen) >= 0;
-    }
+    int ok = tmp != NULL;
+    for (int i = 0; ok && i <= n; i++) /* db_array[0..n-1] then the query */
+        ok = !add_object(tmp, (i < n) ? db_array[i] : kernel->prob_svm_data[a], i);
     if (!ok || gkm_dev_compute(tmp, n, 1, 0, n, 0, res, n, NULL, NULL, 1))
         gkm_log(GKM_LOG_ERROR, "gkmkernel_kernelfunc_batch: %s", gkmb200_last_error());
-    free(buf);
     gkmb200_problem_free(tmp);
     return res;
 }
@@ -368,6 +402,8 @@ double gkmkernel_kernelfunc(const gkm_data *da, const gkm_data *db)
     return NAN;
 }
 
+/* libgkm.c:1316-1333 + read_fasta_file: every record becomes a gkm_data with the fields the reference fills (sid,
+ * seq, seq_rc, seq_string, kmerids, kmerids_rc, wt, wt_rc, sqnorm) and, beyond the reference, its label. */
 int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *posfile, const char *negfile)
 {
     if (!kernel || !prob) return -1;
@@ -375,33 +411,38 @@ int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *p
     if (!p) return -1;
     int npos = gkmb200_problem_read(p, posfile, negfile);
     if (npos < 0 || gkm_dev_upload(p)) { gkmb200_problem_free(p); return -1; }
-    const int n = p->n, L = kernel->param->L;
+    const int n = p->n;
     prob->l = n;
     prob->y = (double *) malloc(sizeof(double) * (size_t) (n ? n : 1));
-    prob->x = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
-    static const char letters[4] = { 'A', 'C', 'G', 'T' };
-    for (int i = 0; i < n; i++) {
-        const int len = p->len[i], nk = len - L + 1;
+    prob->x = (gkm_data **) calloc((size_t) (n ? n : 1), sizeof(gkm_data *));
+    int bad = !prob->y || !prob->x;
+    for (int i = 0; !bad && i < n; i++) {
         gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
-        d->seqid = i; d->seqlen = len;
+        prob->x[i] = d;
+        if (!d || fill_object(d, kernel->param, p->code[i], p->len[i], NULL, p->sid[i] ? p->sid[i] : "", i)) { bad = 1; break; }
         d->label = (i < npos) ? 1 : -1;
-        d->seq = (u_int8_t *) malloc((size_t) len);
-        d->seq_rc = (u_int8_t *) malloc((size_t) len);
-        d->wt = (u_int8_t *) malloc((size_t) nk);
-        d->wt_rc = (u_int8_t *) malloc((size_t) nk);
-        d->seq_string = (char *) malloc((size_t) len + 1);
-        gkmb200_problem_codes(p, i, d->seq, d->seq_rc);
-        for (int j = 0; j < len; j++) d->seq_string[j] = letters[p->code[i][j]];
-        d->seq_string[len] = '\0';
-        gkm_calc_posweights(nk, kernel->param->kernel_type, kernel->param->M, kernel->param->H, d->wt, d->wt_rc);
         d->sqnorm = p->sqnorm[i];
         prob->y[i] = d->label;
-        prob->x[i] = d;
     }
-    /* keep the uploaded image: build_tree on exactly these objects can reuse it */
+    if (bad) {
+        gkm_set_error("out of memory reading %s / %s", posfile, negfile);
+        if (prob->x) for (int i = 0; i < n; i++) gkmkernel_delete_object(prob->x[i]);
+        free(prob->x); free(prob->y);
+        prob->x = NULL; prob->y = NULL; prob->l = 0;
+        gkmb200_problem_free(p);
+        return -1;
+    }
+    /* keep the uploaded image: gkmkernel_build_tree on exactly these objects, in this order, adopts it
+     * instead of packing and uploading the same sequences again */
     gkm_shadow *sh = shadow_of(kernel);
-    if (sh) { gkmb200_problem_free(sh->prob); sh->prob = p; sh->dirty = 1; }
-    else gkmb200_problem_free(p);
+    if (sh) {
+        gkmb200_problem_free(sh->prob);
+        sh->prob = p; sh->dirty = 1;
+        free(sh->read_x);
+        sh->read_x = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
+        sh->read_n = sh->read_x ? n : 0;
+        if (sh->read_x) memcpy(sh->read_x, prob->x, sizeof(gkm_data *) * (size_t) n);
+    } else gkmb200_problem_free(p);
     return npos;
 }
 

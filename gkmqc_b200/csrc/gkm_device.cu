@@ -120,6 +120,27 @@ struct gkm_devstate {
     int variant;        /* kernel variant of the compute call in progress (choose_variant) */
 };
 
+/* give the cached blocks of one GPU back to the driver (current device must be g's) */
+static void pool_trim(gkm_gpu *g)
+{
+    for (int i = 0; i < g->npool; i++) cudaFree(g->pool[i].ptr);
+    g->npool = 0;
+}
+
+/* cudaMalloc that, when the device is out of memory, first returns this library's own cached blocks (up to 32 blocks
+ * of up to 512 MB per GPU would otherwise stand between a long-lived host and a 50k x 50k problem) and tries again */
+static cudaError_t dev_malloc(gkm_gpu *g, void **out, size_t bytes)
+{
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && g->npool > 0) {
+        cudaGetLastError();
+        gkm_log(GKM_LOG_DEBUG, "GPU %d: out of memory for %zu bytes, releasing %d cached blocks", g->id, bytes, g->npool);
+        pool_trim(g);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+
 static double now_ms(void)
 {
     struct timespec t;
@@ -207,7 +228,7 @@ static int gpu_prepare(gkm_gpu *g, int id, size_t band_bytes, size_t stage_bytes
     if (band_bytes > g->band_cap) {
         for (int i = 0; i < GKM_NBUF; i++) { if (g->d_band[i]) cudaFree(g->d_band[i]); g->d_band[i] = NULL; }
         g->band_cap = 0;
-        for (int i = 0; i < GKM_NBUF; i++) CK(cudaMalloc(&g->d_band[i], band_bytes));
+        for (int i = 0; i < GKM_NBUF; i++) CK(dev_malloc(g, &g->d_band[i], band_bytes));
         g->band_cap = band_bytes;
     }
     if (stage_bytes > g->stage_cap) {
@@ -267,7 +288,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
                 if (g->d_cold[si]) cudaFree(g->d_cold[si]);
                 g->d_cold[si] = NULL; g->cold_cap[si] = 0;
                 const size_t want = need + need / 4 + 4096;
-                CK(cudaMalloc((void **) &g->d_cold[si], want));
+                CK(dev_malloc(g, (void **) &g->d_cold[si], want));
                 g->cold_cap[si] = want;
             }
             ra.cold = g->d_cold[si];
@@ -369,7 +390,7 @@ static int pool_alloc(gkm_gpu *g, void **out, size_t *got, size_t bytes)
         g->pool[best] = g->pool[--g->npool];
         return 0;
     }
-    CK(cudaMalloc(out, need));
+    CK(dev_malloc(g, out, need));
     *got = need;
     return 0;
 }
@@ -574,6 +595,20 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     return 0;
 }
 
+/* drop every cached device block of every GPU (long-lived hosts that change L or n) */
+extern "C" int gkmb200_trim(void)
+{
+    pthread_mutex_lock(&g_lock);
+    for (int i = 0; i < GKM_MAX_DEV; i++) {
+        gkm_gpu *g = &g_gpu[i];
+        if (!g->ready || cudaSetDevice(g->id) != cudaSuccess) { cudaGetLastError(); continue; }
+        cudaStreamSynchronize(g->sc); cudaStreamSynchronize(g->sc2); cudaStreamSynchronize(g->sx);
+        pool_trim(g);
+    }
+    pthread_mutex_unlock(&g_lock);
+    return 0;
+}
+
 extern "C" void gkm_dev_release(gkmb200_problem *p)
 {
     if (!p || !p->dev) return;
@@ -689,6 +724,7 @@ struct gkm_job {
     double **rows;          /* ... or row pointers (absolute column index) */
     int32_t *hist;          /* dense histogram destination (tests) */
     int copy_threads;
+    double thp_cover;       /* advise_chunk: least covered fraction of a chunk's row span that earns the huge-page hint; 0 = never */
     int failed;
     char err[256];
 };
@@ -797,12 +833,46 @@ static void scatter_chunk(gkm_team *tm, const gkm_job *job, const gkm_chunk *c, 
     if (nt > 1) while (sem_wait(&tm->done) != 0) { /* EINTR */ }
 }
 
+/* The caller's matrix is fresh, never-touched memory (np.zeros of 15000 x 15000, gkmsvm.py:75): every 4 KB page the
+ * scatter writes first takes a page fault (~2 us; 1.4-1.8 GB/s per thread).  With transparent huge pages in "madvise"
+ * mode a 2 MB page is zeroed in one fault at ~5 GB/s per thread -- but the WHOLE page, the upper triangle included.
+ * Round 1 hinted the whole matrix and measured no gain: the triangle covers half of it.  The hint is now given per
+ * chunk, only to the whole huge pages inside that chunk's own row span, and only where the chunk's entries cover
+ * at least `thp_cover` of that span (break-even 0.37 on this host: 400 us per huge page against 512 x 2.1 us).
+ * A hint only: it changes no contents and no ownership.  GKM_NO_THP=1 switches it off, GKM_THP_COVER sets the bar. */
+static int advise_chunk(const gkm_job *job, const gkm_chunk *c)
+{
+    const int nr = c->row_end - c->row_begin;
+    if (job->thp_cover <= 0.0 || nr < 2 || c->col_end <= c->col_begin) return 0;
+    const char *first;
+    ptrdiff_t stride;
+    if (job->rows) {
+        first = (const char *) (job->rows[c->row_begin] + c->col_begin);
+        stride = (const char *) job->rows[c->row_begin + 1] - (const char *) job->rows[c->row_begin];
+        for (int r = c->row_begin; r + 1 < c->row_end; r++) /* one array with evenly spaced rows, or no hint */
+            if ((const char *) job->rows[r + 1] - (const char *) job->rows[r] != stride) return 0;
+    } else if (job->out) {
+        stride = (ptrdiff_t) job->ld * (ptrdiff_t) sizeof(double);
+        first = (const char *) (job->out + (size_t) (c->row_begin - job->row0) * (size_t) job->ld + (size_t) (c->col_begin - job->col0));
+    } else return 0;
+    if (stride <= 0) return 0;
+    const double span = (double) stride * (double) nr;
+    if ((double) c->entries * 8.0 < job->thp_cover * span) return 0;
+    const uintptr_t huge = (uintptr_t) 2 << 20;
+    uintptr_t lo = ((uintptr_t) first + huge - 1) & ~(huge - 1);
+    uintptr_t hi = ((uintptr_t) first + (uintptr_t) stride * (uintptr_t) (nr - 1) + (uintptr_t) (c->col_end - c->col_begin) * sizeof(double)) & ~(huge - 1);
+    if (hi <= lo) return 0;
+    return madvise((void *) lo, (size_t) (hi - lo), MADV_HUGEPAGE) == 0;
+}
+
 struct gkm_devthread {
     gkm_job *job;
     int slot;          /* index into devstate */
     double kernel_ms;
+    double scatter_ms, wait_ms; /* host time of this device thread spent copying into caller rows / waiting for the GPU */
     long long launches, d2h_bytes, entries;
     int variant;
+    int thp_chunks;    /* chunks whose destination got the huge-page hint */
 };
 
 static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const gkm_chunk *c, int buf, int32_t *d_hist)
@@ -821,6 +891,7 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     kp.hist = d_hist;
     kp.hist_cols = width;
     cudaStream_t st = (buf & 1) ? g->sc2 : g->sc;
+    dt->thp_chunks += advise_chunk(job, c); /* ahead of the kernel: off the critical path of the copy-out */
     CK(cudaEventRecord(g->k0[buf], st));
     if (launch_hist(job->p, im, g, kp, st, &dt->variant)) return 1;
     CK(cudaEventRecord(g->k1[buf], st));
@@ -852,7 +923,7 @@ static int dev_thread_run(gkm_devthread *dt, gkm_team *team_p)
     gkm_team &team = *team_p;
     int32_t *d_hist = NULL, *h_hist = NULL;
     if (job->hist) {
-        CK(cudaMalloc(&d_hist, maxhist ? maxhist : 4));
+        CK(dev_malloc(g, (void **) &d_hist, maxhist ? maxhist : 4));
         h_hist = (int32_t *) malloc(maxhist ? maxhist : 4);
         if (!h_hist) { gkm_set_error("out of memory"); return 1; }
     }
@@ -921,8 +992,11 @@ static int dev_thread_run(gkm_devthread *dt, gkm_team *team_p)
             inflight++;
         }
     }
-    gkm_log(GKM_LOG_DEBUG, "GPU %d: %.2f ms in all: issue %.2f, waiting for chunks %.2f, scatter %.2f (after the last chunk arrived: %.2f)",
-            ds->dev[dt->slot], now_ms() - tb0, t_issue, t_wait, t_scatter, now_ms() - t_lastsync);
+    dt->scatter_ms = t_scatter; dt->wait_ms = t_wait;
+    gkm_log(GKM_LOG_DEBUG, "GPU %d: %.2f ms in all: issue %.2f, waiting for chunks %.2f, scatter %.2f = %.1f GB/s with %d threads, %d chunks "
+            "hinted huge (after the last chunk arrived: %.2f)",
+            ds->dev[dt->slot], now_ms() - tb0, t_issue, t_wait, t_scatter, t_scatter > 0 ? (double) dt->entries * 8e-6 / t_scatter : 0.0,
+            team.nthreads, dt->thp_chunks, now_ms() - t_lastsync);
     if (rc) cudaDeviceSynchronize();
     if (d_hist) cudaFree(d_hist);
     free(h_hist);
@@ -958,46 +1032,34 @@ static long long plan_budget(const gkmb200_problem *p, long long total_cells, in
 
 /* Host threads that scatter finished chunks into the caller's rows.  The reference's `nthreads` (default 1 in
  * bin/gkmqc.py:107,162) is its number of COMPUTE threads; here the only host work that scales with it is the copy-out,
- * which at 10k is 100 000 first-touch page faults of the caller's fresh matrix: 72 / 54 / 50 ms per call with 4 / 8 /
- * >= 12 threads on the 16-core GPU box (tools/e2e_ab.py), GPU-bound from 12 on.  So the request is a lower bound and
- * the library uses the cores this process may run on (its affinity mask: cgroup- and slurm-aware), 16 at most.
- * GKM_COPY_THREADS overrides. */
+ * which is first-touch page faults of the caller's fresh matrix (100 000 of them at 10k, 2.4 million at 50k; ~2 us
+ * each on this host: tools/pagefault_probe.c).  So the request is a lower bound and the library uses the cores this
+ * process may run on (its affinity mask: cgroup-, slurm- and taskset-aware).  Round 1 capped that at 16; the 8-GPU box
+ * has 32 cores and the cap left half of them idle.  GKM_COPY_THREADS overrides. */
 #include <sched.h>
-extern "C" int gkm_copy_threads(int requested)
+static int host_cores(void)
 {
-    const char *e = getenv("GKM_COPY_THREADS");
-    if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
     int avail = 0;
     cpu_set_t set;
     CPU_ZERO(&set);
     if (sched_getaffinity(0, sizeof(set), &set) == 0) avail = CPU_COUNT(&set);
     if (avail < 1) avail = (int) sysconf(_SC_NPROCESSORS_ONLN);
-    if (avail > 16) avail = 16;
-    return requested > avail ? (requested > 64 ? 64 : requested) : (avail < 1 ? 1 : avail);
+    return avail < 1 ? 1 : avail;
 }
 
-/* The caller's matrix is fresh, never-touched memory (np.zeros of 15000 x 15000, gkmsvm.py:75): every 4 KB page
- * the scatter writes first takes a page fault.  Where transparent huge pages are in "madvise" mode a hint on the
- * destination span turns ~100 000 small faults of a 10k problem into a few hundred 2 MB ones.  A hint only: it
- * changes no contents and no ownership; GKM_NO_THP=1 switches it off. */
-static void advise_hugepages(double **rows, int row0, int nrows, int col0, int ncols)
+/* threads of one process that shares the box with `world - 1` others (one process per GPU) */
+extern "C" int gkm_copy_threads_shared(int requested, int world)
 {
-    if (nrows < 2 || ncols < 1) return;
-    uintptr_t lo = (uintptr_t) (rows[row0] + col0), hi = lo;
-    for (int r = row0; r < row0 + nrows; r++) {
-        const uintptr_t a = (uintptr_t) (rows[r] + col0), b = a + (uintptr_t) ncols * sizeof(double);
-        if (a < lo) lo = a;
-        if (b > hi) hi = b;
-    }
-    const uintptr_t page = (uintptr_t) sysconf(_SC_PAGESIZE);
-    lo = (lo + page - 1) & ~(page - 1);  /* inwards: only whole pages of the destination itself */
-    hi &= ~(page - 1);
-    if (hi <= lo || hi - lo > ((uintptr_t) 1 << 38) || hi - lo < ((uintptr_t) 4 << 20)) return;
-    /* rows far apart (not one array) would make the span meaningless: require it to be no larger than 4x the rows' own extent */
-    if ((double) (hi - lo) > 4.0 * (double) nrows * (double) ((uintptr_t) rows[row0 + 1] > (uintptr_t) rows[row0]
-                                                          ? (uintptr_t) rows[row0 + 1] - (uintptr_t) rows[row0] : (uintptr_t) ncols * 8)) return;
-    (void) madvise((void *) lo, (size_t) (hi - lo), MADV_HUGEPAGE);
+    const char *e = getenv("GKM_COPY_THREADS");
+    if (e && atoi(e) > 0) return atoi(e) > 64 ? 64 : atoi(e);
+    if (world < 1) world = 1;
+    int n = host_cores() / world;
+    if (n < requested) n = requested;
+    if (n < 1) n = 1;
+    return n > 64 ? 64 : n;
 }
+
+extern "C" int gkm_copy_threads(int requested) { return gkm_copy_threads_shared(requested, 1); }
 
 extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0, int ncols, int lower,
                                double *out, long ld, double **rows, int32_t *hist, int copy_threads)
@@ -1007,11 +1069,8 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
         gkm_set_error("block [%d,+%d) x [%d,+%d) outside the problem (n=%d)", row0, nrows, col0, ncols, p->n);
         return 1;
     }
-    copy_threads = gkm_copy_threads(copy_threads);
-    if (p->shard_world > 1 && !getenv("GKM_COPY_THREADS")) { /* the ranks of one box share its cores */
-        copy_threads /= p->shard_world;
-        if (copy_threads < 2) copy_threads = 2;
-    }
+    /* the ranks of a sharded run (one process per GPU) share the cores of the box */
+    copy_threads = gkm_copy_threads_shared(copy_threads, p->shard_world);
     pthread_mutex_lock(&g_lock);
     const double t0 = now_ms();
     p->stats.launches = 0;
@@ -1033,7 +1092,7 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
         chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
         owned = (int *) malloc(sizeof(int) * (size_t) maxc);
         int nchunks = (chunks && owned) ? gkm_plan_chunks_rows(row0, nrows, col0, ncols, lower, tile_rows,
-                                                               plan_budget(p, total_cells, ds->ndev), by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
+                                                               plan_budget(p, total_cells, ds->ndev), by_rows ? 4 * 148 : 65520 /* grid.y <= 65535 row tiles */, chunks, maxc) : -1;
         if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
         if (!rc) {
             gkm_job job;
@@ -1047,9 +1106,13 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
             }
             job.row0 = row0; job.col0 = col0; job.ncols = ncols; job.lower = lower;
             job.out = out; job.ld = ld; job.rows = rows; job.hist = hist;
-            /* the host threads that scatter finished chunks are shared by the GPUs of the call */
-            job.copy_threads = copy_threads / ds->ndev > 1 ? copy_threads / ds->ndev : (ds->ndev > 1 ? 2 : copy_threads);
-            if (rows && !getenv("GKM_NO_THP")) advise_hugepages(rows, row0, nrows, col0, ncols);
+            /* the host threads that scatter finished chunks are shared by the GPUs of the call: each device thread
+             * leads a team of its share of them (different chunks, so different 2 MB regions of the destination) */
+            job.copy_threads = copy_threads / ds->ndev > 1 ? copy_threads / ds->ndev : 1;
+            if ((rows || out) && !hist && !getenv("GKM_NO_THP")) {
+                const char *tc = getenv("GKM_THP_COVER");
+                job.thp_cover = tc ? atof(tc) : 0.4;
+            }
             gkm_devthread dts[GKM_MAX_DEV];
             pthread_t th[GKM_MAX_DEV];
             int started[GKM_MAX_DEV];
@@ -1065,7 +1128,12 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
                 else dev_thread(&dts[i]);
             }
             p->stats.kernel_ms = 0; p->stats.d2h_bytes = 0; p->stats.entries = 0;
+            p->stats.scatter_ms = 0; p->stats.wait_ms = 0; p->stats.thp_chunks = 0;
+            p->stats.copy_threads = job.copy_threads * ds->ndev;
             for (int i = 0; i < ds->ndev; i++) {
+                if (dts[i].scatter_ms > p->stats.scatter_ms) p->stats.scatter_ms = (float) dts[i].scatter_ms;
+                if (dts[i].wait_ms > p->stats.wait_ms) p->stats.wait_ms = (float) dts[i].wait_ms;
+                p->stats.thp_chunks += dts[i].thp_chunks;
                 if (dts[i].kernel_ms > p->stats.kernel_ms) p->stats.kernel_ms = dts[i].kernel_ms;
                 p->stats.launches += dts[i].launches;
                 p->stats.d2h_bytes += dts[i].d2h_bytes;
@@ -1073,6 +1141,7 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
                 if (dts[i].variant) p->stats.kernel_variant = dts[i].variant;
             }
             p->stats.devices = ds->ndev;
+            p->stats.shard_rank = p->shard_rank; p->stats.shard_world = p->shard_world;
             if (job.failed) { gkm_set_error("%s", job.err); rc = 1; }
         }
     }
@@ -1204,7 +1273,7 @@ static int resident_symmetric(gkmb200_problem *p)
     CK(cudaSetDevice(ds->dev[0]));
     if (!im->full) {
         im->full_ld = ((size_t) n + 15) & ~(size_t) 15;
-        CK(cudaMalloc(&im->full, im->full_ld * (size_t) n * sizeof(double)));
+        CK(dev_malloc(g, (void **) &im->full, im->full_ld * (size_t) n * sizeof(double)));
     }
     const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
     const int maxc = n / 16 + 2;
@@ -1263,7 +1332,7 @@ extern "C" int gkm_dev_svm_cv(gkmb200_problem *p, const double *kmat, long ld, i
         if (!rc) {
             gkm_gpu *g = &g_gpu[g_sel[0]];
             rc = gpu_prepare(g, g_sel[0], 0, 0);
-            if (!rc && cudaMalloc(&d_K, sizeof(double) * (size_t) n * (size_t) n) != cudaSuccess) { gkm_set_error("CUDA: svm matrix: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+            if (!rc && dev_malloc(g, (void **) &d_K, sizeof(double) * (size_t) n * (size_t) n) != cudaSuccess) { gkm_set_error("CUDA: svm matrix: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
             if (!rc && cudaMemcpy2DAsync(d_K, sizeof(double) * (size_t) n, kmat, sizeof(double) * (size_t) ld, sizeof(double) * (size_t) n, (size_t) n,
                                          cudaMemcpyHostToDevice, g->sc) != cudaSuccess) { gkm_set_error("CUDA: svm matrix upload: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
             if (!rc) rc = gkm_svm_run(d_K, (long long) n, n, ntasks, tasks, train_idx, train_y, test_idx, C, eps, max_iter, scores, fits, alpha, g->sc);
@@ -1293,7 +1362,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
             if (cudaSetDevice(ds->dev[0]) != cudaSuccess) { rc = 1; break; }
             if (!im->full) {
                 im->full_ld = ((size_t) n + 15) & ~(size_t) 15;
-                if (cudaMalloc(&im->full, im->full_ld * (size_t) n * sizeof(double)) != cudaSuccess) { rc = 1; break; }
+                if (dev_malloc(g, (void **) &im->full, im->full_ld * (size_t) n * sizeof(double)) != cudaSuccess) { rc = 1; break; }
             }
             if (flush_l2 && !g->d_flush && cudaMalloc(&g->d_flush, GKM_FLUSH_BYTES) != cudaSuccess) { rc = 1; break; }
         } while (0);

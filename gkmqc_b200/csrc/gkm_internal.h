@@ -39,6 +39,7 @@ struct gkmb200_problem {
     int npos;      /* set by read_problem */
     int *len;      /* bases per sequence */
     uint8_t **code;/* forward strand, base codes 0..3 (A,C,G,T) */
+    char **sid;    /* FASTA record ids (first token after '>', libgkm.c:1287-1292); NULL for sequences added in memory */
     int nonacgt;   /* characters mapped to 'A' so far */
 
     /* packed image (gkm_pack_problem) */
@@ -57,6 +58,7 @@ struct gkmb200_problem {
 };
 
 int gkm_problem_reserve(gkmb200_problem *p, int extra);
+void gkm_problem_shard_from_env(gkmb200_problem *p); /* GKM_SHARD="rank/world": gkm_main_pywrapper only */
 int gkm_pack_problem(gkmb200_problem *p);
 void gkm_unpack_problem(gkmb200_problem *p);
 

@@ -30,13 +30,10 @@ gkmb200_problem *gkmb200_problem_new(const gkm_parameter *param)
     p->param = *param;
     p->nbins = param->d + 1;
     p->weighted = (param->kernel_type == EST_TRUNC_PW || param->kernel_type == EST_TRUNC_PW_RBF);
+    /* every problem computes all of its chunks unless told otherwise (gkmb200_problem_set_shard, or the
+     * environment for gkm_main_pywrapper's own problem: gkm_problem_shard_from_env) */
     p->shard_rank = 0;
     p->shard_world = 1;
-    { /* one process per GPU (torchrun-style launches): GKM_SHARD="rank/world" shards the chunk list */
-        const char *sh = getenv("GKM_SHARD");
-        int r = 0, w = 1;
-        if (sh && sscanf(sh, "%d/%d", &r, &w) == 2 && w >= 1 && r >= 0 && r < w) { p->shard_rank = r; p->shard_world = w; }
-    }
     if (gkm_calc_weights(param->kernel_type, param->L, param->k, p->w)) {
         gkm_set_error("cannot compute weights for L=%d k=%d", param->L, param->k);
         free(p);
@@ -45,13 +42,25 @@ gkmb200_problem *gkmb200_problem_new(const gkm_parameter *param)
     return p;
 }
 
+/* One process per GPU (torchrun-style launches): GKM_SHARD="rank/world" makes this process compute only the
+ * chunks it owns.  Read for the problem of gkm_main_pywrapper alone -- the caller that set the variable knows that
+ * its matrix is partial; the problems behind the libgkm ABI (gkmkernel_kernelfunc_batch_all: one row, one chunk)
+ * and the CLI would silently return zeros on every rank but one. */
+void gkm_problem_shard_from_env(gkmb200_problem *p)
+{
+    const char *sh = getenv("GKM_SHARD");
+    int r = 0, w = 1;
+    if (sh && sscanf(sh, "%d/%d", &r, &w) == 2 && w >= 1 && r >= 0 && r < w) { p->shard_rank = r; p->shard_world = w; }
+}
+
 void gkmb200_problem_free(gkmb200_problem *p)
 {
     if (!p) return;
     gkm_dev_release(p);
     gkm_unpack_problem(p);
-    for (int i = 0; i < p->n; i++) free(p->code[i]);
+    for (int i = 0; i < p->n; i++) { free(p->code[i]); if (p->sid) free(p->sid[i]); }
     free(p->code);
+    free(p->sid);
     free(p->len);
     free(p);
 }
@@ -67,6 +76,10 @@ int gkm_problem_reserve(gkmb200_problem *p, int extra)
     uint8_t **code = (uint8_t **) realloc(p->code, sizeof(uint8_t *) * (size_t) cap);
     if (!code) return 1;
     p->code = code;
+    char **sid = (char **) realloc(p->sid, sizeof(char *) * (size_t) cap);
+    if (!sid) return 1;
+    for (int i = p->cap; i < cap; i++) sid[i] = NULL;
+    p->sid = sid;
     p->cap = cap;
     return 0;
 }
@@ -138,8 +151,20 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
     }
     p->len[p->n] = len;
     p->code[p->n] = c;
+    p->sid[p->n] = NULL;
     gkm_unpack_problem(p); /* packed image is stale now */
     return p->n++;
+}
+
+static int fasta_add(gkmb200_problem *p, const char *seq, int seqlen, const char *id, int idlen)
+{
+    const int i = gkmb200_problem_add(p, seq, seqlen);
+    if (i >= 0 && id) {
+        char *s = (char *) malloc((size_t) idlen + 1);
+        if (s) { memcpy(s, id, (size_t) idlen); s[idlen] = '\0'; }
+        p->sid[i] = s;
+    }
+    return i;
 }
 
 /* one FASTA file; the line discipline of libgkm.c:1207-1225,1268-1304:
@@ -172,6 +197,7 @@ int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
     }
     fclose(fp);
     int seqlen = 0, open_rec = 0, added = 0, warned = 0, fail = 0;
+    const char *id0 = NULL; int idlen = 0; /* id of the open record: the first token of its header line behind '>' */
     const char *cur = buf, *end = buf + got;
     while (!fail && cur < end) {
         const char *nl = (const char *) memchr(cur, '\n', (size_t) (end - cur));
@@ -184,10 +210,13 @@ int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
         if (nul) le = nul;
         if (le > cur && cur[0] == '>') {
             if (open_rec) {
-                if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
+                if (fasta_add(p, seq, seqlen, id0, idlen) < 0) fail = 1; else added++;
             }
             if ((added % 1000) == 0) gkm_log(GKM_LOG_INFO, "reading... %d", added);
             open_rec = 1; seqlen = 0; warned = 0;
+            /* strtok(line, " \t\r\n") then +1 (libgkm.c:1287-1292): the token that starts with '>' */
+            id0 = cur + 1; idlen = 0;
+            while (id0 + idlen < le && id0[idlen] != ' ' && id0[idlen] != '\t') idlen++;
         } else if (open_rec && seqlen < GKM_MAX_BASES) {
             size_t ll = (size_t) (le - cur);
             if ((size_t) seqlen + ll > GKM_MAX_BASES) {
@@ -203,7 +232,7 @@ int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path)
         cur = next;
     }
     if (!fail && open_rec) {
-        if (gkmb200_problem_add(p, seq, seqlen) < 0) fail = 1; else added++;
+        if (fasta_add(p, seq, seqlen, id0, idlen) < 0) fail = 1; else added++;
     }
     gkm_log(GKM_LOG_INFO, "reading... done");
     free(buf);
@@ -247,6 +276,8 @@ int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *ne
                     p->len[p->n] = job.q->len[i];
                     p->code[p->n] = job.q->code[i];
                     job.q->code[i] = NULL;
+                    p->sid[p->n] = job.q->sid[i];
+                    job.q->sid[i] = NULL;
                     p->n++;
                 }
                 p->nonacgt += job.q->nonacgt;
@@ -271,6 +302,13 @@ int gkmb200_problem_seqlen(const gkmb200_problem *p, int i)
 {
     if (!p || i < 0 || i >= p->n) return -1;
     return p->len[i];
+}
+
+/* id of a record read from FASTA (gkm_data.sid: the first token behind '>', libgkm.c:1287-1292); NULL for in-memory sequences */
+const char *gkmb200_problem_sid(const gkmb200_problem *p, int i)
+{
+    if (!p || i < 0 || i >= p->n) return NULL;
+    return p->sid[i];
 }
 
 /* the byte arrays the reference would hold in gkm_data.seq / seq_rc (codes 1..4) */

@@ -70,12 +70,14 @@ int main(int argc, char **argv)
     (void) threads;
     for (int r0 = 0; r0 < n; r0 += band) {
         const int r1 = (r0 + band < n) ? r0 + band : n;
-        if (gkmb200_kernel_block(p, r0, r1 - r0, 0, r1, 1, buf, r1)) {
+        /* always the full column range: the index blocks partition the columns of the first call, and a range that
+         * grew from band to band made every band rebuild all of them */
+        if (gkmb200_kernel_block(p, r0, r1 - r0, 0, n, 1, buf, n)) {
             fprintf(stderr, "gkmkern: %s\n", gkmb200_last_error());
             return 1;
         }
         for (int a = r0; a < r1; a++) {
-            const double *row = buf + (size_t) (a - r0) * (size_t) r1;
+            const double *row = buf + (size_t) (a - r0) * (size_t) n;
             if (binary) {
                 fwrite(row, sizeof(double), (size_t) a, fo);
             } else {

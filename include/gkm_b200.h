@@ -34,7 +34,11 @@ typedef struct gkmb200_stats {
     long long d2h_bytes;     /* bytes copied device->host by the last compute call */
     int devices;             /* GPUs used */
     int kernel_variant;      /* 1 = lmer (XOR/LOP3/POPC per pair), 2 = diag (bit-sliced diagonals), 3 = mma (tcgen05), 4 = index */
-    int reserved[6];
+    int shard_rank, shard_world; /* the call computed only the chunks of shard rank/world (1 = everything) */
+    int copy_threads;        /* host threads that copied finished chunks into the caller's rows */
+    int thp_chunks;          /* chunks whose destination rows got the transparent-huge-page hint */
+    float scatter_ms;        /* host time spent in that copy (page faults of a fresh matrix included), slowest GPU thread */
+    float wait_ms;           /* host time spent waiting for the GPU, slowest GPU thread */
 } gkmb200_stats;
 
 /* ---- process-wide ---- */
@@ -44,6 +48,7 @@ int gkmb200_device_count(void);                      /* visible CUDA devices of 
 int gkmb200_set_devices(const int *ids, int n);      /* default: env GKM_DEVICES ("0,1,.."), else all */
 int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag|mma|index ; "max_L" = 12|16 ; "tile_rows", "chunk_mb", "index_cols", "index_wide" */
 void gkmb200_set_verbosity(int level);               /* 0..4 like gkmOpt.verbosity */
+int gkmb200_trim(void);                              /* give the cached device blocks of every GPU back to the driver */
 
 /* ---- host-only arithmetic of the path (no GPU needed) ---- */
 const char *gkmb200_check_parameter(const gkm_parameter *param); /* NULL if ok; the gate of gkmkern_pylib.c:38-64 */
@@ -58,6 +63,7 @@ int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path);        /* 
 int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *negfile); /* n_pos, or -1 (libgkm.c:1316) */
 int gkmb200_problem_size(const gkmb200_problem *p);
 int gkmb200_problem_seqlen(const gkmb200_problem *p, int i);
+const char *gkmb200_problem_sid(const gkmb200_problem *p, int i);            /* FASTA id (libgkm.c:1287-1292) or NULL */
 int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t *rc);   /* 1..4 like gkm_data.seq */
 int gkmb200_problem_get_weights(const gkmb200_problem *p, double *w);        /* d+1 values */
 int gkmb200_problem_set_shard(gkmb200_problem *p, int rank, int world);      /* this process computes chunk c iff owner(c) == rank */
@@ -69,7 +75,8 @@ int gkmb200_problem_sqnorm(gkmb200_problem *p, double *out);                 /* 
 /* ---- the kernel ---- */
 /* triangular matrix into caller rows: rows[a][j] = K(a,j) for j<a, rows[a][a] = 1 (gkmkern_pylib.c:169-221).
  * copy_threads is a lower bound on the host threads that scatter finished chunks into the rows: the library uses
- * the cores of its affinity mask, 16 at most (env GKM_COPY_THREADS overrides; gkm_device.cu:gkm_copy_threads) */
+ * the cores of its affinity mask, divided by the ranks of a sharded run (env GKM_COPY_THREADS overrides;
+ * gkm_device.cu:gkm_copy_threads_shared) */
 int gkmb200_kernel_lower(gkmb200_problem *p, double **rows, int copy_threads);
 /* dense block: out[(r-row0)*ld + (c-col0)] = K(r,c).  lower != 0: only c < r is written (and r == c gets 1.0).
  * With the SVs at ids [0,nSV) this is gkmkernel_kernelfunc_batch_all(a, 0, nSV) for a whole batch of rows. */

@@ -89,9 +89,16 @@ def test_fasta_quirks(tmp_path, product_lib):
     with capi.Problem(2, 11, 7, 3) as P:
         assert P.read_fasta(str(p)) == 4
         assert [P.seqlen(i) for i in range(4)] == [16, 16, 2047, 13]
+        assert [P.sid(i) for i in range(4)] == [b"id1", b"id2", b"id3", b"id4"]  # first token behind '>' (libgkm.c:1287-1292)
+        assert P.add("ACGTACGTACGTACGT") == 4 and P.sid(4) is None
         assert list(P.codes(1)[0]) == [1, 2, 3, 4, 1, 1, 1, 2, 3, 4, 1, 2, 3, 4, 1, 2]  # n -> A
         with pytest.raises(capi.GkmError):
             P.read_fasta(str(tmp_path / "nope.fa"))
+    ids = tmp_path / "ids.fa"
+    ids.write_bytes(b">\tchr1:5-20 extra\nACGTACGTACGTAC\n> spaced\nACGTACGTACGTAC\n>tab\there\r\nACGTACGTACGTAC\n")
+    with capi.Problem(2, 11, 7, 3) as P:
+        assert P.read_fasta(str(ids)) == 3
+        assert [P.sid(i) for i in range(3)] == [b"", b"", b"tab"]
     short = tmp_path / "s.fa"
     short.write_text(">x\nACGT\n")
     with capi.Problem(2, 11, 7, 3) as P:
@@ -177,18 +184,33 @@ def test_svm_task_preparation_follows_libsvm_grouping():
 
 def test_copy_threads_policy(monkeypatch):
     """the reference's nthreads (default 1 in bin/gkmqc.py) is only a lower bound on the copy-out threads: the library
-    takes the cores of its affinity mask, 16 at most; GKM_COPY_THREADS overrides (gkm_device.cu:gkm_copy_threads)"""
+    takes the cores of its affinity mask (no fixed cap: the 8-GPU box has 32), shared among the ranks of a
+    one-process-per-GPU run; GKM_COPY_THREADS overrides (gkm_device.cu:gkm_copy_threads_shared)"""
     import ctypes
     lib = capi.load()
-    lib.gkm_copy_threads.restype = ctypes.c_int
+    for f in (lib.gkm_copy_threads, lib.gkm_copy_threads_shared):
+        f.restype = ctypes.c_int
     lib.gkm_copy_threads.argtypes = [ctypes.c_int]
+    lib.gkm_copy_threads_shared.argtypes = [ctypes.c_int, ctypes.c_int]
     monkeypatch.delenv("GKM_COPY_THREADS", raising=False)
-    avail = min(16, len(os.sched_getaffinity(0)))
+    avail = min(64, len(os.sched_getaffinity(0)))
     assert lib.gkm_copy_threads(1) == avail
-    assert lib.gkm_copy_threads(avail + 3) == avail + 3
+    assert lib.gkm_copy_threads(avail + 3) == min(64, avail + 3)
     assert lib.gkm_copy_threads(1000) == 64
+    assert lib.gkm_copy_threads_shared(1, 2) == max(1, avail // 2)
+    assert lib.gkm_copy_threads_shared(1, 8) == max(1, avail // 8)
+    assert lib.gkm_copy_threads_shared(3, 10 ** 6) == 3          # never below what the caller asked for
     monkeypatch.setenv("GKM_COPY_THREADS", "5")
-    assert lib.gkm_copy_threads(1) == 5 and lib.gkm_copy_threads(32) == 5
+    assert lib.gkm_copy_threads(1) == 5 and lib.gkm_copy_threads_shared(32, 8) == 5
+    # under taskset -c 0 the affinity mask is what counts, not the machine
+    import subprocess, sys
+    code = ("import ctypes,sys; sys.path.insert(0, %r); from gkmqc_b200 import capi; l = capi.load(); "
+            "l.gkm_copy_threads.restype = ctypes.c_int; print(l.gkm_copy_threads(1))" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = {k: v for k, v in os.environ.items() if k != "GKM_COPY_THREADS"}
+    cpu = sorted(os.sched_getaffinity(0))[0]
+    out = subprocess.run(["taskset", "-c", str(cpu), sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    if out.returncode == 0:   # taskset may be missing in a minimal image
+        assert out.stdout.strip() == "1"
 
 
 def test_two_file_read_equals_two_sequential_reads(tmp_path):
