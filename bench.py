@@ -3,19 +3,25 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); torch.distributed is used for the
-barrier and the max-over-ranks only -- the path has no collective.  A "step" is one full pass of the
-hot path: the strict lower triangle of the kernel matrix of the workload below.
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); torch.distributed is used for the barrier and the
+max-over-ranks only -- the path has no collective.  A "step" is one full pass of the hot path: the strict lower
+triangle of the kernel matrix of the workload below.
 
-Workload (BASELINE.json configs[1]): 5 000 + 5 000 synthetic 300-bp sequences, full 10k x 10k kernel,
-kernel type 2 (EST_TRUNC), L=11 k=7 d=3.  For N > 1 the matrix grows so that the work per GPU stays
-fixed (n = 10 000 * sqrt(N): weak scaling) and its chunks of row tiles are sharded over the ranks.
+Workload (BASELINE.json configs[3], the north-star target): 25 000 + 25 000 synthetic 300-bp sequences, the full
+50k x 50k kernel matrix, kernel type 2 (EST_TRUNC), L=11 k=7 d=3 -- the SAME problem at every N ("scaling": "strong"):
+its chunks of row tiles are sharded round-robin over the ranks.
 
-  value  device-resident: packed sequences and the output matrix stay in HBM, CUDA-event time of the pass
-  e2e    gkm_main_pywrapper(FASTA files -> caller's numpy rows), wall clock: file parse, H2D, kernels,
-         D2H and the copy into the caller's matrix all inside the timed region
+  value     device-resident: packed sequences and the output matrix stay in HBM, CUDA-event time of the pass
+  e2e       gkm_main_pywrapper(FASTA files -> caller's fresh numpy rows), wall clock: file parse, pack, H2D, sqnorm,
+            index build, kernels, D2H and the copy into the caller's matrix all inside the timed region
+  parity    rows of the matrix the e2e call RETURNED (and their integer histograms through gkmb200_hist_block)
+            against the unmodified reference (oracle/_ref) -- a mismatch makes the run exit non-zero
+  secondary configs[1] (10k, resident + e2e + one full unsampled run of the reference's own gkm_main_pywrapper),
+            gkmQC's real default (wgkm L=10 k=6 d=3 on 600-bp sequences), non-uniform input, configs[4] batch scoring
 """
 import argparse
+import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -30,28 +36,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 L, K, D, KTYPE, SEQLEN = 11, 7, 3, 2, 300
-BASE_N = 10000
+BASE_N = 50000          # BASELINE.json configs[3]
+SECOND_N = 10000        # BASELINE.json configs[1]
+NSV, NTEST_PER_GPU = 10000, 125000   # BASELINE.json configs[4]: 1M test x 10k SV over 8 GPUs = 125k test rows per GPU
 PAIRS_PER_ENTRY = (SEQLEN - L + 1) * 2 * (SEQLEN - L + 1)   # 168 200 L-mer pair comparisons
 INT_OPS_PER_PAIR = 5                                        # canonical XOR/SHR/LOP3/POPC/ISETP count
+METRIC = "gkm kernel entries/sec (300bp, l=11 k=7 d=3)"
+VARIANTS = {1: "lmer", 2: "diag", 3: "mma", 4: "index"}
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
-def synth(n, seed=1234):
+def synth(n, seed=1234, seqlen=SEQLEN):
     rng = np.random.default_rng(seed)
-    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-    return acgt[rng.integers(0, 4, size=(n, SEQLEN))]
+    return ACGT[rng.integers(0, 4, size=(n, seqlen))]
 
 
-def write_problem(tmp, n):
-    arr = synth(n)
+def write_fasta(path, arr, first_id):
+    """>s<i>\\n<bases>\\n per row, assembled in numpy (50k records in ~50 ms)"""
+    n, ln = arr.shape
+    ids = [b">s%d\n" % i for i in range(first_id, first_id + n)]
+    with open(path, "wb") as f:
+        rows = [None] * (2 * n)
+        rows[0::2] = ids
+        body = np.concatenate((arr, np.full((n, 1), 10, np.uint8)), axis=1)
+        rows[1::2] = [body[i].tobytes() for i in range(n)]
+        f.write(b"".join(rows))
+
+
+def write_problem(tmp, n, seed=1234, seqlen=SEQLEN, tag=""):
+    arr = synth(n, seed, seqlen)
     half = n // 2
-    paths = []
-    for name, lo, hi in (("pos.fa", 0, half), ("neg.fa", half, n)):
-        p = os.path.join(tmp, name)
-        with open(p, "w") as f:
-            for i in range(lo, hi):
-                f.write(">s%d\n%s\n" % (i, arr[i].tobytes().decode()))
-        paths.append(p)
-    return paths
+    pos, neg = os.path.join(tmp, "pos%s.fa" % tag), os.path.join(tmp, "neg%s.fa" % tag)
+    write_fasta(pos, arr[:half], 0)
+    write_fasta(neg, arr[half:], half)
+    return pos, neg
 
 
 class ClockSampler(threading.Thread):
@@ -130,24 +148,22 @@ def dist_setup(world):
     return dist
 
 
-def dist_max(dist, x):
+def _dist_reduce(dist, x, op):
     if dist is None:
         return x
     import torch
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
     t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
+
+
+def dist_max(dist, x):
+    return _dist_reduce(dist, x, "MAX")
 
 
 def dist_sum(dist, x):
-    if dist is None:
-        return x
-    import torch
-    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    t = torch.tensor([x], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    return _dist_reduce(dist, x, "SUM")
 
 
 def dist_barrier(dist):
@@ -155,59 +171,133 @@ def dist_barrier(dist):
         dist.barrier()
 
 
-def index_probe_counts(L, d, slot_bytes):
+def index_probe_counts(L_, d_, slot_bytes):
     """probes and distinct 32-byte sectors per query L-mer of the index variant, from the product's own mask list
-    (slot_bytes = 8: compact slots of the unit-weight kernel types, 16: slots with weights)"""
+    (slot_bytes = 8: compact slots, 16: wide slots with weights)"""
     from gkmqc_b200 import capi
-    import ctypes
     lib = capi.load()
     lib.gkm_idx_delta_count.restype = ctypes.c_longlong
     lib.gkm_idx_deltas.restype = ctypes.c_longlong
     lib.gkm_idx_deltas.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong]
-    nd = lib.gkm_idx_delta_count(L, d)
+    nd = lib.gkm_idx_delta_count(L_, d_)
     a = np.zeros(nd, dtype=np.uint32)
-    assert lib.gkm_idx_deltas(L, d, a.ctypes.data, nd) == nd
+    assert lib.gkm_idx_deltas(L_, d_, a.ctypes.data, nd) == nd
     return int(nd), int(len(np.unique((a & 0x0FFFFFFF) >> (2 if slot_bytes == 8 else 1))))   # 32-byte sector = 4 or 2 slots
 
 
-def measured_hbm():
+def measured_peaks():
     try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def kernel_source_hash():
+    """identity of the dominant kernel's source: an ncu capture is only attached to a bench line of the same code"""
+    h = hashlib.sha256()
+    for f in ("gkm_index.cu", "gkm_index.h", "gkm_index_dev.h"):
+        h.update(open(os.path.join(ROOT, "gkmqc_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def thp_mode():
+    try:
+        return open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip()
     except Exception:
         return None
 
 
-def cpu_reference_rate(pos, neg, n, budget_s, threads):
-    """the reference's own CPU path (oracle/_ref, unmodified sources) on a stated subsample of rows of the SAME
-    problem (tree over all n sequences); falls back to the oracle port when the reference was not built here"""
+# ---------------------------------------------------------------------------------------- the reference on the CPU
+def open_reference(pos, neg, ktype=KTYPE, L_=L, k_=K, d_=D):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    if pyoracle.have_ref():
-        h = pyoracle.RefHook(pos, neg, KTYPE, L, K, D)
-        try:
-            probe = np.linspace(n // 4, n - 1, 2 * threads).astype(np.int32)
-            t, _ = h.rows_timed(probe, threads)
-            rate = float(probe.sum()) / max(t, 1e-9)
-            want = max(rate * budget_s, float(probe.sum()))
-            nrows = int(min(n - 1, max(threads, want / (n / 2))))
-            rows = np.unique(np.linspace(1, n - 1, nrows).astype(np.int32))
-            t, cs = h.rows_timed(rows, threads)
-            entries = int(rows.sum())
-        finally:
-            h.close()
-        return dict(value=entries / t, unit="entries/s", cores=threads, kind="reference",
-                    sample="%d evenly spaced rows of the %d-sequence problem (%d entries, %.1f s), k-mer tree over all sequences"
-                           % (len(rows), n, entries, t))
+    if not pyoracle.have_ref():
+        return None
+    t0 = time.time()
+    h = pyoracle.RefHook(pos, neg, ktype, L_, k_, d_)
+    h.open_s = time.time() - t0
+    return h
+
+
+def reference_rate(h, n, budget_s, threads, endcap=0):
+    """the reference's own row loop (oracle/_ref, unmodified sources) on evenly spaced rows of the OPEN problem (k-mer
+    tree over all of its sequences), sized to about budget_s seconds"""
+    cost = (lambda rows: float(len(rows)) * endcap) if endcap else (lambda rows: float(rows.sum()))
+    lo = n // 4 if not endcap else endcap
+    probe = np.linspace(lo, n - 1, 2 * threads).astype(np.int32)
+    t, _ = h.rows_timed(probe, threads, endcap)
+    rate = cost(probe) / max(t, 1e-9)
+    per_row = (n / 2.0) if not endcap else float(endcap)
+    nrows = int(min(n - 1 - (endcap or 0), max(threads, rate * budget_s / per_row)))
+    rows = np.unique(np.linspace(1 if not endcap else endcap, n - 1, nrows).astype(np.int32))
+    t, _ = h.rows_timed(rows, threads, endcap)
+    entries = cost(rows)
+    return dict(value=entries / t, unit="entries/s", cores=threads, kind="reference",
+                sample="%d evenly spaced rows of the %d-sequence problem (%d entries, %.1f s on %d threads), k-mer tree over all sequences"
+                       % (len(rows), n, int(entries), t, threads))
+
+
+def port_rate(pos, neg, n):
+    """fallback where the reference was not built: the brute-force oracle port"""
+    import pyoracle
     o = pyoracle.Oracle(KTYPE, L, K, D)
     o.read_problem(pos, neg)
     rows = np.linspace(1, n - 1, 4).astype(np.int32)
     t0 = time.time()
     o.rect(rows, 256, with_hist=False)
     t = time.time() - t0
-    return dict(value=len(rows) * 256 / t, unit="entries/s", cores=os.cpu_count(), kind="port",
+    return dict(value=len(rows) * 256 / t, unit="entries/s", cores=1, kind="port",
                 sample="%d rows x 256 columns by the brute-force oracle port (%.1f s)" % (len(rows), t))
 
 
+def parity_rows(n, blk_cols, nblk, want=96, seed=7):
+    """rows 1 and n-1, both sides of every column-block boundary of the index, both sides of chunk boundaries
+    (multiples of 148 rows: one CTA per SM and wave; chunks hold up to 4 waves) spread over the matrix, random rows"""
+    rows = {1, 2, n - 2, n - 1}
+    for k in range(1, max(nblk, 1)):
+        cb = k * blk_cols
+        rows.update(r for r in (cb - 1, cb, cb + 1) if 0 < r < n)
+    waves = np.unique(np.linspace(1, (n - 1) // 148, 14).astype(int))
+    for w in waves:
+        rows.update(r for r in (148 * w - 1, 148 * w) if 0 < r < n)
+    for w in np.unique(np.linspace(1, (n - 1) // 592, 6).astype(int)):
+        rows.update(r for r in (592 * w - 1, 592 * w) if 0 < r < n)
+    rng = np.random.default_rng(seed)
+    while len(rows) < min(want, n - 1):
+        rows.add(int(rng.integers(1, n)))
+    return np.array(sorted(rows), np.int32)
+
+
+def check_parity(h, kmat, hist_of_rows, n, layout, threads, owned_only=True):
+    """rows of the matrix the product returned (and their integer histograms) against the reference's own numbers"""
+    nblk, blk_cols = layout[0], layout[1] or n
+    rows = parity_rows(n, blk_cols, nblk)
+    if owned_only:   # a sharded call fills only the rows of this rank's chunks: their unit diagonal tells which
+        rows = rows[[kmat[r, r] == 1.0 for r in rows]]
+    Kref, Href, t = h.rows_values(rows, threads)
+    max_rel, hist_ok, bad = 0.0, True, []
+    for i, r in enumerate(rows):
+        got, ref = kmat[r, :r], Kref[i, :r]
+        if not np.array_equal(got, ref):
+            rel = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+            max_rel = max(max_rel, rel)
+            bad.append(int(r))
+        if kmat[r, r] != 1.0 or (r + 1 < kmat.shape[1] and kmat[r, r + 1:].any()):
+            bad.append(int(r))   # unit diagonal, untouched upper triangle (gkmkern_pylib.c:169-221)
+        Hg = hist_of_rows(int(r))            # [r, d+1]
+        if not np.array_equal(Hg, Href[i, :, :r].T):
+            hist_ok = False
+            bad.append(int(r))
+    hits = None
+    return {"rows": int(len(rows)), "entries": int(rows.sum()), "hist_bit_exact": bool(hist_ok), "kmat_max_rel": max_rel,
+            "kmat_bit_identical": max_rel == 0.0 and not bad, "mismatching_rows": sorted(set(bad))[:8],
+            "against": "oracle/_ref (unmodified reference): gkmkernel_kernelfunc_batch_all for the doubles, kmertree_dfs mmprofile for the integers",
+            "row_set": "rows 1, 2, n-2, n-1; cb-1, cb, cb+1 of every index column block (%d blocks of %d columns); both sides of "
+                       "chunk boundaries (multiples of 148 / 592 rows); random rows" % (nblk, blk_cols),
+            "reference_seconds": t, "ok": bool(hist_ok and max_rel <= 1e-9 and not bad)}, hits
+
+
+# ---------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,42 +307,57 @@ def main():
     ap.add_argument("--n", type=int, default=0, help="override the number of sequences (debugging only)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-full", action="store_true", help="skip the full unsampled reference run of configs[1] (~1 min)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="profiling runs only")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    n = args.n or int(round(BASE_N * np.sqrt(world) / 16.0)) * 16
+    n = args.n or BASE_N
     total_entries = n * (n - 1) // 2
-    config = {"workload": "gkm kernel matrix, %d synthetic 300-bp seqs (%d pos + %d neg), strict lower triangle, "
-                          "kernel type 2 (EST_TRUNC) L=11 k=7 d=3" % (n, n // 2, n - n // 2),
+    config = {"workload": "BASELINE configs[3]: gkm kernel matrix, %d synthetic 300-bp seqs (%d pos + %d neg), strict lower triangle "
+                          "(%d x %d), kernel type 2 (EST_TRUNC) L=11 k=7 d=3; the same problem at every N" % (n, n // 2, n - n // 2, n, n),
               "n_seqs": n, "entries_per_step": total_entries, "lmer_pairs_per_entry": PAIRS_PER_ENTRY,
               "sharding": "chunks of row tiles round-robin over %d rank(s), no collective" % world,
               "l2": "L2 flushed (256 MB memset) before every timed pass; %d MB of output written per pass"
-                    % (n * n * 8 // (1 << 20))}
+                    % (n * n * 8 // (1 << 20)),
+              "resident_excludes": "pack + H2D + sqnorm + index build happen once before the timed passes (about 3 % of a pass at 10k; "
+                                   "e2e includes them every step)"}
 
     tmp = tempfile.mkdtemp(prefix="gkmbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     pos, neg = write_problem(tmp, n)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = os.cpu_count() or 1
         budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
-        vals = []
-        for it in range(args.warmup + args.steps):
-            r = cpu_reference_rate(pos, neg, n, budget, threads)
-            if it >= args.warmup:
-                vals.append(r["value"])
+        h = open_reference(pos, neg)
+        vals, r = [], None
+        if h is None:
+            r = port_rate(pos, neg, n)
+            vals = [r["value"]]
+        else:
+            try:
+                for it in range(args.warmup + args.steps):
+                    r = reference_rate(h, n, budget, threads)
+                    if it >= args.warmup:
+                        vals.append(r["value"])
+                r["setup_s"] = h.open_s
+                r["setup"] = "read FASTA, per-sequence sqnorm and k-mer tree over all %d sequences: %.1f s, once, not in the rate" % (n, h.open_s)
+            finally:
+                h.close()
         v = float(np.mean(vals))
         r["value"] = v
         per_step_ms = 1e3 * total_entries / v
         print(json.dumps({
-            "impl": "reference", "metric": "gkm kernel entries/sec (300bp, l=11 k=7 d=3)", "value": v, "unit": "entries/s",
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "entries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step_ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": config, "cpu_baseline": r,
             "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -263,11 +368,12 @@ def main():
     lib = capi.load()
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no B200 visible and the product has no CPU fallback: " + capi.last_error())
-    ids = (capi.ctypes.c_int * 1)(local_rank)
+    ids = (ctypes.c_int * 1)(local_rank)
     if lib.gkmb200_set_devices(ids, 1) != 0:
         raise SystemExit(capi.last_error())
-    os.environ["GKM_SHARD"] = "%d/%d" % (rank, world)   # read by gkm_main_pywrapper's problem
+    os.environ["GKM_SHARD"] = "%d/%d" % (rank, world)   # read by gkm_main_pywrapper's problem only
     dist = dist_setup(world)
+    verbosity = int(os.environ.get("GKM_BENCH_V", "0"))
 
     P = capi.Problem(KTYPE, L, K, D)
     P.read(pos, neg)
@@ -283,83 +389,182 @@ def main():
     dist_barrier(dist)
     ms = P.bench_lower_resident(args.steps, max(args.warmup, 3), flush_l2=True)
     st = P.stats()
+    layout = P.index_layout()
     my_ms = float(ms.sum())
     dist_barrier(dist)
     t_max = dist_max(dist, my_ms)
-    launches = int(dist_sum(dist, st["launches"] * args.steps))
+    launches_per_step = int(dist_sum(dist, st["launches"]))
     value = total_entries * args.steps / (t_max * 1e-3)
     ms_per_step = t_max / args.steps
 
     # e2e: the drop-in call with host buffers (fresh, untouched output matrix every step, like gkmsvm.py:75)
     e2e_steps = args.e2e_steps or max(1, min(args.steps, 3))
-    walls = []
+    walls, kmat, e2e_stats = [], None, None
     h2d = d2h = 0
     for it in range(0 if args.no_e2e else 1 + e2e_steps):
+        kmat = None
         kmat = np.zeros((n, n))
         dist_barrier(dist)
         t0 = time.perf_counter()
         # nthreads is gkmQC's own default (bin/gkmqc.py:107,162: 1); the library sizes its copy-out threads by the host's cores
-        ret, kmat, npos, nneg = capi.main_pywrapper(pos, neg, kernel_type=KTYPE, L=L, k=K, d=D, nthreads=1, verbosity=int(os.environ.get("GKM_BENCH_V", "0")), kmat=kmat)
+        ret, kmat, npos, nneg = capi.main_pywrapper(pos, neg, kernel_type=KTYPE, L=L, k=K, d=D, nthreads=1, verbosity=verbosity, kmat=kmat)
         t1 = time.perf_counter()
         if ret != 0:
             raise SystemExit("gkm_main_pywrapper failed: " + capi.last_error())
         if it > 0:
             walls.append(dist_max(dist, t1 - t0))
         pst = capi.gkmb200_stats()
-        lib.gkmb200_get_stats(None, capi.ctypes.byref(pst))
+        lib.gkmb200_get_stats(None, ctypes.byref(pst))
         h2d, d2h = int(pst.h2d_bytes), int(pst.d2h_bytes)
-        del kmat
+        e2e_stats = pst.as_dict()
     if args.no_e2e:
         walls = [float("nan")]
     e2e_value = total_entries / float(np.mean(walls))
     h2d = int(dist_sum(dist, h2d))
     d2h = int(dist_sum(dist, d2h))
     clocks = sampler.finish() if rank == 0 else None
+
+    # ---- configs[4], batch scoring: every rank scores its own 125k test rows against the same 10k SVs,
+    # decision values reduced on the device; at N = 8 that is the 1M x 10k problem
+    scoring = None
+    if not args.no_secondary and not args.n:
+        sv = synth(NSV, seed=99)
+        test = synth(NTEST_PER_GPU, seed=1000 + rank)
+        alpha = np.random.default_rng(3).standard_normal(NSV)
+        with capi.Problem(KTYPE, L, K, D) as PS:
+            t0 = time.perf_counter()
+            PS.add_block(sv)
+            PS.add_block(test)
+            t_add = time.perf_counter() - t0
+            PS.upload()
+            PS.decision_values(NSV, 2368, 0, NSV, alpha, bias=-0.1)   # builds the SV index, sizes the scratch
+            dist_barrier(dist)
+            t0 = time.perf_counter()
+            dv = PS.decision_values(NSV, NTEST_PER_GPU, 0, NSV, alpha, bias=-0.1)
+            dt = dist_max(dist, time.perf_counter() - t0)
+            scoring = {"workload": "BASELINE configs[4]: %d test x %d SV per GPU (%d test rows in all), fused decision values"
+                                   % (NTEST_PER_GPU, NSV, NTEST_PER_GPU * world),
+                       "value": NTEST_PER_GPU * world * NSV / dt, "unit": "entries/s", "seconds": dt, "scaling": "weak",
+                       "add_sequences_s": t_add, "d2h_bytes": 8 * NTEST_PER_GPU * world}
+            if rank == 0 and not args.no_parity:   # sampled test rows against the reference: SVs first, then the rows
+                pick = np.unique(np.linspace(0, NTEST_PER_GPU - 1, 48).astype(int))
+                p2, n2 = os.path.join(tmp, "sv.fa"), os.path.join(tmp, "tests.fa")
+                write_fasta(p2, sv, 0)
+                write_fasta(n2, test[pick], NSV)
+                hs = open_reference(p2, n2)
+                if hs is not None:
+                    try:
+                        rows = np.arange(NSV, NSV + len(pick), dtype=np.int32)
+                        Kr, _, tref = hs.rows_values(rows, threads, endcap=NSV, with_hist=False)
+                        want = Kr @ alpha - 0.1
+                        rel = float(np.max(np.abs(dv[pick] - want) / np.maximum(np.abs(want), 1e-12)))
+                        scoring["parity"] = {"rows": int(len(pick)), "max_rel": rel, "ok": bool(rel <= 1e-9),
+                                             "against": "oracle/_ref batch_all(test, 0, nSV) @ alpha + b"}
+                        if not args.no_cpu_baseline and world == 1:
+                            rb = reference_rate(hs, NSV + len(pick), 6.0, threads, endcap=NSV)
+                            scoring["cpu_baseline"] = rb
+                    finally:
+                        hs.close()
+
     if dist is not None:   # the last collective is behind us: what follows is rank 0's own reporting
         dist.barrier()
         dist.destroy_process_group()
         dist = None
-
     if rank != 0:
         return
 
-    # roofline of the dominant kernel, by the variant that actually ran:
-    #   index: random 16-byte slot probes of an L2-resident table -> L1/L2 sector rate, measured by an in-run gather
-    #          micro-benchmark (neither HBM nor the tensor pipe binds: SURVEY.md 8d)
-    #   diag / lmer / mma: integer-ALU issue rate (LOP3 lane-ops/s measured in-run)
-    variant = {1: "lmer", 2: "diag", 3: "mma", 4: "index"}.get(st["kernel_variant"], "?")
+    # ------------------------------------------------------------------ parity of what the e2e call returned + CPU baseline
+    parity, cpu, hits_per_entry = None, None, None
+    href = None
+    if (not args.no_parity and kmat is not None) or not args.no_cpu_baseline:
+        href = open_reference(pos, neg)
+    try:
+        if not args.no_parity and kmat is not None and href is not None:
+            def hist_of_row(r):
+                return P.hist_block(r, 1, 0, r)[0]
+            P.set_shard(0, 1)
+            parity, _ = check_parity(href, kmat, hist_of_row, n, layout, threads, owned_only=world > 1)
+            parity["checked"] = "the numpy matrix returned by the timed gkm_main_pywrapper call (rank 0's rows)" + \
+                                (" of %d ranks" % world if world > 1 else "")
+            # hits per entry of this input, exactly: the histogram of one band of rows, all bins (unit weights: one per L-mer pair within d)
+            r0 = min(n - 1, 30000)
+            Hb = P.hist_block(r0, min(8, n - r0), 0, r0)
+            hits_per_entry = float(Hb.sum()) / float(Hb.shape[0] * Hb.shape[1])
+        elif not args.no_parity and kmat is not None:
+            parity = {"ok": None, "unavailable": "oracle/_ref was not built on this box"}
+        kmat = None
+        if world == 1 and not args.no_cpu_baseline:
+            if href is not None:
+                cpu = reference_rate(href, n, 15.0, threads)
+                one = reference_rate(href, n, 5.0, 1)   # the 1-thread figure beside the all-cores one
+                cpu["single_thread"] = {"value": one["value"], "unit": one["unit"], "kind": one["kind"], "sample": one["sample"]}
+                cpu["setup_s"] = href.open_s
+            else:
+                cpu = port_rate(pos, neg, n)
+    finally:
+        if href is not None:
+            href.close()
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    variant = VARIANTS.get(st["kernel_variant"], "?")
+    peaks = measured_peaks()
     peak_lop3 = capi.microbench("lop3")       # 1e9 lane-ops/s on this GPU, measured now
     peak_popc = capi.microbench("popc")
     per_gpu_entries_s = value / world
     int_alu_equiv = per_gpu_entries_s * PAIRS_PER_ENTRY * INT_OPS_PER_PAIR / 1e9
-    ncu = None
-    tf = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")   # written from the committed ncu --set full capture
+    ncu, traffic = None, None
+    tf = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")   # summary of the committed ncu --set full capture
     if os.path.exists(tf):
         try:
-            ncu = json.load(open(tf))
-            if ncu.get("variant", "diag") != variant:
-                ncu = None
-        except Exception:
-            ncu = None
-    traffic = ncu.get("dram_bytes_per_launch") if ncu else None
-    avg_launch_ms = ms_per_step / max(1, st["launches"])
+            cap = json.load(open(tf))
+            if cap.get("variant", "diag") == variant and cap.get("source_sha256") == kernel_source_hash():
+                ncu = dict(cap, source="committed capture profiles/ncu_dominant_kernel.json of this kernel source (sha256 %s), not measured in this run" % cap.get("source_sha256"))
+                traffic = cap.get("dram_bytes_per_launch")
+            else:
+                ncu = {"unavailable": "profiles/ncu_dominant_kernel.json was captured on another build of the kernel (variant %s, source %s; this run: %s, %s)"
+                                      % (cap.get("variant"), cap.get("source_sha256"), variant, kernel_source_hash())}
+        except Exception as e:
+            ncu = {"unavailable": str(e)}
+    launches_mine = max(1, st["launches"])
+    avg_launch_ms = ms_per_step / launches_mine   # two compute streams overlap launches: this is pass time / launches
     if variant == "index":
         peak_gather = capi.microbench("gather16")     # 1e9 random 16-byte gathers (one 32-byte sector each) per second
-        slot_bytes = 16 if KTYPE in (4, 5) else 8
-        probes, sectors = index_probe_counts(L, D, slot_bytes)
+        peak_atoms = capi.microbench("atoms7")        # 1e9 shared-memory atomic adds per second at ~7 active lanes of 32, random columns
+        probes, sectors = index_probe_counts(L, D, 8)
         nq = SEQLEN - L + 1
-        my_rows = n / world                            # chunks of equal row counts, round-robin over the ranks
-        sector_bytes = my_rows * nq * sectors * 32.0   # algorithmic: distinct sectors the probes of one pass must fetch
+        nblk, blk_cols = layout[0], max(1, layout[1])
+        # a row probes every column block that starts below it (strict lower triangle)
+        probed_blocks = float(sum(min(nblk, (a + blk_cols - 1) // blk_cols) for a in range(1, n))) / world
+        sector_bytes = probed_blocks * nq * sectors * 32.0   # algorithmic: distinct sectors the probes of one pass must fetch
         achieved = sector_bytes / (ms_per_step * 1e-3) / 1e9
-        roofline = {"bound": "l2_sector", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
+        hpe = hits_per_entry if hits_per_entry is not None else PAIRS_PER_ENTRY * probes / 4.0 ** L
+        hits = hpe * total_entries / world
+        t_sectors = sector_bytes / 32.0 / (peak_gather * 1e9)
+        t_hits = hits / (peak_atoms * 1e9)
+        roofline = {"bound": "l1tex", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
                     "frac": achieved / (peak_gather * 32.0), "traffic": traffic,
-                    "note": "index variant: every forward L-mer of a row probes %d %d-byte slots of the L2-resident table (%d distinct "
-                            "32-byte sectors); achieved = rows x %d L-mers x sectors x 32 B per pass / time; peak = random 16-byte gathers "
-                            "from a 64 MB table measured in this run (x 32 B per sector). MEASURED_PEAKS.json hbm_gbs = %s for scale: "
-                            "the probes are served by L2, DRAM traffic is `traffic`" % (probes, slot_bytes, sectors, nq, measured_hbm()),
+                    "traffic_note": "DRAM bytes per launch from the committed ncu capture; the output alone is ~8 B x entries per launch, the rest "
+                                    "is the slot table re-fetched after each L2 flush -- harmless at < 1 % of HBM bandwidth (MEASURED_PEAKS hbm_gbs = %s)" % peaks.get("hbm_gbs"),
+                    "note": "index variant: every forward L-mer of a row probes %d 8-byte slots (%d distinct 32-byte sectors) of every L2-resident "
+                            "column-block table that starts below the row; achieved = sum over rows of blocks x %d L-mers x sectors x 32 B per pass / time; "
+                            "peak = random 16-byte gathers from a 64 MB table measured in this run (x 32 B per sector). This is a UTILISATION of the "
+                            "L1TEX gather ceiling by implementation traffic, not algorithmic work; `l1tex_model` adds the irreducible part "
+                            "(one shared atomic per L-mer pair within d)" % (probes, sectors, nq),
                     "probes_per_lmer": probes, "sectors_per_lmer": sectors, "peak_gather_gsectors": peak_gather,
+                    "index_blocks": nblk, "index_block_cols": blk_cols,
+                    "hits": {"per_entry": hpe, "per_entry_source": "gkmb200_hist_block on 8 rows of this input" if hits_per_entry is not None else "uniform-sequence expectation",
+                             "per_pass": hits, "achieved_ghits_s": hits / (ms_per_step * 1e-3) / 1e9, "peak_gatoms_s": peak_atoms,
+                             "frac": hits / (ms_per_step * 1e-3) / 1e9 / peak_atoms,
+                             "note": "shared-memory atomic adds at ~7 active lanes per warp instruction on random columns of an 80 KB histogram row "
+                                     "(gkmb200_microbench atoms7), the pattern the hot loop produces"},
+                    "l1tex_model": {"sector_s": t_sectors, "hit_s": t_hits, "sum_s": t_sectors + t_hits, "measured_s": ms_per_step * 1e-3,
+                                    "frac": (t_sectors + t_hits) / (ms_per_step * 1e-3),
+                                    "note": "slot loads and shared atomics share the L1TEX data pipe: lower bound = sectors / gather peak + hits / atomic peak"},
                     "int_alu_equivalent": {"achieved_gops": int_alu_equiv, "peak_lop3_gops": peak_lop3, "ratio": int_alu_equiv / peak_lop3,
-                                           "note": "what the canonical 5-op XOR/POPC form would need for the same entries/s (SURVEY.md 8d)"},
+                                           "note": "SURVEY.md 8d's unit, labelled as such: what the canonical 5-op XOR/POPC form would need for the same "
+                                                   "entries/s; the index variant never touches pairs farther apart than d, so this is not a utilisation"},
+                    "hbm": {"algorithmic_bytes_per_entry": 8, "achieved_gbs": per_gpu_entries_s * 8 / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                            "frac": (per_gpu_entries_s * 8 / 1e9 / peaks["hbm_gbs"]) if peaks.get("hbm_gbs") else None},
                     "ncu": ncu, "avg_launch_ms": avg_launch_ms, "kernel_variant": variant}
     else:
         roofline = {"bound": "int_alu", "achieved": int_alu_equiv, "peak": peak_lop3, "unit": "Gop/s", "frac": int_alu_equiv / peak_lop3,
@@ -369,50 +574,119 @@ def main():
                             "peak). The bit-sliced kernel needs < 1 op per pair, so frac > 1 is possible; see DESIGN.md",
                     "peak_popc_gops": peak_popc, "ncu": ncu, "avg_launch_ms": avg_launch_ms, "kernel_variant": variant}
 
-    # secondary figure: gkmQC's default weighted kernel, type 4 (wgkm, M=50 H=50), same sequences
+    # ------------------------------------------------------------------ secondary figures (rank 0, N = 1 only)
     secondary = None
-    if world == 1:
-        with capi.Problem(4, L, K, D, 50, 50.0, 1.0) as P4:
-            P4.read(pos, neg)
-            ms4 = P4.bench_lower_resident(2, 1, flush_l2=True)
-            secondary = {"kernel_type": 4, "value": total_entries / (float(ms4.mean()) * 1e-3), "unit": "entries/s",
-                         "ms_per_step": float(ms4.mean()), "note": "wgkm (EST_TRUNC_PW) on the same workload, resident pass"}
+    if world == 1 and not args.no_secondary and not args.n:
+        secondary = {}
+        n2 = SECOND_N
+        e2 = n2 * (n2 - 1) // 2
+        pos2, neg2 = write_problem(tmp, n2, tag="_10k")
 
-    # second secondary figure: the same problem size on genome-like, NON-uniform input (AT-rich background,
-    # a repeat family in 20 % of the sequences, poly-A tracts in 10 %, dinucleotide repeats in 5 %, 5 % exact duplicates)
-    nonuniform = None
-    if world == 1:
+        def e2e_of(posf, negf, nn, reps=3, **kw):
+            w = []
+            for it in range(reps + 1):
+                km = np.zeros((nn, nn))
+                t0 = time.perf_counter()
+                ret, km, _, _ = capi.main_pywrapper(posf, negf, nthreads=1, verbosity=verbosity, kmat=km, **kw)
+                if ret != 0:
+                    raise SystemExit("gkm_main_pywrapper failed: " + capi.last_error())
+                if it > 0:
+                    w.append(time.perf_counter() - t0)
+                del km
+            return float(np.mean(w))
+
+        # configs[1]: 5k + 5k x 300 bp, the workload round 1 reported
+        with capi.Problem(KTYPE, L, K, D) as P2:
+            P2.read(pos2, neg2)
+            m2 = P2.bench_lower_resident(3, 2, flush_l2=True)
+        w2 = e2e_of(pos2, neg2, n2, kernel_type=KTYPE, L=L, k=K, d=D)
+        sec1 = {"workload": "BASELINE configs[1]: 5k + 5k x 300 bp, type 2, L=11 k=7 d=3", "value": e2 / (float(m2.mean()) * 1e-3),
+                "ms_per_step": float(m2.mean()), "e2e": {"value": e2 / w2, "ms_per_step": 1e3 * w2}, "unit": "entries/s"}
+        with capi.Problem(4, L, K, D, 50, 50.0, 1.0) as P4:
+            P4.read(pos2, neg2)
+            ms4 = P4.bench_lower_resident(3, 2, flush_l2=True)
+            sec1["type4"] = {"value": e2 / (float(ms4.mean()) * 1e-3), "ms_per_step": float(ms4.mean()),
+                             "note": "wgkm (EST_TRUNC_PW, M=50 H=50) on the same sequences, resident pass"}
+        if not args.no_cpu_baseline and not args.no_cpu_full:
+            try:   # the unmodified reference through the same ctypes call on the same files, all rows, nothing sampled
+                import pyoracle
+                if pyoracle.have_ref():
+                    kmr = np.zeros((n2, n2))
+                    t0 = time.perf_counter()
+                    ret, kmr, _, _ = pyoracle.call_pywrapper(pyoracle.ref_pywrapper(), pos2, neg2, kernel_type=KTYPE, L=L, k=K, d=D,
+                                                             nthreads=threads, verbosity=0, kmat=kmr)
+                    tr = time.perf_counter() - t0
+                    kmo = np.zeros((n2, n2))
+                    ret2, kmo, _, _ = capi.main_pywrapper(pos2, neg2, kernel_type=KTYPE, L=L, k=K, d=D, nthreads=1, verbosity=0, kmat=kmo)
+                    sec1["cpu_full"] = {"value": e2 / tr, "unit": "entries/s", "seconds": tr, "cores": threads, "kind": "reference",
+                                        "call": "oracle/_ref/gkmkern_pylib.so::gkm_main_pywrapper on the same FASTA files, every row, nthreads = all cores",
+                                        "whole_matrix_identical_to_ours": bool(ret == 0 and ret2 == 0 and np.array_equal(kmr, kmo)),
+                                        "e2e_ratio": tr / w2}
+                    del kmr, kmo
+            except Exception as e:
+                sec1["cpu_full"] = {"error": str(e)}
+        secondary["configs1_10k"] = sec1
+
+        # gkmQC's real default (bin/gkmqc.py:154,169-199): wgkm type 4, L=10 k=6 d=3, 600-bp window, 5k + 5k
+        posd, negd = write_problem(tmp, n2, seed=4321, seqlen=600, tag="_600")
+        with capi.Problem(4, 10, 6, 3, 50, 50.0, 1.0) as Pd:
+            Pd.read(posd, negd)
+            md = Pd.bench_lower_resident(3, 2, flush_l2=True)
+            vd = VARIANTS.get(Pd.stats()["kernel_variant"], "?")
+        wd = e2e_of(posd, negd, n2, kernel_type=4, L=10, k=6, d=3, M=50, H=50.0)
+        pairs600 = (600 - 10 + 1) * 2 * (600 - 10 + 1)
+        secondary["gkmqc_default"] = {"workload": "gkmQC default: wgkm (type 4, M=50 H=50) L=10 k=6 d=3, 5k + 5k x 600 bp", "unit": "entries/s",
+                                      "value": e2 / (float(md.mean()) * 1e-3), "ms_per_step": float(md.mean()), "kernel_variant": vd,
+                                      "e2e": {"value": e2 / wd, "ms_per_step": 1e3 * wd},
+                                      "lmer_pairs_per_entry": pairs600, "lmer_pairs_per_s": e2 / (float(md.mean()) * 1e-3) * pairs600,
+                                      "type4_300bp_L11_lmer_pairs_per_s": sec1["type4"]["value"] * PAIRS_PER_ENTRY}
+
+        # genome-like, NON-uniform input (AT-rich background, a repeat family in 20 %, poly-A tracts in 10 %, dinucleotide repeats in 5 %, 5 % duplicates)
         try:
             import importlib.util
             spec = importlib.util.spec_from_file_location("nonuniform", os.path.join(ROOT, "tools", "nonuniform.py"))
             nu = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(nu)
-            x = nu.workloads(n)["mixed"]
+            x = nu.workloads(n2)["mixed"]
             with capi.Problem(KTYPE, L, K, D) as Pn:
-                Pn.add_many([nu.ACGT[r].tobytes().decode() for r in x])
+                Pn.add_block(nu.ACGT[x])
                 msn = Pn.bench_lower_resident(2, 1, flush_l2=True)
-                nonuniform = {"workload": "mixed (tools/nonuniform.py)", "value": total_entries / (float(msn.mean()) * 1e-3), "unit": "entries/s",
-                              "ms_per_step": float(msn.mean()), "kernel_variant": {1: "lmer", 2: "diag", 3: "mma", 4: "index"}.get(Pn.stats()["kernel_variant"], "?"),
-                              "note": "resident pass, kernel type 2; bit-exact against the bit-sliced kernel in tests/test_gpu_parity.py::test_nonuniform_index_vs_bitsliced"}
+                secondary["nonuniform"] = {"workload": "10k x 300 bp, mixed (tools/nonuniform.py)", "value": e2 / (float(msn.mean()) * 1e-3), "unit": "entries/s",
+                                           "ms_per_step": float(msn.mean()), "kernel_variant": VARIANTS.get(Pn.stats()["kernel_variant"], "?"),
+                                           "note": "resident pass, kernel type 2; bit-exact against the bit-sliced kernel in tests/test_gpu_parity.py::test_nonuniform_index_vs_bitsliced"}
         except Exception as e:   # a reporting extra must not take the bench line down
-            nonuniform = {"error": str(e)}
+            secondary["nonuniform"] = {"error": str(e)}
+    P.close()
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_rate(pos, neg, n, 15.0, os.cpu_count() or 1)
-        one = cpu_reference_rate(pos, neg, n, 5.0, 1)   # the 1-thread figure beside the all-cores one
-        cpu["single_thread"] = {"value": one["value"], "unit": one["unit"], "kind": one["kind"], "sample": one["sample"]}
-
-    print(json.dumps({
-        "metric": "gkm kernel entries/sec (300bp, l=11 k=7 d=3)", "value": value, "unit": "entries/s",
+    out = {
+        "metric": METRIC, "value": value, "unit": "entries/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": config, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "entries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * float(np.mean(walls)), "steps": e2e_steps,
-                "call": "gkm_main_pywrapper(FASTA paths, double** rows of a fresh numpy matrix, int[2])"},
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary, "nonuniform": nonuniform}))
+                "call": "gkm_main_pywrapper(FASTA paths, double** rows of a fresh numpy matrix, int[2])",
+                "host": {"cores": threads, "thp": thp_mode(),
+                         "copy_threads": e2e_stats and e2e_stats["copy_threads"], "thp_chunks": e2e_stats and e2e_stats["thp_chunks"],
+                         "scatter_ms": e2e_stats and e2e_stats["scatter_ms"], "gpu_wait_ms": e2e_stats and e2e_stats["wait_ms"],
+                         "kernel_ms": e2e_stats and e2e_stats["kernel_ms"],
+                         "first_touch_gbs": (e2e_stats["d2h_bytes"] / 1e6 / e2e_stats["scatter_ms"]) if e2e_stats and e2e_stats["scatter_ms"] else None,
+                         "note": "rank 0's last call: the copy-out writes a fresh np.zeros matrix, i.e. page faults (tools/pagefault_probe.c)"}},
+        "gpu_launches": launches_per_step * args.steps, "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
+        "scoring": scoring, "secondary": secondary}
+    print(json.dumps(out))
     sys.stdout.flush()
+    try:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    except Exception:
+        pass
+    if parity is not None and parity.get("ok") is False:
+        sys.stderr.write("bench.py: PARITY FAILURE against the reference: %s\n" % json.dumps(parity))
+        raise SystemExit(3)
+    if scoring and scoring.get("parity") and scoring["parity"]["ok"] is False:
+        sys.stderr.write("bench.py: PARITY FAILURE (scoring) against the reference: %s\n" % json.dumps(scoring["parity"]))
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

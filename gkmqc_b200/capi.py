@@ -98,6 +98,7 @@ def _declare(lib):
     lib.gkmb200_problem_new.argtypes = [ctypes.POINTER(gkm_parameter)]
     lib.gkmb200_problem_free.argtypes = [P]
     lib.gkmb200_problem_add.argtypes = [P, ctypes.c_char_p, I]
+    lib.gkmb200_problem_add_block.argtypes = [P, ctypes.c_void_p, ctypes.c_long, I, I]
     lib.gkmb200_problem_read_fasta.argtypes = [P, ctypes.c_char_p]
     lib.gkmb200_problem_read.argtypes = [P, ctypes.c_char_p, ctypes.c_char_p]
     lib.gkmb200_problem_size.argtypes = [P]
@@ -116,6 +117,8 @@ def _declare(lib):
         ("gkmb200_hist_block", [P, I, I, I, I, I, c_i32_p]),
         ("gkmb200_decision_values", [P, I, I, I, I, c_dbl_p, ctypes.c_double, c_dbl_p]),
         ("gkmb200_get_stats", [P, ctypes.POINTER(gkmb200_stats)]),
+        ("gkmb200_problem_index_layout", [P, c_int_p]),
+        ("gkmb200_trim", []),
         ("gkmb200_bench_lower_resident", [P, I, I, I, c_dbl_p]),
         ("gkmb200_microbench", [ctypes.c_char_p, c_dbl_p]),
         ("gkmb200_svm_cv", [P, ctypes.c_void_p, ctypes.c_long, I, I, ctypes.POINTER(gkmb200_svm_task), c_int_p,
@@ -223,6 +226,14 @@ class Problem:
         for s in seqs:
             self.add(s)
 
+    def add_block(self, letters):
+        """letters: uint8 matrix [n, len] of ASCII bases (one sequence per row)"""
+        a = np.ascontiguousarray(letters, np.uint8)
+        r = self.lib.gkmb200_problem_add_block(self.h, a.ctypes.data, a.strides[0], a.shape[0], a.shape[1])
+        if r < 0:
+            raise GkmError(last_error(self.lib))
+        return r
+
     def read_fasta(self, path):
         r = self.lib.gkmb200_problem_read_fasta(self.h, os.fsencode(path))
         if r < 0:
@@ -300,6 +311,12 @@ class Problem:
         st = gkmb200_stats()
         _check(self.lib.gkmb200_get_stats(self.h, ctypes.byref(st)), self.lib)
         return st.as_dict()
+
+    def index_layout(self):
+        """(column blocks, columns per block, first column) of the index variant's last call; (0, 0, 0) otherwise"""
+        out = (ctypes.c_int * 3)()
+        _check(self.lib.gkmb200_problem_index_layout(self.h, out), self.lib)
+        return tuple(out)
 
     def bench_lower_resident(self, steps, warmup, flush_l2=True):
         ms = np.zeros(steps)

@@ -595,6 +595,20 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     return 0;
 }
 
+/* how the last compute call of this problem cut its columns for the index variant: out = {number of column blocks,
+ * columns per block, first column}; {0, 0, 0} when another variant ran.  For tests and the bench's parity rows. */
+extern "C" int gkmb200_problem_index_layout(const gkmb200_problem *p, int *out)
+{
+    if (!p || !out) { gkm_set_error("null argument"); return 1; }
+    out[0] = out[1] = out[2] = 0;
+    pthread_mutex_lock(&g_lock);
+    if (p->dev && p->dev->variant == GKM_KERNEL_INDEX && p->dev->img[0].blk) {
+        out[0] = p->dev->img[0].nblk; out[1] = p->dev->img[0].blk_cols; out[2] = p->dev->img[0].part_lo;
+    }
+    pthread_mutex_unlock(&g_lock);
+    return 0;
+}
+
 /* drop every cached device block of every GPU (long-lived hosts that change L or n) */
 extern "C" int gkmb200_trim(void)
 {
@@ -1478,6 +1492,63 @@ __global__ void __launch_bounds__(1024, 1) gkm_mb_gather_kernel(const uint4 *__r
     if (acc == 0x9E3779B9u) out[0] = acc;
 }
 
+/* shared-memory atomic adds the way the index variant's hit path issues them: each warp instruction has ~`active` of
+ * its 32 lanes on (a probe finds a posting in the wanted range for a few lanes only), each on a random column of an
+ * 80 KB histogram row; two CTAs of 1024 threads per SM like the hot loop.  Result: atomics per second. */
+__global__ void __launch_bounds__(1024, 2) gkm_mb_atoms_kernel(int iters, uint32_t ncols, uint32_t active, unsigned long long *total)
+{
+    extern __shared__ int32_t mbH[];
+    for (uint32_t i = threadIdx.x; i < ncols; i += 1024u) mbH[i] = 0;
+    __syncthreads();
+    uint32_t s = (blockIdx.x * 1024u + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t cnt = 0;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+            const uint32_t col = __umulhi(s, ncols);
+            const bool on = ((s >> 3) & 31u) < active;
+            if (on) atomicAdd(&mbH[col], 1);
+            cnt += on;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xFFFFFFFFu, cnt, o);
+    if ((threadIdx.x & 31u) == 0u) atomicAdd(total, (unsigned long long) cnt + (mbH[threadIdx.x % ncols] < 0 ? 1ull : 0ull));
+}
+
+static int microbench_atoms(gkm_gpu *g, uint32_t active, double *result)
+{
+    unsigned long long *d = NULL, h = 0;
+    if (cudaMalloc(&d, sizeof(*d)) != cudaSuccess) { gkm_set_error("CUDA: microbench buffers: %s", cudaGetErrorString(cudaGetLastError())); return 1; }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->id);
+    const uint32_t ncols = 20000;
+    const unsigned smem = ncols * 4;
+    const int iters = 4096;
+    cudaFuncSetAttribute(gkm_mb_atoms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    int rc = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaMemsetAsync(d, 0, sizeof(*d), g->sc);
+        cudaEventRecord(e0, g->sc);
+        gkm_mb_atoms_kernel<<<2 * sms, 1024, smem, g->sc>>>(iters, ncols, active, d);
+        cudaEventRecord(e1, g->sc);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { gkm_set_error("CUDA: microbench failed: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+        cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    if (!rc) *result = (double) h / ((double) best * 1e-3) / 1e9;
+    return rc;
+}
+
 static int microbench_gather(gkm_gpu *g, double *result)
 {
     const size_t slots = (size_t) 1 << 22; /* 4 Mi x 16 B = 64 MB, the size of the L = 11 slot table */
@@ -1521,6 +1592,8 @@ extern "C" int gkm_dev_microbench(const char *what, double *result)
             gkm_gpu *g = &g_gpu[g_sel[0]];
             if (gpu_prepare(g, g_sel[0], 0, 0)) { rc = 1; break; }
             if (!strcmp(what, "gather16")) { rc = microbench_gather(g, result); break; }
+            if (!strcmp(what, "atoms7")) { rc = microbench_atoms(g, 7u, result); break; }
+            if (!strcmp(what, "atoms32")) { rc = microbench_atoms(g, 32u, result); break; }
             uint32_t *d = NULL;
             if (cudaMalloc(&d, 64) != cudaSuccess) { rc = 1; break; }
             int sms = 148;

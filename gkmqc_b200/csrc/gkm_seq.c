@@ -156,6 +156,17 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
     return p->n++;
 }
 
+/* n sequences of `len` bases each, `stride` bytes apart in one buffer (a numpy uint8 matrix of letters): the in-memory
+ * entry point for batches */
+int gkmb200_problem_add_block(gkmb200_problem *p, const char *bases, long stride, int n, int len)
+{
+    if (!p || !bases || n < 0 || len < 0 || stride < len) { gkm_set_error("bad sequence block"); return -1; }
+    if (gkm_problem_reserve(p, n)) { gkm_set_error("out of memory"); return -1; }
+    for (int i = 0; i < n; i++)
+        if (gkmb200_problem_add(p, bases + (size_t) i * (size_t) stride, len) < 0) return -1;
+    return p->n;
+}
+
 static int fasta_add(gkmb200_problem *p, const char *seq, int seqlen, const char *id, int idlen)
 {
     const int i = gkmb200_problem_add(p, seq, seqlen);

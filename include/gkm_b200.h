@@ -59,6 +59,7 @@ int gkmb200_posweights(int nk, int kernel_type, int M, double H, uint8_t *wt, ui
 gkmb200_problem *gkmb200_problem_new(const gkm_parameter *param);
 void gkmb200_problem_free(gkmb200_problem *p);
 int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len);       /* len < 0: strlen. returns the id or -1 */
+int gkmb200_problem_add_block(gkmb200_problem *p, const char *bases, long stride, int n, int len); /* n sequences of len bases, stride bytes apart; returns the new size or -1 */
 int gkmb200_problem_read_fasta(gkmb200_problem *p, const char *path);        /* records appended, or -1 (libgkm.c:1251) */
 int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *negfile); /* n_pos, or -1 (libgkm.c:1316) */
 int gkmb200_problem_size(const gkmb200_problem *p);
@@ -117,6 +118,8 @@ int gkmb200_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int n
                    double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha);
 
 /* ---- measurement ---- */
+/* out[3] = {column blocks, columns per block, first column} of the index variant's last compute call on p (zeros: another variant ran) */
+int gkmb200_problem_index_layout(const gkmb200_problem *p, int *out);
 int gkmb200_get_stats(const gkmb200_problem *p, gkmb200_stats *out);
 /* `steps` timed passes over the full lower triangle with inputs and outputs resident in HBM;
  * ms_each[steps] = CUDA-event time of each pass; flush_l2 != 0 rewrites a >L2-sized buffer between passes */

@@ -214,6 +214,8 @@ class RefHook:
         lib.gkmref_row.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dbl_p]
         lib.gkmref_rows_timed.restype = ctypes.c_double
         lib.gkmref_rows_timed.argtypes = [c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dbl_p]
+        lib.gkmref_rows_values.restype = ctypes.c_double
+        lib.gkmref_rows_values.argtypes = [c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_dbl_p, c_int_p, ctypes.c_long]
         self.L, self.d = L, d
         self.n = lib.gkmref_open(kernel_type, L, k, d, M, H, gamma, os.fsencode(posfile), os.fsencode(negfile))
         if self.n < 0:
@@ -263,6 +265,17 @@ class RefHook:
         if end > start:
             self.lib.gkmref_row(a, start, end, res.ctypes.data_as(c_dbl_p))
         return res[: end - start]
+
+    def rows_values(self, rows, nthreads, endcap=0, with_hist=True):
+        """(K [len(rows), ld], H [len(rows), d+1, ld] or None, seconds): K[i, j] = K(rows[i], j) and H[i, m, j] = H_m(rows[i], j)
+        for j < (endcap or rows[i]), every number produced by reference code, rows interleaved over nthreads"""
+        rows = np.ascontiguousarray(rows, np.int32)
+        ld = int(endcap if endcap > 0 else max(int(rows.max()), 1))
+        K = np.zeros((len(rows), ld))
+        H = np.zeros((len(rows), self.d + 1, ld), np.int32) if with_hist else None
+        t = self.lib.gkmref_rows_values(rows.ctypes.data_as(c_int_p), len(rows), nthreads, endcap, K.ctypes.data_as(c_dbl_p),
+                                        H.ctypes.data_as(c_int_p) if with_hist else None, ld)
+        return K, H, t
 
     def rows_timed(self, rows, nthreads, endcap=0):
         rows = np.ascontiguousarray(rows, np.int32)

@@ -164,6 +164,51 @@ double gkmref_rows_timed(const int *rows, int nrows, int nthreads, int endcap, d
     return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ---- parity driver: many rows at once, the reference's own numbers ----
+ * For every i: kout[i*ld + j] = K(rows[i], j) for j < end_i through the public entry point (libgkm.c:1156) and, when
+ * hout is given, hout[(i*(d+1) + m)*ld + j] = H_m(rows[i], j) from the reference's own DFS (gkmref_mmprofile above);
+ * end_i = endcap > 0 ? endcap : rows[i].  Rows are interleaved over nthreads like gkmkern_pylib.c:70-90. */
+typedef struct { const int *rows; int nrows, tid, nthreads, endcap; double *kout; int *hout; long ld; } vals_job_t;
+
+static void *vals_worker(void *p)
+{
+    vals_job_t *job = (vals_job_t *) p;
+    const int nb = g_param.d + 1;
+    int *tmp = job->hout ? (int *) malloc(sizeof(int) * (size_t) nb * (size_t) (g_prob.l + 1)) : NULL;
+    for (int i = job->tid; i < job->nrows; i += job->nthreads) {
+        const int a = job->rows[i];
+        const int end = (job->endcap > 0) ? job->endcap : a;
+        if (end <= 0) continue;
+        gkmkernel_kernelfunc_batch_all(g_kernel, a, 0, end, job->kout + (size_t) i * (size_t) job->ld);
+        if (tmp) {
+            gkmref_mmprofile(a, end, tmp);
+            for (int m = 0; m < nb; m++)
+                memcpy(job->hout + ((size_t) i * (size_t) nb + (size_t) m) * (size_t) job->ld, tmp + (size_t) m * (size_t) end, sizeof(int) * (size_t) end);
+        }
+    }
+    free(tmp);
+    return 0;
+}
+
+double gkmref_rows_values(const int *rows, int nrows, int nthreads, int endcap, double *kout, int *hout, long ld)
+{
+    struct timespec t0, t1;
+    if (nthreads < 1) nthreads = 1;
+    vals_job_t *jobs = (vals_job_t *) malloc(sizeof(vals_job_t) * (size_t) nthreads);
+    pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t) * (size_t) nthreads);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < nthreads; t++) {
+        vals_job_t j = { rows, nrows, t, nthreads, endcap, kout, hout, ld };
+        jobs[t] = j;
+        if (t > 0) pthread_create(&th[t], NULL, vals_worker, &jobs[t]);
+    }
+    vals_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(jobs); free(th);
+    return (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+}
+
 void gkmref_close(void)
 {
     if (!g_kernel) return;

@@ -415,3 +415,62 @@ def test_driver_mirror_returns_what_gkmsvm_would():
     n = len(g["lens"])
     assert (npos, nneg) == (int(g["npos"]), n - int(g["npos"])) and kmat.shape == (n, n)
     assert np.array_equal(kmat, np.maximum(g["kmat"], g["kmat"].T))
+
+
+@pytest.mark.parametrize("kernel_type", [2, 4])
+def test_full_size_index_against_bitsliced_and_reference(kernel_type, tmp_path):
+    """BASELINE configs[1] at full size (5k + 5k x 300 bp): the build that produces the headline number (compact slots,
+    two CTAs per SM) against the bit-sliced kernel on the WHOLE matrix, and against the unmodified reference on 32 rows
+    (doubles and integer histograms) where oracle/_ref exists"""
+    import bench
+    n = 10000
+    arr = bench.synth(n)
+    pos, neg = str(tmp_path / "p.fa"), str(tmp_path / "n.fa")
+    bench.write_fasta(pos, arr[: n // 2], 0)
+    bench.write_fasta(neg, arr[n // 2:], n // 2)
+    mats = {}
+    for v in ("index", "diag"):
+        capi.set_option("kernel", v)
+        try:
+            with capi.Problem(kernel_type, 11, 7, 3) as P:
+                P.read(pos, neg)
+                mats[v] = P.kernel_lower()
+                assert P.stats()["kernel_variant"] == {"diag": 2, "index": 4}[v]
+                if v == "index":
+                    rows = bench.parity_rows(n, P.index_layout()[1] or n, P.index_layout()[0], want=32)[:40]
+                    hist = {int(r): P.hist_block(int(r), 1, 0, int(r))[0] for r in rows}
+        finally:
+            capi.set_option("kernel", "auto")
+    assert np.array_equal(mats["index"], mats["diag"]), "index and bit-sliced kernels differ somewhere in the 10k x 10k matrix"
+    K = mats["index"]
+    assert np.all(np.diag(K) == 1.0) and not np.triu(K, 1).any()
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref not built here: the cross-variant half of the test ran")
+    h = pyoracle.RefHook(pos, neg, kernel_type, 11, 7, 3)
+    try:
+        Kr, Hr, _ = h.rows_values(rows, os.cpu_count() or 1)
+        for i, r in enumerate(rows):
+            assert np.array_equal(K[r, :r], Kr[i, :r]), "row %d differs from the reference" % r
+            assert np.array_equal(hist[int(r)], Hr[i, :, :r].T), "histograms of row %d differ from the reference" % r
+    finally:
+        h.close()
+
+
+def test_one_core_affinity_still_correct(tmp_path):
+    """a caller pinned to one core (slurm job that asked for one): the copy-out runs on that core alone and the
+    matrix is the same"""
+    import subprocess
+    import sys
+    g, cfg, pos, neg = load_golden("uni_t2_L11k7d3")
+    out = tmp_path / "k.npy"
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from gkmqc_b200 import capi; "
+            "ret, k, a, b = capi.main_pywrapper(%r, %r, kernel_type=2, L=11, k=7, d=3, nthreads=1, nmax=64); "
+            "st = capi.gkmb200_stats(); capi.load().gkmb200_get_stats(None, capi.ctypes.byref(st)); "
+            "assert ret == 0 and st.copy_threads == 1, (ret, st.copy_threads); np.save(%r, k)"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), pos, neg, str(out)))
+    env = {k: v for k, v in os.environ.items() if k != "GKM_COPY_THREADS"}
+    cpu = sorted(os.sched_getaffinity(0))[0]
+    r = subprocess.run(["taskset", "-c", str(cpu), sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n = len(g["lens"])
+    assert np.array_equal(np.load(out)[:n, :n], g["kmat"])

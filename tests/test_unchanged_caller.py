@@ -1,0 +1,61 @@
+"""The reference's own caller, unchanged: /root/reference/scripts/gkmsvm.py imported as it is, with its module
+global `bin_dir` (gkmsvm.py:38, read at call time :85) pointed at gkmqc_b200/bin.  Runs only where the reference
+tree exists (this container); the GPU box has no /root/reference, there gkmqc_b200/driver.py -- the line-for-line
+mirror of that caller -- carries the same checks (tests/test_gpu_parity.py::test_driver_mirror_returns_what_gkmsvm_would).
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from gkmqc_b200 import capi
+
+REF_SCRIPT = "/root/reference/scripts/gkmsvm.py"
+
+
+def load_reference_caller():
+    if not os.path.exists(REF_SCRIPT):
+        pytest.skip("no reference tree on this box")
+    spec = importlib.util.spec_from_file_location("gkmsvm_unchanged", REF_SCRIPT)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gkmsvm_unchanged"] = mod
+    spec.loader.exec_module(mod)
+    mod.bin_dir = capi.BIN_DIR
+    return mod
+
+
+def test_unchanged_gkmsvm_binds_to_the_library_and_fails_loudly_without_a_gpu():
+    """no GPU here: the call must reach gkm_main_pywrapper of OUR library through gkmsvm.py's own ctypes code and come
+    back as the error return that gkmsvm.py turns into sys.exit() (gkmsvm.py:90-92) -- never a CPU result"""
+    capi.load()
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is visible: the GPU test below covers this box")
+    mod = load_reference_caller()
+    g, cfg, pos, neg = load_golden("uni_t4_L10k6d3")
+    with pytest.raises(SystemExit):
+        mod.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, pos, neg, 1, 0])
+    assert "no sm_100" in capi.last_error()
+
+
+@pytest.mark.gpu
+def test_unchanged_gkmsvm_end_to_end_with_fork_after_cuda():
+    """computeGkmKernel + crossValidate of the unchanged script: the kernel matrix it symmetrises equals the
+    reference's, and its multiprocessing.Pool forks AFTER the CUDA context is alive in the parent (gkmsvm.py:152-155;
+    the children only run sklearn)"""
+    mod = load_reference_caller()
+    if capi.device_count() < 1:
+        pytest.fail("no B200 visible; the product has no CPU fallback")
+    g, cfg, pos, neg = load_golden("uni_t4_L10k6d3")
+    kmat, npos, nneg = mod.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, pos, neg, 1, 0])
+    n = len(g["lens"])
+    assert (npos, nneg) == (int(g["npos"]), n - int(g["npos"])) and kmat.shape == (n, n)
+    assert np.array_equal(kmat, np.maximum(g["kmat"], g["kmat"].T))
+    # regularization, precision, shrinking, cache_size, ncv, repeats, fast_estimation, random_seeds, processes
+    auc, std = mod.crossValidate([1.0, 1e-3, 0, 100, 2, 2, 0, 1, 2], kmat, npos, nneg)
+    assert 0.0 <= auc <= 1.0 and np.isfinite(std)
+    # the parent's CUDA context is still usable after the pool's fork + join
+    kmat2, _, _ = mod.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, pos, neg, 1, 0])
+    assert np.array_equal(kmat2, kmat)
