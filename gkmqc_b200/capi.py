@@ -118,6 +118,7 @@ def _declare(lib):
         ("gkmb200_decision_values", [P, I, I, I, I, c_dbl_p, ctypes.c_double, c_dbl_p]),
         ("gkmb200_get_stats", [P, ctypes.POINTER(gkmb200_stats)]),
         ("gkmb200_problem_index_layout", [P, c_int_p]),
+        ("gkmb200_problem_image", [P, ctypes.c_void_p, ctypes.c_void_p, c_int_p]),
         ("gkmb200_trim", []),
         ("gkmb200_bench_lower_resident", [P, I, I, I, c_dbl_p]),
         ("gkmb200_microbench", [ctypes.c_char_p, c_dbl_p]),
@@ -311,6 +312,16 @@ class Problem:
         st = gkmb200_stats()
         _check(self.lib.gkmb200_get_stats(self.h, ctypes.byref(st)), self.lib)
         return st.as_dict()
+
+    def image(self):
+        """(planes [n, 3, W] uint32, wend [n, 32 W] uint8 or None): the packed image as it lies on GPU 0"""
+        shape = (ctypes.c_int * 2)()
+        _check(self.lib.gkmb200_problem_image(self.h, None, None, shape), self.lib)
+        n, W = shape[0], shape[1]
+        planes = np.zeros((n, 3, W), np.uint32)
+        wend = np.zeros((n, 32 * W), np.uint8) if self.kernel_type in (4, 5) else None
+        _check(self.lib.gkmb200_problem_image(self.h, planes.ctypes.data, wend.ctypes.data if wend is not None else None, shape), self.lib)
+        return planes, wend
 
     def index_layout(self):
         """(column blocks, columns per block, first column) of the index variant's last call; (0, 0, 0) otherwise"""

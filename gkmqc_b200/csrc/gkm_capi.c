@@ -286,7 +286,7 @@ gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seq
     if (!d) return NULL;
     /* one-sequence problem: coding, and sqnorm = sqrt(Kraw(x,x)) on the device */
     gkmb200_problem *one = gkmb200_problem_new(pa);
-    if (!one || gkmb200_problem_add(one, seq, len) < 0 || fill_object(d, pa, one->code[0], len, seq, sid, seqid) || gkm_dev_upload(one)) {
+    if (!one || gkmb200_problem_add(one, seq, len) < 0 || fill_object(d, pa, gkm_code(one, 0), len, seq, sid, seqid) || gkm_dev_upload(one)) {
         gkmb200_problem_free(one);
         gkmkernel_delete_object(d);
         return NULL;
@@ -419,7 +419,7 @@ int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *p
     for (int i = 0; !bad && i < n; i++) {
         gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
         prob->x[i] = d;
-        if (!d || fill_object(d, kernel->param, p->code[i], p->len[i], NULL, p->sid[i] ? p->sid[i] : "", i)) { bad = 1; break; }
+        if (!d || fill_object(d, kernel->param, gkm_code(p, i), p->len[i], NULL, p->sid[i] ? p->sid[i] : "", i)) { bad = 1; break; }
         d->label = (i < npos) ? 1 : -1;
         d->sqnorm = p->sqnorm[i];
         prob->y[i] = d->label;

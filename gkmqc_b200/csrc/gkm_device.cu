@@ -103,7 +103,8 @@ struct gkm_image {
     int32_t *lens;
     uint8_t *wend;
     double *sqnorm;
-    size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes; /* block sizes as handed out by the pool */
+    uint8_t *codes;     /* device packing: the base codes as uploaded (one byte per base), kept until release */
+    size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes, codes_bytes; /* block sizes as handed out by the pool */
     double *full;       /* resident N x ldfull result (bench, svm consumer) */
     size_t full_ld;
     int full_sym;       /* the resident matrix is complete and symmetric (unit diagonal) */
@@ -595,6 +596,31 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     return 0;
 }
 
+static int upload_locked(gkmb200_problem *p, int need_host);
+
+/* the image as it lies on GPU 0 (tests: device packing against the host packer): planes [n][3][W] and, for the
+ * weighted kernel types, wend [n][32 W]; either pointer may be NULL.  out_shape = {n, W}. */
+extern "C" int gkmb200_problem_image(gkmb200_problem *p, uint32_t *planes, uint8_t *wend, int *out_shape)
+{
+    if (!p) { gkm_set_error("null problem"); return 1; }
+    pthread_mutex_lock(&g_lock);
+    int rc = upload_locked(p, 0);
+    if (!rc) {
+        gkm_devstate *ds = p->dev;
+        gkm_gpu *g = &g_gpu[ds->dev[0]];
+        const size_t n = (size_t) p->n, W = (size_t) p->Wmax;
+        if (out_shape) { out_shape[0] = p->n; out_shape[1] = p->Wmax; }
+        do {
+            if (cudaSetDevice(ds->dev[0]) != cudaSuccess || cudaStreamSynchronize(g->sc) != cudaSuccess) { rc = 1; break; }
+            if (planes && cudaMemcpy(planes, ds->img[0].planes, n * 3 * W * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
+            if (wend && p->weighted && cudaMemcpy(wend, ds->img[0].wend, n * 32 * W, cudaMemcpyDeviceToHost) != cudaSuccess) { rc = 1; break; }
+        } while (0);
+        if (rc) gkm_set_error("CUDA: image read-back: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
 /* how the last compute call of this problem cut its columns for the index variant: out = {number of column blocks,
  * columns per block, first column}; {0, 0, 0} when another variant ran.  For tests and the bench's parity rows. */
 extern "C" int gkmb200_problem_index_layout(const gkmb200_problem *p, int *out)
@@ -637,11 +663,52 @@ extern "C" void gkm_dev_release(gkmb200_problem *p)
         pool_free(g, im->lens, im->lens_bytes);
         pool_free(g, im->wend, im->wend_bytes);
         pool_free(g, im->sqnorm, im->sqnorm_bytes);
+        pool_free(g, im->codes, im->codes_bytes);
         release_index(g, im);
         cudaFree(im->full);
     }
     free(ds);
     p->dev = NULL;
+}
+
+/* ------------------------------------------------------------------ */
+/* packing on the device: base codes -> the image of 3 */
+/* ------------------------------------------------------------------ */
+/* What gkm_seq.c:pack_worker does on the host (it stays there for the CPU emulators of the test tier), one CTA per
+ * sequence, one warp per 32-position word of the circular string: forward strand at [0, len), reverse complement
+ * (3 - code, mirrored: libgkm.c:878-888) at [len, 2 len), zero padding; plane bits by warp ballot; E = positions at
+ * which an L-mer of either strand may end; wend[j] = positional weight of the L-mer ending at j, looked up by its
+ * distance from the centre L-mer in a table the host computed with the reference's expression (libgkm.c:910-932) --
+ * no exp() on the device, so the bytes are the host's. */
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(128)
+gkm_pack_kernel(const uint8_t *__restrict__ codes, const unsigned long long *__restrict__ off, const int32_t *__restrict__ lens,
+                int W, int L, const uint8_t *__restrict__ wtab, uint32_t *__restrict__ planes, uint8_t *__restrict__ wend)
+{
+    const int i = (int) blockIdx.x;
+    const int len = lens[i], nk = len - L + 1, centre = nk / 2;
+    const uint8_t *c = codes + off[i];
+    const int lane = (int) threadIdx.x & 31;
+    for (int wi = (int) threadIdx.x >> 5; wi < W; wi += 4) {
+        const int j = wi * 32 + lane;
+        uint32_t code = 0;
+        int s = -1; /* start index (forward-strand numbering of wt[]) of the L-mer that ends at j, if any */
+        if (j < len) {
+            code = c[j];
+            if (j >= L - 1) s = j - (L - 1);
+        } else if (j < 2 * len) {
+            code = 3u - c[2 * len - 1 - j];
+            const int rel = j - len;
+            if (rel >= L - 1) s = nk - 1 - (rel - (L - 1)); /* wt_rc[t] = wt[nk - 1 - t] */
+        }
+        const uint32_t p0 = __ballot_sync(0xFFFFFFFFu, code & 1u), p1 = __ballot_sync(0xFFFFFFFFu, code & 2u);
+        const uint32_t pe = __ballot_sync(0xFFFFFFFFu, s >= 0);
+        if (lane == 0) {
+            uint32_t *pl = planes + (size_t) i * 3 * (size_t) W;
+            pl[wi] = p0; pl[W + wi] = p1; pl[2 * W + wi] = pe;
+        }
+        if (WEIGHTED) wend[(size_t) i * 32 * (size_t) W + (size_t) j] = (s >= 0) ? wtab[abs(centre - s)] : (uint8_t) 0;
+    }
 }
 
 /* bring sqnorm back to the host (only the ABI functions that expose it need that) */
@@ -664,7 +731,10 @@ static int upload_locked(gkmb200_problem *p, int need_host)
     if (ensure_selected()) return 1;
     const double t0 = now_ms();
     gkm_dev_release(p);
-    if (gkm_pack_problem(p)) return 1;
+    const int pack_host = gkm_opt_pack_host();
+    if (pack_host ? gkm_pack_problem(p) : gkm_shape_problem(p)) return 1;
+    uint8_t wtab[GKM_MAX_BASES + 1];
+    if (!pack_host && p->weighted) gkm_posweight_table(p->param.kernel_type, p->param.M, p->param.H, wtab);
     gkm_devstate *ds = (gkm_devstate *) calloc(1, sizeof(gkm_devstate));
     if (!ds) { gkm_set_error("out of memory"); return 1; }
     p->dev = ds;
@@ -679,13 +749,30 @@ static int upload_locked(gkmb200_problem *p, int need_host)
         if (pool_alloc(g, (void **) &im->planes, &im->planes_bytes, n * 3 * W * sizeof(uint32_t))) return 1;
         if (pool_alloc(g, (void **) &im->lens, &im->lens_bytes, n * sizeof(int32_t))) return 1;
         if (pool_alloc(g, (void **) &im->sqnorm, &im->sqnorm_bytes, n * sizeof(double))) return 1;
-        CK(cudaMemcpyAsync(im->planes, p->planes, n * 3 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
         CK(cudaMemcpyAsync(im->lens, p->len, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->sc));
-        h2d += (long long) (n * 3 * W * sizeof(uint32_t) + n * sizeof(int32_t));
-        if (p->weighted) {
-            if (pool_alloc(g, (void **) &im->wend, &im->wend_bytes, n * 32 * W)) return 1;
-            CK(cudaMemcpyAsync(im->wend, p->wend, n * 32 * W, cudaMemcpyHostToDevice, g->sc));
-            h2d += (long long) (n * 32 * W);
+        h2d += (long long) (n * sizeof(int32_t));
+        if (p->weighted && pool_alloc(g, (void **) &im->wend, &im->wend_bytes, n * 32 * W)) return 1;
+        if (pack_host) {
+            CK(cudaMemcpyAsync(im->planes, p->planes, n * 3 * W * sizeof(uint32_t), cudaMemcpyHostToDevice, g->sc));
+            h2d += (long long) (n * 3 * W * sizeof(uint32_t));
+            if (p->weighted) {
+                CK(cudaMemcpyAsync(im->wend, p->wend, n * 32 * W, cudaMemcpyHostToDevice, g->sc));
+                h2d += (long long) (n * 32 * W);
+            }
+        } else {
+            /* one byte per base goes up (3 MB at 10k x 300 bp; the packed image of a weighted problem was 8.3 MB) and the
+             * GPU packs: codes | offsets | weight table in one block */
+            const size_t off_at = (p->arena_len + 15) & ~(size_t) 15, tab_at = off_at + n * sizeof(unsigned long long);
+            if (pool_alloc(g, (void **) &im->codes, &im->codes_bytes, tab_at + sizeof(wtab))) return 1;
+            CK(cudaMemcpyAsync(im->codes, p->arena, p->arena_len, cudaMemcpyHostToDevice, g->sc));
+            CK(cudaMemcpyAsync(im->codes + off_at, p->off, n * sizeof(unsigned long long), cudaMemcpyHostToDevice, g->sc));
+            if (p->weighted) CK(cudaMemcpyAsync(im->codes + tab_at, wtab, sizeof(wtab), cudaMemcpyHostToDevice, g->sc));
+            h2d += (long long) (p->arena_len + n * sizeof(unsigned long long) + (p->weighted ? sizeof(wtab) : 0));
+            const unsigned long long *d_off = (const unsigned long long *) (im->codes + off_at);
+            if (p->weighted) gkm_pack_kernel<true><<<(unsigned) n, 128, 0, g->sc>>>(im->codes, d_off, im->lens, (int) W, p->param.L, im->codes + tab_at, im->planes, im->wend);
+            else gkm_pack_kernel<false><<<(unsigned) n, 128, 0, g->sc>>>(im->codes, d_off, im->lens, (int) W, p->param.L, NULL, im->planes, NULL);
+            CK(cudaGetLastError());
+            p->stats.launches++;
         }
         /* sqnorm: Kraw(a,a) by the same kernel in diagonal mode, in blocks of 1024 rows */
         gkm_kparams kp;

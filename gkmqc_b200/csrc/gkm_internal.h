@@ -38,11 +38,15 @@ struct gkmb200_problem {
     int n, cap;
     int npos;      /* set by read_problem */
     int *len;      /* bases per sequence */
-    uint8_t **code;/* forward strand, base codes 0..3 (A,C,G,T) */
+    uint8_t *arena;/* forward strands of all sequences back to back, base codes 0..3 (A,C,G,T): what goes to the GPU */
+    size_t arena_len, arena_cap;
+    size_t *off;   /* first base of sequence i in the arena */
     char **sid;    /* FASTA record ids (first token after '>', libgkm.c:1287-1292); NULL for sequences added in memory */
     int nonacgt;   /* characters mapped to 'A' so far */
 
-    /* packed image (gkm_pack_problem) */
+    /* shape of the packed image (gkm_shape_problem); the image itself is built ON THE DEVICE from the arena
+     * (gkm_device.cu: gkm_pack_kernel).  planes / wend on the host exist only after gkm_pack_problem, which the CPU
+     * emulators of the test tier and the pack = host A/B option use. */
     int packed;
     int Wmax;        /* 32-bit words per bit plane = ceil(2*maxlen / 32): both strands in one circular string */
     int Wa;          /* ceil(maxlen / 32): 32-position chunks of a query */
@@ -59,7 +63,11 @@ struct gkmb200_problem {
 
 int gkm_problem_reserve(gkmb200_problem *p, int extra);
 void gkm_problem_shard_from_env(gkmb200_problem *p); /* GKM_SHARD="rank/world": gkm_main_pywrapper only */
-int gkm_pack_problem(gkmb200_problem *p);
+int gkm_shape_problem(gkmb200_problem *p);   /* Wmax, Wa, sqnorm buffer; no image */
+int gkm_pack_problem(gkmb200_problem *p);    /* + the image on the host */
+static inline const uint8_t *gkm_code(const gkmb200_problem *p, int i) { return p->arena + p->off[i]; }
+/* positional weight by distance from the centre L-mer (libgkm.c:910-932): tab[dist], dist = 0..GKM_MAX_BASES */
+void gkm_posweight_table(int kernel_type, int M, double H, uint8_t *tab);
 void gkm_unpack_problem(gkmb200_problem *p);
 
 /* ---- chunk planning (gkm_sched.c), pure host logic ---- */

@@ -6,6 +6,7 @@
  *   GKM_MAX_L    = 12 | 16                 ceiling of the parameter gate in gkm_main_pywrapper
  *   GKM_CHUNK_MB = n                       upper bound of one chunk's dense output
  *   GKM_INDEX_COLS = n                     upper bound of the columns of one index block (tests: forces several blocks)
+ *   GKM_PACK     = device | host           who builds the 2-bit plane image from the base codes (default: the GPU)
  *   GKM_DEVICES  = "0,1,.."                GPUs to use (gkm_device.cu)
  */
 #include <stdlib.h>
@@ -22,6 +23,7 @@ static int g_tile_rows = 0;
 static int g_diag_flavor = -1;
 static int g_index_cols = 0;
 static int g_index_wide = 0;
+static int g_pack_host = 0;
 
 static int parse_kernel(const char *v, int *out)
 {
@@ -45,6 +47,7 @@ static void load_env(void)
     if ((v = getenv("GKM_DIAG_FLAVOR")) != NULL) { int x = atoi(v); if (x >= -1 && x <= 7) g_diag_flavor = x; }
     if ((v = getenv("GKM_INDEX_COLS")) != NULL) { int x = atoi(v); if (x >= 32) g_index_cols = x & ~31; }
     if ((v = getenv("GKM_INDEX_WIDE")) != NULL) g_index_wide = atoi(v) != 0;
+    if ((v = getenv("GKM_PACK")) != NULL) g_pack_host = !strcmp(v, "host");
     if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
 }
 
@@ -55,6 +58,7 @@ int gkm_opt_tile_rows(void) { load_env(); return g_tile_rows; }
 int gkm_opt_diag_flavor(void) { load_env(); return g_diag_flavor; }
 int gkm_opt_index_cols(void) { load_env(); return g_index_cols; }
 int gkm_opt_index_wide(void) { load_env(); return g_index_wide; }
+int gkm_opt_pack_host(void) { load_env(); return g_pack_host; }
 
 int gkmb200_set_option(const char *key, const char *value)
 {
@@ -87,6 +91,11 @@ int gkmb200_set_option(const char *key, const char *value)
     }
     if (!strcmp(key, "index_wide")) { /* 1: 16-byte slots even where the compact 8-byte ones would do (A/B, tests) */
         g_index_wide = x != 0;
+        return 0;
+    }
+    if (!strcmp(key, "pack")) { /* device (default): the GPU packs the bit planes from one byte per base; host: gkm_seq.c does (A/B, tests) */
+        if (strcmp(value, "host") && strcmp(value, "device")) { gkm_set_error("pack must be host or device"); return 1; }
+        g_pack_host = !strcmp(value, "host");
         return 0;
     }
     if (!strcmp(key, "tile_rows")) {

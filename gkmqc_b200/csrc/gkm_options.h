@@ -11,6 +11,7 @@ int gkm_opt_tile_rows(void);
 int gkm_opt_diag_flavor(void);
 int gkm_opt_index_cols(void);
 int gkm_opt_index_wide(void);
+int gkm_opt_pack_host(void);
 #ifdef __cplusplus
 }
 #endif

@@ -58,8 +58,9 @@ void gkmb200_problem_free(gkmb200_problem *p)
     if (!p) return;
     gkm_dev_release(p);
     gkm_unpack_problem(p);
-    for (int i = 0; i < p->n; i++) { free(p->code[i]); if (p->sid) free(p->sid[i]); }
-    free(p->code);
+    for (int i = 0; i < p->n; i++) if (p->sid) free(p->sid[i]);
+    free(p->arena);
+    free(p->off);
     free(p->sid);
     free(p->len);
     free(p);
@@ -73,14 +74,27 @@ int gkm_problem_reserve(gkmb200_problem *p, int extra)
     int *len = (int *) realloc(p->len, sizeof(int) * (size_t) cap);
     if (!len) return 1;
     p->len = len;
-    uint8_t **code = (uint8_t **) realloc(p->code, sizeof(uint8_t *) * (size_t) cap);
-    if (!code) return 1;
-    p->code = code;
+    size_t *off = (size_t *) realloc(p->off, sizeof(size_t) * (size_t) cap);
+    if (!off) return 1;
+    p->off = off;
     char **sid = (char **) realloc(p->sid, sizeof(char *) * (size_t) cap);
     if (!sid) return 1;
     for (int i = p->cap; i < cap; i++) sid[i] = NULL;
     p->sid = sid;
     p->cap = cap;
+    return 0;
+}
+
+/* room for `extra` more bases (+ 16 of slack: the SSE2 coder stores whole vectors) */
+static int arena_reserve(gkmb200_problem *p, size_t extra)
+{
+    if (p->arena_len + extra + 16 <= p->arena_cap) return 0;
+    size_t cap = p->arena_cap ? p->arena_cap : ((size_t) 1 << 16);
+    while (cap < p->arena_len + extra + 16) cap *= 2;
+    uint8_t *a = (uint8_t *) realloc(p->arena, cap);
+    if (!a) return 1;
+    p->arena = a;
+    p->arena_cap = cap;
     return 0;
 }
 
@@ -108,9 +122,8 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
         gkm_set_error("sequence %d has %d bases, fewer than L=%d", p->n, len, p->param.L);
         return -1;
     }
-    if (gkm_problem_reserve(p, 1)) { gkm_set_error("out of memory"); return -1; }
-    uint8_t *c = (uint8_t *) malloc((size_t) len);
-    if (!c) { gkm_set_error("out of memory"); return -1; }
+    if (gkm_problem_reserve(p, 1) || arena_reserve(p, (size_t) len)) { gkm_set_error("out of memory"); return -1; }
+    uint8_t *c = p->arena + p->arena_len;
     code_tab_init();
     unsigned any_bad = 0;
     int i = 0;
@@ -150,7 +163,8 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
         }
     }
     p->len[p->n] = len;
-    p->code[p->n] = c;
+    p->off[p->n] = p->arena_len;
+    p->arena_len += (size_t) len;
     p->sid[p->n] = NULL;
     gkm_unpack_problem(p); /* packed image is stale now */
     return p->n++;
@@ -281,16 +295,17 @@ int gkmb200_problem_read(gkmb200_problem *p, const char *posfile, const char *ne
         nn = job.n;
         if (np >= 0 && nn >= 0) {
             gkm_log(GKM_LOG_INFO, "reading sequences from %s", negfile);
-            if (gkm_problem_reserve(p, job.q->n)) { gkm_set_error("out of memory"); nn = -1; }
+            if (gkm_problem_reserve(p, job.q->n) || arena_reserve(p, job.q->arena_len)) { gkm_set_error("out of memory"); nn = -1; }
             else {
-                for (int i = 0; i < job.q->n; i++) { /* the code arrays change owner */
+                memcpy(p->arena + p->arena_len, job.q->arena, job.q->arena_len); /* 1.5 MB per 5 000 x 300 bp */
+                for (int i = 0; i < job.q->n; i++) {
                     p->len[p->n] = job.q->len[i];
-                    p->code[p->n] = job.q->code[i];
-                    job.q->code[i] = NULL;
+                    p->off[p->n] = p->arena_len + job.q->off[i];
                     p->sid[p->n] = job.q->sid[i];
                     job.q->sid[i] = NULL;
                     p->n++;
                 }
+                p->arena_len += job.q->arena_len;
                 p->nonacgt += job.q->nonacgt;
                 gkm_unpack_problem(p);
             }
@@ -328,8 +343,8 @@ int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t
     if (!p || i < 0 || i >= p->n) return 1;
     const int n = p->len[i];
     for (int j = 0; j < n; j++) {
-        if (fwd) fwd[j] = (uint8_t) (p->code[i][j] + 1);
-        if (rc) rc[j] = (uint8_t) (4 - p->code[i][n - 1 - j]);
+        if (fwd) fwd[j] = (uint8_t) (gkm_code(p, i)[j] + 1);
+        if (rc) rc[j] = (uint8_t) (4 - gkm_code(p, i)[n - 1 - j]);
     }
     return 0;
 }
@@ -379,7 +394,7 @@ static void *pack_worker(void *arg)
     int wt_nk = -1; /* positional weights depend on the number of L-mers only: reuse them across equal lengths */
     for (int i = job->i0; i < job->i1; i++) {
         const int n = p->len[i];
-        const uint8_t *c = p->code[i];
+        const uint8_t *c = gkm_code(p, i);
         uint32_t *pl = p->planes + (size_t) i * 3 * (size_t) W;
         /* Forward strand: bit b of the codes, eight bases per multiply (the byte-to-bit gather trick); the reverse
          * complement half is the forward half mirrored and complemented (3 - c = ~c & 3; libgkm.c:878-888), so it
@@ -466,19 +481,30 @@ static void *pack_worker(void *arg)
  * complement at [len,2len), zero padding behind.  planes[i][0..1][Wc] = the two code bit planes,
  * planes[i][2][Wc] = E, the positions at which an L-mer of either strand may END
  * (L-1 <= j < len and len+L-1 <= j < 2len).  wend[i][32*Wc] = weight of the L-mer ending at j. */
-int gkm_pack_problem(gkmb200_problem *p)
+/* shape of the image: words per plane and the sqnorm buffer; the image itself is built on the device */
+int gkm_shape_problem(gkmb200_problem *p)
 {
     if (p->packed) return 0;
     if (p->n == 0) { gkm_set_error("problem has no sequences"); return 1; }
     int maxlen = 0;
     for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
-    const int W = (2 * maxlen + 31) / 32;
-    p->Wmax = W;
+    p->Wmax = (2 * maxlen + 31) / 32;
     p->Wa = (maxlen + 31) / 32;
-    p->planes = (uint32_t *) calloc((size_t) p->n * 3 * (size_t) W, sizeof(uint32_t));
     p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
+    if (!p->sqnorm) { gkm_set_error("out of memory"); return 1; }
+    p->packed = 1;
+    p->have_sqnorm = 0;
+    return 0;
+}
+
+int gkm_pack_problem(gkmb200_problem *p)
+{
+    if (p->packed && p->planes) return 0;
+    if (gkm_shape_problem(p)) return 1;
+    const int W = p->Wmax;
+    p->planes = (uint32_t *) calloc((size_t) p->n * 3 * (size_t) W, sizeof(uint32_t));
     if (p->weighted) p->wend = (uint8_t *) calloc((size_t) p->n * 32 * (size_t) W, 1);
-    if (!p->planes || !p->sqnorm || (p->weighted && !p->wend)) {
+    if (!p->planes || (p->weighted && !p->wend)) {
         gkm_unpack_problem(p);
         gkm_set_error("out of memory packing %d sequences", p->n);
         return 1;
@@ -504,7 +530,5 @@ int gkm_pack_problem(gkmb200_problem *p)
         if (started[t]) pthread_join(th[t], NULL);
         else pack_worker(&jobs[t]);
     }
-    p->packed = 1;
-    p->have_sqnorm = 0;
     return 0;
 }

@@ -125,20 +125,32 @@ int gkm_calc_weights(int kernel_type, int L, int k, double *w)
 
 /* positional weights per L-mer start (libgkm.c:910-932): exponential decay from the centre
  * for the wgkm types, 1 otherwise; the reverse-complement strand gets the mirrored vector */
+/* weight of the L-mer `dist` starts away from the centre one (libgkm.c:922-925, the reference's own expression) */
+static uint8_t posweight_at(int dist, int M, double H)
+{
+    const double x = floor(M * exp((-1) * log(2) * dist / H) + 1);
+    uint8_t v = (uint8_t) (int) x; /* the reference stores into u_int8_t: 256 wraps to 0 */
+    if (v > M) v = (uint8_t) M;
+    return v;
+}
+
 void gkm_calc_posweights(int nk, int kernel_type, int M, double H, uint8_t *wt, uint8_t *wt_rc)
 {
     const int centre = nk / 2;
     const int decays = (kernel_type == EST_TRUNC_PW || kernel_type == EST_TRUNC_PW_RBF);
     for (int i = 0; i < nk; i++) {
-        uint8_t v = 1;
-        if (decays) {
-            const double x = floor(M * exp((-1) * log(2) * abs(centre - i) / H) + 1);
-            v = (uint8_t) (int) x; /* the reference stores into u_int8_t: 256 wraps to 0 */
-            if (v > M) v = (uint8_t) M;
-        }
+        const uint8_t v = decays ? posweight_at(abs(centre - i), M, H) : 1;
         wt[i] = v;
         wt_rc[nk - 1 - i] = v;
     }
+}
+
+/* The weight depends on the distance from the centre only: one table serves every sequence length.  The device
+ * packer (gkm_device.cu: gkm_pack_kernel) indexes it; exp() never runs on the GPU, so the bytes are the host's. */
+void gkm_posweight_table(int kernel_type, int M, double H, uint8_t *tab)
+{
+    const int decays = (kernel_type == EST_TRUNC_PW || kernel_type == EST_TRUNC_PW_RBF);
+    for (int dist = 0; dist <= GKM_MAX_BASES; dist++) tab[dist] = decays ? posweight_at(dist, M, H) : 1;
 }
 
 const char *gkmb200_check_parameter(const gkm_parameter *param) { return gkm_param_problem(param, 12); }

@@ -46,7 +46,7 @@ const char *gkmb200_last_error(void);
 int gkmb200_abi_version(void);
 int gkmb200_device_count(void);                      /* visible CUDA devices of compute capability 10.x; 0 if none */
 int gkmb200_set_devices(const int *ids, int n);      /* default: env GKM_DEVICES ("0,1,.."), else all */
-int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag|mma|index ; "max_L" = 12|16 ; "tile_rows", "chunk_mb", "index_cols", "index_wide" */
+int gkmb200_set_option(const char *key, const char *value); /* "kernel" = auto|lmer|diag|mma|index ; "max_L" = 12|16 ; "tile_rows", "chunk_mb", "index_cols", "index_wide", "pack" = device|host */
 void gkmb200_set_verbosity(int level);               /* 0..4 like gkmOpt.verbosity */
 int gkmb200_trim(void);                              /* give the cached device blocks of every GPU back to the driver */
 
@@ -69,7 +69,8 @@ int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t
 int gkmb200_problem_get_weights(const gkmb200_problem *p, double *w);        /* d+1 values */
 int gkmb200_problem_set_shard(gkmb200_problem *p, int rank, int world);      /* this process computes chunk c iff owner(c) == rank */
 
-/* pack to 2-bit planes, copy to every selected GPU, compute sqnorm there (libgkm.c:723-759) */
+/* copy the base codes (one byte per base) to every selected GPU, pack them there into the 2-bit plane image
+ * (SURVEY.md 8f/f2), compute sqnorm there (libgkm.c:723-759) */
 int gkmb200_problem_upload(gkmb200_problem *p);
 int gkmb200_problem_sqnorm(gkmb200_problem *p, double *out);                 /* n values */
 
@@ -116,6 +117,10 @@ typedef struct gkmb200_svm_fit {
 int gkmb200_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,
                    const int *train_idx, const signed char *train_y, const int *test_idx,
                    double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha);
+
+/* the packed image as it lies on GPU 0: planes[n][3][W] (code bit 0, code bit 1, window-end plane E; both strands in one
+ * circular string) and, weighted kernel types only, wend[n][32 W]; either may be NULL; out_shape = {n, W} */
+int gkmb200_problem_image(gkmb200_problem *p, uint32_t *planes, uint8_t *wend, int *out_shape);
 
 /* ---- measurement ---- */
 /* out[3] = {column blocks, columns per block, first column} of the index variant's last compute call on p (zeros: another variant ran) */

@@ -212,3 +212,32 @@ def test_gkm_shard_reaches_the_pywrapper_only(lib, tmp_path, monkeypatch):
         parts.append(kmat[:n, :n])
     low = np.tril_indices(n, -1)
     assert np.array_equal(parts[0][low] + parts[1][low], g["kmat"][low])
+
+
+@pytest.mark.parametrize("kernel_type,L,M,H", [(2, 11, 50, 50.0), (4, 11, 50, 50.0), (5, 10, 255, 20.0), (4, 3, 1, 3.0)])
+def test_device_packing_equals_host_packing(kernel_type, L, M, H, lib):
+    """the GPU builds the 2-bit plane image (both strands, window-end plane, positional weights by end
+    position) from one byte per base; gkm_seq.c builds the same image on the host for the CPU emulators.  Same bytes."""
+    seqs = random_seqs(257, 400, seed=11, ragged=True)
+    rng = np.random.default_rng(5)
+    for ln in (L, L + 1, 31, 32, 33, 63, 64, 65, 96, 1024, 2046, 2047):
+        if ln >= L:
+            seqs.append(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, ln)].tobytes().decode())
+    seqs = [s for s in seqs if len(s) >= L]
+    seqs[3] = "acgtNNacgtRYacgtacgt" + seqs[3]      # lower case and non-ACGT letters count as A (libgkm.c:864-875)
+    images = {}
+    try:
+        for who in ("device", "host"):
+            capi.set_option("pack", who)
+            with capi.Problem(kernel_type, L, min(L, 7), min(3, L - min(L, 7)), M, H, 1.0) as P:
+                P.add_many(seqs)
+                images[who] = P.image()
+                st = P.stats()
+    finally:
+        capi.set_option("pack", "device")
+    assert np.array_equal(images["device"][0], images["host"][0]), "bit planes"
+    if kernel_type in (4, 5):
+        assert np.array_equal(images["device"][1], images["host"][1]), "positional weights by window end"
+        assert images["device"][1].max() == M
+    else:
+        assert images["device"][1] is None
