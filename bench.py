@@ -544,7 +544,7 @@ def main():
         roofline = {"bound": "l1tex", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
                     "frac": achieved / (peak_gather * 32.0), "traffic": traffic,
                     "traffic_note": "DRAM bytes per launch from the committed ncu capture; the output alone is ~8 B x entries per launch, the rest "
-                                    "is the slot table re-fetched after each L2 flush -- harmless at < 1 % of HBM bandwidth (MEASURED_PEAKS hbm_gbs = %s)" % peaks.get("hbm_gbs"),
+                                    "is the slot table re-fetched after each L2 flush -- harmless at < 1 %% of HBM bandwidth (MEASURED_PEAKS hbm_gbs = %s)" % peaks.get("hbm_gbs"),
                     "note": "index variant: every forward L-mer of a row probes %d 8-byte slots (%d distinct 32-byte sectors) of every L2-resident "
                             "column-block table that starts below the row; achieved = sum over rows of blocks x %d L-mers x sectors x 32 B per pass / time; "
                             "peak = random 16-byte gathers from a 64 MB table measured in this run (x 32 B per sector). This is a UTILISATION of the "

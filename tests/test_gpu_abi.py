@@ -238,6 +238,6 @@ def test_device_packing_equals_host_packing(kernel_type, L, M, H, lib):
     assert np.array_equal(images["device"][0], images["host"][0]), "bit planes"
     if kernel_type in (4, 5):
         assert np.array_equal(images["device"][1], images["host"][1]), "positional weights by window end"
-        assert images["device"][1].max() == M
+        assert images["device"][1].max() == (M if M < 255 else 247)  # M = 255: the centre weight 256 wraps to 0 in the reference's u_int8_t
     else:
         assert images["device"][1] is None
