@@ -529,7 +529,6 @@ def main():
     avg_launch_ms = ms_per_step / launches_mine   # two compute streams overlap launches: this is pass time / launches
     if variant == "index":
         peak_gather = capi.microbench("gather16")     # 1e9 random 16-byte gathers (one 32-byte sector each) per second
-        peak_atoms = capi.microbench("atoms7")        # 1e9 shared-memory atomic adds per second at ~7 active lanes of 32, random columns
         probes, sectors = index_probe_counts(L, D, 8)
         nq = SEQLEN - L + 1
         nblk, blk_cols = layout[0], max(1, layout[1])
@@ -539,27 +538,30 @@ def main():
         achieved = sector_bytes / (ms_per_step * 1e-3) / 1e9
         hpe = hits_per_entry if hits_per_entry is not None else PAIRS_PER_ENTRY * probes / 4.0 ** L
         hits = hpe * total_entries / world
-        t_sectors = sector_bytes / 32.0 / (peak_gather * 1e9)
-        t_hits = hits / (peak_atoms * 1e9)
+        # lanes that are on in the shared atomic of a posting: the postings a probe finds in the wanted range, over the slot's four positions
+        lanes_on = 32.0 * hits / (probed_blocks * nq * probes) / 4.0
+        atoms_kind = "atoms7" if lanes_on < 10.5 else "atoms14"
+        peak_atoms = capi.microbench(atoms_kind)      # 1e9 shared-memory atomic adds per second at ~7 / ~14 active lanes of 32, random columns
+        sector_frac = achieved / (peak_gather * 32.0)
+        hits_rate = hits / (ms_per_step * 1e-3) / 1e9
         roofline = {"bound": "l1tex", "achieved": achieved, "peak": peak_gather * 32.0, "unit": "GB/s",
-                    "frac": achieved / (peak_gather * 32.0), "traffic": traffic,
+                    "frac": sector_frac, "traffic": traffic,
                     "traffic_note": "DRAM bytes per launch from the committed ncu capture; the output alone is ~8 B x entries per launch, the rest "
                                     "is the slot table re-fetched after each L2 flush -- harmless at < 1 %% of HBM bandwidth (MEASURED_PEAKS hbm_gbs = %s)" % peaks.get("hbm_gbs"),
                     "note": "index variant: every forward L-mer of a row probes %d 8-byte slots (%d distinct 32-byte sectors) of every L2-resident "
                             "column-block table that starts below the row; achieved = sum over rows of blocks x %d L-mers x sectors x 32 B per pass / time; "
-                            "peak = random 16-byte gathers from a 64 MB table measured in this run (x 32 B per sector). This is a UTILISATION of the "
-                            "L1TEX gather ceiling by implementation traffic, not algorithmic work; `l1tex_model` adds the irreducible part "
-                            "(one shared atomic per L-mer pair within d)" % (probes, sectors, nq),
+                            "peak = random 16-byte gathers from a 64 MB table measured in this run (x 32 B per sector). A UTILISATION of the L1TEX "
+                            "gather ceiling by implementation traffic, not algorithmic work: the irreducible part is `hits` (one shared atomic per "
+                            "L-mer pair within d). Slot loads and shared atomics are wavefronts of the same L1TEX data pipe: the two fractions add up "
+                            "to the pipe's load, neither reaches 1 alone" % (probes, sectors, nq),
                     "probes_per_lmer": probes, "sectors_per_lmer": sectors, "peak_gather_gsectors": peak_gather,
                     "index_blocks": nblk, "index_block_cols": blk_cols,
                     "hits": {"per_entry": hpe, "per_entry_source": "gkmb200_hist_block on 8 rows of this input" if hits_per_entry is not None else "uniform-sequence expectation",
-                             "per_pass": hits, "achieved_ghits_s": hits / (ms_per_step * 1e-3) / 1e9, "peak_gatoms_s": peak_atoms,
-                             "frac": hits / (ms_per_step * 1e-3) / 1e9 / peak_atoms,
-                             "note": "shared-memory atomic adds at ~7 active lanes per warp instruction on random columns of an 80 KB histogram row "
-                                     "(gkmb200_microbench atoms7), the pattern the hot loop produces"},
-                    "l1tex_model": {"sector_s": t_sectors, "hit_s": t_hits, "sum_s": t_sectors + t_hits, "measured_s": ms_per_step * 1e-3,
-                                    "frac": (t_sectors + t_hits) / (ms_per_step * 1e-3),
-                                    "note": "slot loads and shared atomics share the L1TEX data pipe: lower bound = sectors / gather peak + hits / atomic peak"},
+                             "per_pass": hits, "lanes_on_per_atomic": lanes_on, "achieved_ghits_s": hits_rate, "peak_gatoms_s": peak_atoms,
+                             "frac": hits_rate / peak_atoms,
+                             "note": "peak = shared-memory atomic adds with ~%d of 32 lanes on per warp instruction, random columns of an 80 KB histogram row, two CTAs "
+                                     "of 1024 threads per SM (gkmb200_microbench %s): the pattern of the hot loop at this problem size"
+                                     % (7 if atoms_kind == "atoms7" else 14, atoms_kind)},
                     "int_alu_equivalent": {"achieved_gops": int_alu_equiv, "peak_lop3_gops": peak_lop3, "ratio": int_alu_equiv / peak_lop3,
                                            "note": "SURVEY.md 8d's unit, labelled as such: what the canonical 5-op XOR/POPC form would need for the same "
                                                    "entries/s; the index variant never touches pairs farther apart than d, so this is not a utilisation"},

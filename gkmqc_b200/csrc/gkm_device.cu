@@ -1680,6 +1680,7 @@ extern "C" int gkm_dev_microbench(const char *what, double *result)
             if (gpu_prepare(g, g_sel[0], 0, 0)) { rc = 1; break; }
             if (!strcmp(what, "gather16")) { rc = microbench_gather(g, result); break; }
             if (!strcmp(what, "atoms7")) { rc = microbench_atoms(g, 7u, result); break; }
+            if (!strcmp(what, "atoms14")) { rc = microbench_atoms(g, 14u, result); break; }
             if (!strcmp(what, "atoms32")) { rc = microbench_atoms(g, 32u, result); break; }
             uint32_t *d = NULL;
             if (cudaMalloc(&d, 64) != cudaSuccess) { rc = 1; break; }

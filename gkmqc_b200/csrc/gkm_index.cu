@@ -463,69 +463,6 @@ __device__ __forceinline__ void idx_walk_long(const uint32_t *__restrict__ ovf, 
     }
 }
 
-/* ---- hit queues (HQ > 0): shared atomics with fuller warps ----
- * A probe finds a posting in the wanted column range for a few lanes only: the shared-memory atomic add that counts it
- * runs with ~7 of 32 lanes on at 10k columns, ~14 at 50k -- and costs the same 6-7 clocks of the SM's L1TEX data pipe as
- * one with 32 (gkmb200_microbench atoms7 / atoms32: 0.29 against 1.42 T atomics/s).  At 50k x 50k the four atomics of a
- * warp probe are what bounds the kernel (35 clocks per warp probe against 24 for its sectors).  So a hit is not
- * counted on the spot: the lane appends the histogram word it belongs to (16 bits; with weights 16 more for the
- * product) to a queue of its own in shared memory -- transposed, entry t of lane l at q[t * 32 + l]: no bank conflicts, no
- * cross-lane traffic, one predicated store per posting instead of a branch around an atomic -- and when any lane of the
- * warp runs out of room the warp empties all 32 queues together, entry t of every lane in one atomic. */
-template <int FMT> struct idx_hq { typedef uint16_t type; };          /* C16: histogram word index */
-template <> struct idx_hq<GKM_IDX_FMT_W20> { typedef uint32_t type; }; /* W20: index | wt_a * wt_b << 16 */
-
-template <bool RANGE, typename T>
-__device__ __forceinline__ void idx_push(T *&qp, uint32_t b, uint32_t blo, uint32_t bhi, uint32_t hoff, uint32_t v)
-{
-    bool ok = b < bhi;
-    if (RANGE) ok = ok && b >= blo;
-    if (ok) { *qp = (T) ((hoff + b) | (sizeof(T) == 4 ? (v << 16) : 0u)); qp += 32; } /* hoff holds -blo already */
-}
-
-template <typename T>
-__device__ __forceinline__ void idx_hq_drain(int32_t *H, T *qb, T *&qp)
-{
-    const int n = (int) (qp - qb) >> 5;
-    const int nmax = __reduce_max_sync(0xFFFFFFFFu, n);
-    for (int t = 0; t < nmax; t++)
-        if (t < n) {
-            const uint32_t e = qb[t * 32];
-            if (sizeof(T) == 4) atomicAdd(H + (e & 0xFFFFu), (int) (e >> 16)); else atomicAdd(H + e, 1);
-        }
-    qp = qb;
-}
-
-/* the inline postings of a slot into the lane's hit queue; return value as idx_slot16 / idx_slot20 */
-template <bool RANGE>
-__device__ __forceinline__ uint32_t idx_slot16_q(const uint2 sl, uint16_t *&qp, uint32_t blo, uint32_t bhi, uint32_t hoff)
-{
-    const uint32_t c1 = sl.x >> 16, c3 = sl.y >> 16;
-    idx_push<RANGE>(qp, sl.x & 0xFFFFu, blo, bhi, hoff, 1u);
-    idx_push<RANGE>(qp, c1, blo, bhi, hoff, 1u);
-    if (!(sl.y & GKM_IDX_PTR) || c3 == GKM_IDX_C16_NONE) {
-        idx_push<RANGE>(qp, sl.y & 0xFFFFu, blo, bhi, hoff, 1u);
-        idx_push<RANGE>(qp, c3, blo, bhi, hoff, 1u);
-        return ~0u;
-    }
-    return (c1 < bhi) ? (sl.y & ~GKM_IDX_PTR) : ~0u;
-}
-
-template <bool RANGE>
-__device__ __forceinline__ uint32_t idx_slot20_q(const uint2 sl, uint32_t *&qp, uint32_t blo, uint32_t bhi, uint32_t hoff, uint32_t w)
-{
-    const uint32_t p0 = sl.x & 0xFFFFFu, p1 = (sl.x >> 20) | ((sl.y & 0xFFu) << 12);
-    const uint32_t c0 = p0 & GKM_IDX_W20_COL_MASK, c1 = p1 & GKM_IDX_W20_COL_MASK;
-    idx_push<RANGE>(qp, c0, blo, bhi, hoff, w * (p0 >> GKM_IDX_W20_COL_BITS));
-    idx_push<RANGE>(qp, c1, blo, bhi, hoff, w * (p1 >> GKM_IDX_W20_COL_BITS));
-    if (!(sl.y & GKM_IDX_PTR) || c0 == GKM_IDX_W20_COL_MASK) {
-        const uint32_t p2 = (sl.y >> 8) & 0xFFFFFu;
-        idx_push<RANGE>(qp, p2 & GKM_IDX_W20_COL_MASK, blo, bhi, hoff, w * (p2 >> GKM_IDX_W20_COL_BITS));
-        return ~0u;
-    }
-    return (c1 < bhi) ? ((((sl.y >> 9) & 0x3FFFFFu) << 2) | ((sl.y >> 8) & GKM_IDX_LONG)) : ~0u;
-}
-
 /* queue entries.  o = offset of the overflow list in entries (a multiple of 8 / 4) | GKM_IDX_LONG */
 template <bool C16> struct idx_qe;
 template <> struct idx_qe<true> {
@@ -640,14 +577,11 @@ __device__ __forceinline__ void idx_drain(const gkm_idx_rowargs &r, typename idx
  * would stall the other 31 behind a dependent load in divergent code, and nearly every warp probe has one -- but
  * pushes (list, bin row, weight) on the warp's queue in shared memory; whenever 32 walks are queued the warp runs
  * them together (idx_drain). */
-template <bool WEIGHTED, bool RANGE, int FMT, int UNR, int HQ>
+template <bool WEIGHTED, bool RANGE, int FMT, int UNR>
 __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_begin, int t_end, const uint32_t *xq, const uint8_t *wq,
                                               int nq, int32_t *H, int mbase, int ldh, uint32_t blo, uint32_t bhi,
-                                              typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *queue, typename idx_hq<FMT>::type *hqb)
+                                              typename idx_qe<FMT == GKM_IDX_FMT_C16>::type *queue)
 {
-    typedef typename idx_hq<FMT>::type hq_t;
-    hq_t *hqp = hqb;                                /* next free entry of this lane's hit queue (HQ > 0) */
-    hq_t *const hqlim = hqb + (HQ - (FMT == GKM_IDX_FMT_C16 ? 4 : 3)) * 32; /* beyond it the postings of one more slot may not fit */
     typedef idx_qe<FMT == GKM_IDX_FMT_C16> QE;
     const int tid = (int) threadIdx.x, lane = tid & 31;
     const uint32_t lt = (1u << lane) - 1u;
@@ -667,7 +601,6 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
         const uint32_t dx = dl & 0x0FFFFFFFu;
         const int mrow = lane_ok ? (int) (dl >> 28) - mbase : 0;
         int32_t *Hm = H + (size_t) mrow * (size_t) ldh;
-        const uint32_t hoff = (uint32_t) (mrow * ldh) - (RANGE ? blo : 0u); /* histogram word of column 0 of this lane's bin */
         const uint32_t bhi_l = lane_ok ? bhi : 0u; /* a lane without a mask never hits */
         const int n_it = (nq + nph - 1) / nph;     /* the same for every lane */
         for (int it = 0; it < n_it; it += UNR) {
@@ -686,11 +619,7 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 uint32_t o;
-                if constexpr (HQ > 0 && FMT != GKM_IDX_FMT_P32) {
-                    if (__any_sync(0xFFFFFFFFu, hqp > hqlim)) idx_hq_drain(H, hqb, hqp);
-                    if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16_q<RANGE>(sc[u], hqp, blo, bhi_l, hoff);
-                    else o = idx_slot20_q<RANGE>(sc[u], hqp, blo, bhi_l, hoff, (uint32_t) w[u]);
-                } else if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bhi_l);
+                if constexpr (FMT == GKM_IDX_FMT_C16) o = idx_slot16<RANGE>(sc[u], Hm, blo, bhi_l);
                 else if constexpr (FMT == GKM_IDX_FMT_W20) o = idx_slot20<RANGE>(sc[u], Hm, blo, bhi_l, w[u]);
                 else o = idx_slot<WEIGHTED, RANGE>(sl[u], Hm, blo, bhi_l, w[u]);
                 const uint32_t mk = __ballot_sync(0xFFFFFFFFu, o != ~0u);
@@ -711,11 +640,9 @@ __device__ __forceinline__ void idx_probe_hot(const gkm_idx_rowargs &r, int t_be
     __syncwarp();
     idx_drain<WEIGHTED, RANGE, FMT>(r, lane < qn ? queue[lane] : QE::none(), lane < qn, H, ldh, blo, bhi, lq, lqn, lt);
     if (lqn) idx_long<WEIGHTED, RANGE, FMT>(r, lq, lqn, H, ldh, blo, bhi, lane);
-    if constexpr (HQ > 0 && FMT != GKM_IDX_FMT_P32) idx_hq_drain(H, hqb, hqp);
-    (void) hqlim;
 }
 
-template <bool WEIGHTED, bool RANGE, int FMT, int MINB, int HQ>
+template <bool WEIGHTED, bool RANGE, int FMT, int MINB>
 __global__ void __launch_bounds__(GKM_IDX_THREADS, MINB)
 gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gkm_idx_rowargs r)
 {
@@ -741,11 +668,6 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     int *lqcnt = reinterpret_cast<int *>(qbase + GKM_IDX_QBYTES_FMT(FMT == GKM_IDX_FMT_C16)) - GKM_IDX_THREADS / 32 + (tid >> 5); /* cold phase only */
     uint32_t *xq = reinterpret_cast<uint32_t *>(qbase + GKM_IDX_QBYTES_FMT(FMT == GKM_IDX_FMT_C16));
     uint8_t *wq = reinterpret_cast<uint8_t *>(xq + r.maxq);
-    /* hit queues behind the query (16-byte aligned): HQ entries per lane, transposed per warp */
-    typedef typename idx_hq<FMT>::type hq_t;
-    hq_t *hqb = reinterpret_cast<hq_t *>(smem + (((size_t) nhot * (size_t) ldh * 4 + GKM_IDX_QBYTES_FMT(FMT == GKM_IDX_FMT_C16) +
-                                                  (size_t) r.maxq * (WEIGHTED ? 5 : 4) + 15) & ~(size_t) 15)) +
-                (size_t) (tid >> 5) * (size_t) (HQ > 0 ? HQ : 1) * 32 + (size_t) (tid & 31);
 
     const int ncol = (int) (bhi - blo);
     for (int m = 0; m < nhot; m++)
@@ -769,7 +691,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     /* weighted types at two CTAs per SM: two loads in flight per thread instead of four (the same number per SM as one
      * CTA with four) keep the 32-register build nearly spill-free: wgkm at 10k 50.7 -> 47.8 ms (tools/wgkm_ab.py) */
     constexpr int UNR = (WEIGHTED && MINB == 2) ? 2 : GKM_IDX_UNROLL;
-    idx_probe_hot<WEIGHTED, RANGE, FMT, UNR, HQ>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue, hqb);
+    idx_probe_hot<WEIGHTED, RANGE, FMT, UNR>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
     __syncthreads();
 
     /* epilogue: histogram -> normalised double, the reference's operation order */
@@ -815,9 +737,6 @@ unsigned gkm_idx_row_smem(int nbins, int ldh, int maxq, int weighted, int c16)
     return (unsigned) ((s + 15) & ~(size_t) 15);
 }
 
-/* bytes of the hit queues of one CTA: hq entries per thread, 2 bytes (unit weights) or 4 (weights) each */
-static unsigned idx_hq_bytes(int hq, int weighted) { return (unsigned) (GKM_IDX_THREADS * hq * (weighted ? 4 : 2)); }
-
 size_t gkm_idx_cold_bytes(int nbins, int ldh, int rows)
 {
     const int ncoldb = nbins > GKM_IDX_HOT_BINS ? nbins - GKM_IDX_HOT_BINS : 0;
@@ -852,36 +771,19 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
     if (weighted && ra->skew > GKM_IDX_SKEW_ONE_CTA) two = false;
     { const char *e = getenv("GKM_IDX_MINB"); if (e) two = atoi(e) == 2; } /* A/B knob */
     if ((ra->fmt == GKM_IDX_FMT_C16 && weighted) || (ra->fmt == GKM_IDX_FMT_W20 && !weighted)) { gkm_set_error("index slot format does not match the kernel type"); return 1; }
-    /* hit queues (idx_push / idx_hq_drain): 16 or 8 entries per lane where shared memory has the room, none for the
-     * 16-byte slots.  GKM_IDX_HQ = 0 | 8 | 16 forces a depth (A/B). */
-    int hq = 0;
-    if (ra->fmt != GKM_IDX_FMT_P32) {
-        const unsigned cap = two ? 227u * 1024u / 2u - 1280u : 227u * 1024u - 1280u;
-        const char *e = getenv("GKM_IDX_HQ");
-        const int want = e ? atoi(e) : 16;
-        for (int c = 16; c >= 8; c >>= 1)
-            if (c <= want && smem + idx_hq_bytes(c, weighted) <= cap) { hq = c; break; }
-    }
-    const unsigned smem_all = smem + (hq ? idx_hq_bytes(hq, weighted) : 0u);
     const void *fn;
-#define GKM_IDX_PICK3(W, R, F, B) (hq == 16 ? (const void *) gkm_index_rows_kernel<W, R, F, B, 16> : hq == 8 ? (const void *) gkm_index_rows_kernel<W, R, F, B, 8> \
-                                                                                                  : (const void *) gkm_index_rows_kernel<W, R, F, B, 0>)
-#define GKM_IDX_PICK(W, F) (range ? (two ? GKM_IDX_PICK3(W, true, F, 2) : GKM_IDX_PICK3(W, true, F, 1)) \
-                                  : (two ? GKM_IDX_PICK3(W, false, F, 2) : GKM_IDX_PICK3(W, false, F, 1)))
-#define GKM_IDX_PICK0(W, F) (range ? (two ? (const void *) gkm_index_rows_kernel<W, true, F, 2, 0> : (const void *) gkm_index_rows_kernel<W, true, F, 1, 0>) \
-                                   : (two ? (const void *) gkm_index_rows_kernel<W, false, F, 2, 0> : (const void *) gkm_index_rows_kernel<W, false, F, 1, 0>))
+#define GKM_IDX_PICK(W, F) (range ? (two ? (const void *) gkm_index_rows_kernel<W, true, F, 2> : (const void *) gkm_index_rows_kernel<W, true, F, 1>) \
+                                  : (two ? (const void *) gkm_index_rows_kernel<W, false, F, 2> : (const void *) gkm_index_rows_kernel<W, false, F, 1>))
     if (ra->fmt == GKM_IDX_FMT_C16) fn = GKM_IDX_PICK(false, GKM_IDX_FMT_C16);
     else if (ra->fmt == GKM_IDX_FMT_W20) fn = GKM_IDX_PICK(true, GKM_IDX_FMT_W20);
-    else if (weighted) fn = GKM_IDX_PICK0(true, GKM_IDX_FMT_P32);
-    else fn = GKM_IDX_PICK0(false, GKM_IDX_FMT_P32);
+    else if (weighted) fn = GKM_IDX_PICK(true, GKM_IDX_FMT_P32);
+    else fn = GKM_IDX_PICK(false, GKM_IDX_FMT_P32);
 #undef GKM_IDX_PICK
-#undef GKM_IDX_PICK0
-#undef GKM_IDX_PICK3
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_all);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e == cudaSuccess) {
         void *args[] = { (void *) kp, (void *) ra };
-        e = cudaLaunchKernel(fn, dim3((unsigned) rows, 1, 1), dim3(GKM_IDX_THREADS, 1, 1), args, smem_all, st);
+        e = cudaLaunchKernel(fn, dim3((unsigned) rows, 1, 1), dim3(GKM_IDX_THREADS, 1, 1), args, smem, st);
     }
-    if (e != cudaSuccess) { gkm_set_error("CUDA: index row kernel (%u bytes of shared memory): %s", smem_all, cudaGetErrorString(e)); return 1; }
+    if (e != cudaSuccess) { gkm_set_error("CUDA: index row kernel (%u bytes of shared memory): %s", smem, cudaGetErrorString(e)); return 1; }
     return 0;
 }

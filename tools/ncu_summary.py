@@ -8,7 +8,9 @@ rep, raw_out, variant, source = sys.argv[1:5]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True, check=True).stdout
 open(raw_out, "w").write(raw)
 rows = list(csv.reader(raw.splitlines()))
-h, v = rows[0], rows[2]
+h = rows[0]
+pick = int(sys.argv[5]) if len(sys.argv) > 5 else 0   # which captured launch (0 = first)
+v = rows[2 + pick]
 col = {k: i for i, k in enumerate(h)}
 
 
@@ -19,8 +21,13 @@ def f(name, default=None):
         return default
 
 
+import hashlib, os
+_h = hashlib.sha256()
+for _f in ("gkm_index.cu", "gkm_index.h", "gkm_index_dev.h"):   # bench.py:kernel_source_hash -- the capture belongs to this source
+    _h.update(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gkmqc_b200", "csrc", _f), "rb").read())
 out = {
     "variant": variant,
+    "source_sha256": _h.hexdigest()[:16],
     "source": source + "; " + raw_out,
     "kernel": v[col["Kernel Name"]],
     "grid": v[col["Grid Size"]] if "Grid Size" in col else None,

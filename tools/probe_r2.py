@@ -117,21 +117,4 @@ if "variants" in what:
         print(kern, res["variants"][kern], flush=True); save()
 save()
 
-if "hq" in what:
-    # hit queues of the index kernel (GKM_IDX_HQ = entries per lane; 0 = atomics on the spot, the round-1 kernel)
-    res["hq"] = {}
-    a10, a50, a600, a20 = bench.synth(10000), bench.synth(50000), bench.synth(10000, seed=4321, seqlen=600), bench.synth(20000)
-    for hq in ("0", "8", "16"):
-        os.environ["GKM_IDX_HQ"] = hq
-        for tag, arr, args in (("t2_10k", a10, (2, 11, 7, 3)), ("t4_10k", a10, (4, 11, 7, 3)), ("t2_50k", a50, (2, 11, 7, 3)), ("t4_50k", a50, (4, 11, 7, 3)),
-                               ("t4_L10_600bp", a600, (4, 10, 6, 3)), ("t2_20k_d4", a20, (2, 11, 7, 4)), ("t2_20k_d3", a20, (2, 11, 7, 3))):
-            res["hq"]["%s_hq%s" % (tag, hq)] = resident(*args, arr, kernel="index", steps=2 if "50k" not in tag else 1)
-            print(tag, "hq", hq, res["hq"]["%s_hq%s" % (tag, hq)], flush=True); save()
-    for minb in ("1", "2"):
-        os.environ["GKM_IDX_MINB"] = minb
-        for hq in ("0", "8", "16"):
-            os.environ["GKM_IDX_HQ"] = hq
-            res["hq"]["t2_10k_minb%s_hq%s" % (minb, hq)] = resident(2, 11, 7, 3, a10, kernel="index")
-            print("t2_10k minb", minb, "hq", hq, res["hq"]["t2_10k_minb%s_hq%s" % (minb, hq)], flush=True); save()
-    os.environ.pop("GKM_IDX_MINB"); os.environ.pop("GKM_IDX_HQ")
-    save()
+save()
