@@ -104,6 +104,10 @@ struct gkm_image {
     uint8_t *wend;
     double *sqnorm;
     uint8_t *codes;     /* device packing: the base codes as uploaded (one byte per base), kept until release */
+    uint32_t *pimg;     /* "mma" variant: copy of planes with a 16-byte row pitch, the source of its TMA loads */
+    size_t pimg_bytes;
+    CUtensorMap tmap;   /* 2-D map over pimg: {P words, n rows}, box {box words, 1 row} */
+    gkm_mma_args mma;
     size_t planes_bytes, lens_bytes, wend_bytes, sqnorm_bytes, codes_bytes; /* block sizes as handed out by the pool */
     double *full;       /* resident N x ldfull result (bench, svm consumer) */
     size_t full_ld;
@@ -256,7 +260,7 @@ static int base_variant(const gkmb200_problem *p)
 static int pick_variant(const gkmb200_problem *p, int mode)
 {
     int v = (p->dev && p->dev->variant) ? p->dev->variant : base_variant(p);
-    if (v == GKM_KERNEL_INDEX && mode == GKM_MODE_DIAG) v = GKM_KERNEL_DIAG; /* sqnorm: n pairs only */
+    if ((v == GKM_KERNEL_INDEX || v == GKM_KERNEL_MMA) && mode == GKM_MODE_DIAG) v = GKM_KERNEL_DIAG; /* sqnorm: n pairs only */
     return v;
 }
 
@@ -299,6 +303,49 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
     return 0;
 }
 
+static int pool_alloc(gkm_gpu *g, void **out, size_t *got, size_t bytes);
+
+/* "mma" variant: the 16-byte-pitched copy of the plane image and the TMA descriptor over it, made on first use */
+typedef CUresult (*gkm_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int ensure_mma(const gkmb200_problem *p, gkm_image *im, gkm_gpu *g, cudaStream_t st)
+{
+    if (im->pimg) return 0;
+    const size_t n = (size_t) p->n, W3 = 3 * (size_t) p->Wmax;
+    const size_t P = (W3 + 3) & ~(size_t) 3;
+    static gkm_encode_tiled_fn encode = NULL;
+    if (!encode) {
+        void *fn = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            gkm_set_error("mma variant: the driver has no cuTensorMapEncodeTiled");
+            return 1;
+        }
+        encode = (gkm_encode_tiled_fn) fn;
+    }
+    if (pool_alloc(g, (void **) &im->pimg, &im->pimg_bytes, n * P * 4)) return 1;
+    CK(cudaMemsetAsync(im->pimg, 0, n * P * 4, st));
+    CK(cudaMemcpy2DAsync(im->pimg, P * 4, im->planes, W3 * 4, W3 * 4, n, cudaMemcpyDeviceToDevice, st));
+    im->mma.P = (int) P;
+    im->mma.nbox = (int) ((P + GKM_MMA_TMA_BOX - 1) / GKM_MMA_TMA_BOX);
+    im->mma.box = (int) ((((P + im->mma.nbox - 1) / im->mma.nbox) + 31) & ~(size_t) 31); /* 128-byte pieces: every box lands 128-byte aligned */
+    const int maxnk = p->maxlen - p->param.L + 1;
+    im->mma.QA = GKM_MMA_ROWS_CAP / (maxnk > 0 ? maxnk : 1);
+    if (im->mma.QA > GKM_MMA_QA) im->mma.QA = GKM_MMA_QA;
+    if (im->mma.QA < 1) { gkm_set_error("sequence too long for the mma kernel"); return 1; }
+    const cuuint64_t gdim[2] = { (cuuint64_t) P, (cuuint64_t) n };
+    const cuuint64_t gstr[1] = { (cuuint64_t) P * 4 };
+    const cuuint32_t box[2] = { (cuuint32_t) im->mma.box, 1 };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult r = encode(&im->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, im->pimg, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { gkm_set_error("mma variant: cuTensorMapEncodeTiled failed (%d)", (int) r); return 1; }
+    return 0;
+}
+
 static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g, gkm_kparams kp, cudaStream_t st, int *variant_out)
 {
     const int variant = pick_variant(p, kp.mode);
@@ -328,12 +375,23 @@ static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g
         kp.TA = cand[chosen][0];
         kp.TB = cand[chosen][1];
     } else if (variant == GKM_KERNEL_MMA) {
+        gkm_image *imw = const_cast<gkm_image *>(im);
+        if (ensure_mma(p, imw, g, st)) return 1;
+        if (st == g->sc) { CK(cudaEventRecord(g->join, g->sc)); CK(cudaStreamWaitEvent(g->sc2, g->join, 0)); } /* the other compute stream sees the copy too */
         fn = p->weighted ? (const void *) gkm_mma_kernel<true> : (const void *) gkm_mma_kernel<false>;
-        smem = gkm_mma_smem_bytes(p->Wa, p->nbins, p->weighted);
-        if (smem > 220u * 1024u) { gkm_set_error("sequence too long for the mma kernel"); return 1; }
-        if (smem < 100u * 1024u) smem = 100u * 1024u; /* at most 2 CTAs per SM: each holds 256 of the 512 TMEM columns */
-        kp.TA = 1;
+        const int maxnk = p->maxlen - p->param.L + 1;
+        const int tiles = (im->mma.QA * maxnk + GKM_MMA_M - 1) / GKM_MMA_M;
+        smem = gkm_mma_smem_bytes(tiles, gkm_mma_stage_words(im->mma), p->nbins, p->weighted);
+        if (smem > 227u * 1024u) { gkm_set_error("sequence too long for the mma kernel"); return 1; }
+        kp.TA = im->mma.QA;
         kp.TB = GKM_MMA_TB;
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        dim3 grid((unsigned) ((cols + kp.TB - 1) / kp.TB), (unsigned) ((rows + kp.TA - 1) / kp.TA), 1);
+        if (grid.y > 65535u) { gkm_set_error("chunk has too many row tiles"); return 1; }
+        void *args[] = { &kp, (void *) &im->mma, (void *) &im->tmap };
+        CK(cudaLaunchKernel(fn, grid, dim3(GKM_MMA_THREADS, 1, 1), args, smem, st));
+        if (variant_out) *variant_out = variant;
+        return 0;
     } else {
         fn = p->weighted ? (const void *) gkm_lmer_kernel<true> : (const void *) gkm_lmer_kernel<false>;
         static const int cand[][2] = { {8, 8}, {4, 4}, {2, 2}, {1, 1} };
@@ -664,6 +722,7 @@ extern "C" void gkm_dev_release(gkmb200_problem *p)
         pool_free(g, im->wend, im->wend_bytes);
         pool_free(g, im->sqnorm, im->sqnorm_bytes);
         pool_free(g, im->codes, im->codes_bytes);
+        pool_free(g, im->pimg, im->pimg_bytes);
         release_index(g, im);
         cudaFree(im->full);
     }

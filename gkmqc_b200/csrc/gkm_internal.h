@@ -50,6 +50,7 @@ struct gkmb200_problem {
     int packed;
     int Wmax;        /* 32-bit words per bit plane = ceil(2*maxlen / 32): both strands in one circular string */
     int Wa;          /* ceil(maxlen / 32): 32-position chunks of a query */
+    int maxlen;      /* longest sequence */
     uint32_t *planes;/* [n][3][Wmax]: code bit 0, code bit 1, valid-window-end plane E */
     uint8_t *wend;   /* weighted only: [n][32*Wmax] weight by window END position */
     double *sqnorm;  /* [n], filled by the device */

@@ -31,7 +31,16 @@
 
 #include "gkm_diag_kernel.cuh" /* gkm_emit_entry */
 
-#define GKM_MMA_THREADS 384      /* warps 0-7 epilogue, 8 MMA, 9 TMA, 10-11 builders */
+#ifndef GKM_MMA_EPI
+#define GKM_MMA_EPI 16           /* epilogue warps: TMEM lane quarter (w & 3) x column group (w >> 2) */
+#endif
+#define GKM_MMA_CW (GKM_MMA_N / (GKM_MMA_EPI / 4))   /* accumulator columns per epilogue warp */
+#ifndef GKM_MMA_PACK16
+#define GKM_MMA_PACK16 1         /* tcgen05.ld ... .pack::16b: two adjacent accumulator columns per register (0: one) */
+#endif
+#define GKM_MMA_NV (GKM_MMA_PACK16 ? GKM_MMA_CW / 2 : GKM_MMA_CW)   /* registers of one epilogue thread per tile */
+#define GKM_MMA_HSETS (GKM_MMA_EPI / 4)              /* histogram sets: one per column group */
+#define GKM_MMA_THREADS ((GKM_MMA_EPI + 4) * 32)     /* epilogue warps, then MMA, TMA, two builder warps */
 #define GKM_MMA_M 128
 #define GKM_MMA_N 256
 #define GKM_MMA_TB 8             /* targets per CTA */
@@ -39,6 +48,9 @@
 #define GKM_MMA_ROWS_CAP 2176    /* stacked query L-mers per CTA (17 tiles of 128: 136 KB of A operand) */
 #define GKM_MMA_BUILDERS 64
 #define GKM_MMA_TMA_BOX 256      /* elements of one TMA box along a plane row, at most */
+#ifndef GKM_MMA_EXP
+#define GKM_MMA_EXP 0            /* timing experiments (tools/ab_variants.sh): 1 no compares, 2 no MMA, 4 no B build, 8 no TMEM loads */
+#endif
 
 struct gkm_mma_args {
     int QA;        /* queries per CTA for this launch: min(4, ROWS_CAP / longest query) */
@@ -56,8 +68,8 @@ __host__ __device__ inline unsigned gkm_mma_smem_bytes(int rows_cap_tiles, int s
     o += 2u * GKM_MMA_N * 64u;                                       /* B operand ring */
     o += (unsigned) (GKM_MMA_QA + GKM_MMA_TB) * (unsigned) stage_words * 4u;   /* plane rows as TMA delivers them */
     o += (unsigned) rows_cap_tiles * GKM_MMA_M;                      /* query of every stacked row */
-    o += GKM_MMA_QA * GKM_MMA_TB * (unsigned) nbins * 4u;            /* histograms */
-    if (weighted) o += (unsigned) rows_cap_tiles * GKM_MMA_M + 2u * GKM_MMA_N;
+    o += (unsigned) GKM_MMA_HSETS * GKM_MMA_QA * GKM_MMA_TB * (unsigned) nbins * 4u;   /* histograms, one set per column group */
+    if (weighted) o += (unsigned) rows_cap_tiles * GKM_MMA_M + 8u * GKM_MMA_N;
     return (o + 127u) & ~127u;
 }
 
@@ -74,7 +86,9 @@ __device__ __forceinline__ uint64_t gkm_umma_desc(uint32_t saddr, uint32_t lbo16
 
 /* one operand row (64 bytes = 16 words, word t = one-hot byte of base t) as 4 chunks of 16 bytes:
  * chunk kc of row r lives at base + kc*rows*16 + r*16 */
-__device__ __forceinline__ void gkm_mma_store_row(unsigned char *base, int rows, int r, uint32_t p0, uint32_t p1, int L, bool valid)
+/* `spare` goes into word L, the first K bytes behind the L-mer (zero for L = 16 and for rows of padding): the bias
+ * factors of gkm_mma_bias */
+__device__ __forceinline__ void gkm_mma_store_row(unsigned char *base, int rows, int r, uint32_t p0, uint32_t p1, int L, bool valid, uint32_t spare)
 {
 #pragma unroll
     for (int kc = 0; kc < 4; kc++) {
@@ -83,7 +97,7 @@ __device__ __forceinline__ void gkm_mma_store_row(unsigned char *base, int rows,
         for (int u = 0; u < 4; u++) {
             const int t = 4 * kc + u;
             const uint32_t code = ((p0 >> t) & 1u) | (((p1 >> t) & 1u) << 1);
-            w[u] = (valid && t < L) ? (1u << (8u * code)) : 0u;
+            w[u] = !valid ? 0u : (t < L) ? (1u << (8u * code)) : (t == L) ? spare : 0u;
         }
         *reinterpret_cast<uint4 *>(base + (size_t) kc * rows * 16 + (size_t) r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -97,6 +111,15 @@ __device__ __forceinline__ void gkm_lmer_planes(const uint32_t *pl, int W, int o
     p0 = __funnelshift_r(pl[wi], n0, sh) & mask;
     p1 = __funnelshift_r(pl[W + wi], n1, sh) & mask;
 }
+
+/* The threshold test rides on the MMA.  K = 64 bytes hold 4 L <= 60 one-hot bytes; two of the spare ones carry factors
+ * whose product sum is 2^15 - thr (255 * 128 + (128 - thr) * 1, thr = L - d matches needed for a hit), so that every
+ * accumulator of two real L-mers comes out of TMEM as matches + 2^15 - thr: bit 15 is set exactly for the hits.  The
+ * epilogue then rejects 16 accumulators with an OR tree (LOP3, 0.5 instructions per accumulator at full ALU rate) instead of
+ * the 3-input max tree of the first build, which ncu showed to be the bound (VIMNMX3 issues at a fraction of the ALU
+ * rate: 344 of 463 ms at 4 000 sequences).  L = 16 has no spare byte and keeps the max tree. */
+__device__ __forceinline__ uint32_t gkm_mma_bias_a(int L, int thr) { return (L <= 15) ? (255u | ((uint32_t) (128 - thr) << 8)) : 0u; }
+__device__ __forceinline__ uint32_t gkm_mma_bias_b(int L) { return (L <= 15) ? (128u | (1u << 8)) : 0u; }
 
 /* ---- mbarrier helpers.  A wait never hangs the device: a lost arrival is a hard error (__trap). ---- */
 __device__ __forceinline__ void gkm_mbar_init(uint64_t *bar, uint32_t count)
@@ -164,11 +187,11 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
             gkm_mbar_init(&bars->b_full[s], GKM_MMA_BUILDERS / 32);
             gkm_mbar_init(&bars->b_empty[s], 1);
             gkm_mbar_init(&bars->acc_full[s], 1);
-            gkm_mbar_init(&bars->acc_empty[s], 8);
+            gkm_mbar_init(&bars->acc_empty[s], GKM_MMA_EPI);
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
-    if (warp == 8) {
+    if (warp == GKM_MMA_EPI) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(gkm_smem_u32(&bars->tmem_slot)), "n"(2 * GKM_MMA_N));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -185,10 +208,13 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
     uint32_t *sPl = reinterpret_cast<uint32_t *>(sBop + 2 * GKM_MMA_N * 64);       /* [QA + TB][SW] */
     uint8_t *sRowQ = reinterpret_cast<uint8_t *>(sPl + (size_t) (GKM_MMA_QA + GKM_MMA_TB) * SW);
     int32_t *sH = reinterpret_cast<int32_t *>(sRowQ + (size_t) MT * GKM_MMA_M);     /* MT*128 is a multiple of 4 */
-    uint8_t *sWa = reinterpret_cast<uint8_t *>(sH + GKM_MMA_QA * GKM_MMA_TB * NBN);
-    uint8_t *sWb = sWa + (WEIGHTED ? MT * GKM_MMA_M : 0);                          /* [2][256] */
+    uint8_t *sWa = reinterpret_cast<uint8_t *>(sH + GKM_MMA_HSETS * GKM_MMA_QA * GKM_MMA_TB * NBN);
+    /* weights of the target L-mers of N tile t live in slot t & 7: the epilogue of tile t still reads them while the
+     * builders fill B stages for later tiles (a stage is free as soon as the MMAs have read it, an accumulator as soon
+     * as it is in registers; with one M tile per N tile the compares of tile t can lag four tiles behind the builders) */
+    uint8_t *sWb = sWa + (WEIGHTED ? MT * GKM_MMA_M : 0);                          /* [8][256] */
 
-    if (warp == 9 && lane == 0) {
+    if (warp == GKM_MMA_EPI + 1 && lane == 0) {
         gkm_mbar_expect_tx(&bars->planes, (uint32_t) (nA + nB) * (uint32_t) SW * 4u);
         for (int q = 0; q < nA; q++)
             for (int b = 0; b < ma.nbox; b++) gkm_tma_row(&tmap, &bars->planes, sPl + (size_t) q * SW + (size_t) b * ma.box, b * ma.box, a0 + q);
@@ -206,7 +232,7 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
         }
         bars->tile0[GKM_MMA_TB] = t0;
     }
-    for (int i = tid; i < GKM_MMA_QA * GKM_MMA_TB * NBN; i += GKM_MMA_THREADS) sH[i] = 0;
+    for (int i = tid; i < GKM_MMA_HSETS * GKM_MMA_QA * GKM_MMA_TB * NBN; i += GKM_MMA_THREADS) sH[i] = 0;
     __syncthreads();
     gkm_mbar_wait(&bars->planes, 0); /* everyone reads the plane rows */
 
@@ -219,7 +245,7 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
         uint32_t p0 = 0, p1 = 0;
         if (valid) gkm_lmer_planes(sPl + (size_t) q * SW, W, li, L, p0, p1);
         const int mt = i / GKM_MMA_M, r = i - mt * GKM_MMA_M;
-        gkm_mma_store_row(sAop + (size_t) mt * GKM_MMA_M * 64, GKM_MMA_M, r, p0, p1, L, valid);
+        gkm_mma_store_row(sAop + (size_t) mt * GKM_MMA_M * 64, GKM_MMA_M, r, p0, p1, L, valid, gkm_mma_bias_a(L, L - d));
         sRowQ[i] = valid ? (uint8_t) q : (uint8_t) 0xFF;
         if (WEIGHTED) sWa[i] = valid ? p.wend[(size_t) (a0 + q) * 32 * W + li + L - 1] : 0;
     }
@@ -230,30 +256,30 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
     const uint32_t tmem_base = bars->tmem_slot;
     const int NTILES = bars->tile0[GKM_MMA_TB];
 
-    if (warp >= 10) {
+    if (warp >= GKM_MMA_EPI + 2) {
         /* ---- builders: target L-mers jj = 256 nt .. +255 over both strands (jj >= nkB: reverse complement) ---- */
-        const int bt = tid - 320;
+        const int bt = tid - (GKM_MMA_EPI + 2) * 32;
         for (int t = 0, b_l = 0; t < NTILES; t++) {
             while (t >= bars->tile0[b_l + 1]) b_l++;
             const int nt = t - bars->tile0[b_l], s = t & 1;
             const int lenB = bars->lenB[b_l], nkB = lenB - L + 1;
             gkm_mbar_wait(&bars->b_empty[s], ((uint32_t) (t >> 1) & 1u) ^ 1u);
             const uint32_t *plb = sPl + (size_t) (GKM_MMA_QA + b_l) * SW;
-            for (int r = bt; r < GKM_MMA_N; r += GKM_MMA_BUILDERS) {
+            for (int r = bt; r < ((GKM_MMA_EXP & 4) ? 0 : GKM_MMA_N); r += GKM_MMA_BUILDERS) {
                 const int jj = GKM_MMA_N * nt + r;
                 const bool valid = jj < 2 * nkB;
                 const int strand = (jj >= nkB) ? 1 : 0;
                 const int o = strand * lenB + (jj - strand * nkB);
                 uint32_t p0 = 0, p1 = 0;
                 if (valid) gkm_lmer_planes(plb, W, o, L, p0, p1);
-                gkm_mma_store_row(sBop + (size_t) s * GKM_MMA_N * 64, GKM_MMA_N, r, p0, p1, L, valid);
-                if (WEIGHTED) sWb[s * GKM_MMA_N + r] = valid ? p.wend[(size_t) (col0 + b_l) * 32 * W + o + L - 1] : 0;
+                gkm_mma_store_row(sBop + (size_t) s * GKM_MMA_N * 64, GKM_MMA_N, r, p0, p1, L, valid, gkm_mma_bias_b(L));
+                if (WEIGHTED) sWb[(t & 7) * GKM_MMA_N + r] = valid ? p.wend[(size_t) (col0 + b_l) * 32 * W + o + L - 1] : 0;
             }
             asm volatile("fence.proxy.async.shared::cta;");
             __syncwarp();
             if (lane == 0) gkm_mbar_arrive(&bars->b_full[s]);
         }
-    } else if (warp == 8) {
+    } else if (warp == GKM_MMA_EPI) {
         /* ---- MMA issuer ---- */
         if (lane == 0) {
             /* instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = unsigned 8 bit (0),
@@ -268,7 +294,7 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
                     gkm_mbar_wait(&bars->acc_empty[buf], ((uint32_t) (j >> 1) & 1u) ^ 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-                    for (int ks = 0; ks < 2; ks++) { /* K = 64 bytes = two K = 32 instructions = chunks (2ks, 2ks+1) */
+                    for (int ks = 0; ks < ((GKM_MMA_EXP & 2) ? 0 : 2); ks++) { /* K = 64 bytes = two K = 32 instructions = chunks (2ks, 2ks+1) */
                         const uint64_t adesc = gkm_umma_desc(gkm_smem_u32(sAop + (size_t) mt * GKM_MMA_M * 64 + (size_t) ks * 2 * GKM_MMA_M * 16), GKM_MMA_M, 8);
                         const uint64_t bdesc = gkm_umma_desc(gkm_smem_u32(sBop + (size_t) s * GKM_MMA_N * 64 + (size_t) ks * 2 * GKM_MMA_N * 16), GKM_MMA_N, 8);
                         const uint32_t acc = ks ? 1u : 0u;
@@ -282,62 +308,106 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
             }
         }
         __syncwarp();
-    } else if (warp < 8) {
+    } else if (warp < GKM_MMA_EPI) {
         /* ---- epilogue: thread = one stacked query L-mer (TMEM lane), 128 target L-mers in 4 loads of 32 columns ---- */
         const int thr = L - d; /* matches needed for a hit; the launcher guarantees thr >= 1 */
-        const int lane_base = 32 * (warp & 3), col_half = (warp >> 2) * (GKM_MMA_N / 2);
+        const int lane_base = 32 * (warp & 3), col_half = (warp >> 2) * GKM_MMA_CW;
         int j = 0;
         for (int t = 0, b_l = 0; t < NTILES; t++) {
             while (t >= bars->tile0[b_l + 1]) b_l++;
-            const int s = t & 1;
             for (int mt = 0; mt < MT; mt++, j++) {
                 const int buf = j & 1;
                 const int i = mt * GKM_MMA_M + lane_base + lane;
-                const int q = sRowQ[i];
-                const int wa = WEIGHTED ? (int) sWa[i] : 1;
-                int32_t *Hq = sH + ((q & 3) * GKM_MMA_TB + b_l) * NBN;
                 gkm_mbar_wait(&bars->acc_full[buf], (uint32_t) (j >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll 1
-                for (int cc = 0; cc < GKM_MMA_N / 2; cc += 32) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t) lane_base << 16) + (uint32_t) (buf * GKM_MMA_N + col_half + cc);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                 : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    /* cheap reject: the maximum of 16 accumulators (3-input max tree) against the threshold, then the exact bins.
-                     * Rows and columns of padding are all-zero operand rows: 0 matches, never a hit (thr >= 1). */
+                /* all columns of this warp's group are requested before the first is looked at (four load -> wait -> compare
+                 * rounds exposed the TMEM latency four times per tile).  GKM_MMA_PACK16: two adjacent columns per register. */
+                uint32_t v[GKM_MMA_NV];
+                const uint32_t taddr = tmem_base + ((uint32_t) lane_base << 16) + (uint32_t) (buf * GKM_MMA_N + col_half);
+#define GKM_LDTM32(o, c, PK) \
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32" PK ".b32 " \
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, " \
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n" \
+                             : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]), \
+                               "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), \
+                               "=r"(v[o + 16]), "=r"(v[o + 17]), "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]), \
+                               "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), "=r"(v[o + 30]), "=r"(v[o + 31]) \
+                             : "r"(taddr + (uint32_t) (c)))
+                if (GKM_MMA_EXP & 8) { for (int u = 0; u < GKM_MMA_NV; u++) v[u] = 0; }
+                else if (GKM_MMA_PACK16) {
+                    GKM_LDTM32(0, 0, ".pack::16b");
+                    if (GKM_MMA_NV > 32) GKM_LDTM32(32 % GKM_MMA_NV, 64, ".pack::16b");
+                } else {
+                    GKM_LDTM32(0, 0, "");
+                    if (GKM_MMA_NV > 32) GKM_LDTM32(32 % GKM_MMA_NV, 32, "");
+                    if (GKM_MMA_NV > 64) { GKM_LDTM32(64 % GKM_MMA_NV, 64, ""); GKM_LDTM32(96 % GKM_MMA_NV, 96, ""); }
+                }
+#undef GKM_LDTM32
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                /* the accumulator is in registers: hand it back to the MMA warp before the compares */
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) gkm_mbar_arrive(&bars->acc_empty[buf]);
+                /* what a hit costs is paid only by a hit: the row's query, weight and histogram are looked up here.  The
+                 * warps of one column group share a histogram set. */
+                auto hit = [&](int col, int matches) {
+                    const int q = sRowQ[i];
+                    int32_t *Hq = sH + ((((warp >> 2) * GKM_MMA_QA) + (q & 3)) * GKM_MMA_TB + b_l) * NBN;
+                    atomicAdd(Hq + (L - matches), WEIGHTED ? (int) sWa[i] * (int) sWb[(t & 7) * GKM_MMA_N + col_half + col] : 1);
+                };
+                /* cheap reject of 16 registers at a time, then the exact bins.  Rows and columns of padding are all-zero
+                 * operand rows: accumulator 0, never a hit. */
+                if (L <= 15) {
+                    /* accumulator = matches + 2^15 - thr (gkm_mma_bias_*): bit 15 marks the hits, an OR tree finds them.
+                     * A hit is rare per accumulator (0.12 % at L = 11, d = 3) but not per WARP: one of the 32 lanes has one
+                     * in a fifth of the groups, and every lane then walks the slow path.  So the slow path is a second look
+                     * at the five partial ORs of the tree (three registers each) and only then at single accumulators. */
+                    constexpr uint32_t HB = GKM_MMA_PACK16 ? 0x80008000u : 0x8000u;
+                    auto look = [&](int r) {
+                        const uint32_t x = v[r];
+                        if (GKM_MMA_PACK16) {
+                            if (x & 0x8000u) hit(2 * r, (int) (x & 0x7FFFu) + thr);
+                            if (x & 0x80000000u) hit(2 * r + 1, (int) ((x >> 16) & 0x7FFFu) + thr);
+                        } else if (x & 0x8000u) hit(r, (int) (x & 0x7FFFu) + thr);
+                    };
 #pragma unroll
-                    for (int g = 0; g < 32; g += 16) {
-                        int mx = max(max((int) v[g], (int) v[g + 1]), (int) v[g + 2]);
-                        mx = max(max(mx, (int) v[g + 3]), (int) v[g + 4]);
-                        mx = max(max(mx, (int) v[g + 5]), (int) v[g + 6]);
-                        mx = max(max(mx, (int) v[g + 7]), (int) v[g + 8]);
-                        mx = max(max(mx, (int) v[g + 9]), (int) v[g + 10]);
-                        mx = max(max(mx, (int) v[g + 11]), (int) v[g + 12]);
-                        mx = max(max(mx, (int) v[g + 13]), (int) v[g + 14]);
-                        mx = max(mx, (int) v[g + 15]);
+                    for (int g = 0; g < ((GKM_MMA_EXP & 1) ? 0 : GKM_MMA_NV); g += 16) {
+                        uint32_t tr[5];
+#pragma unroll
+                        for (int k = 0; k < 5; k++) tr[k] = v[g + 3 * k] | v[g + 3 * k + 1] | v[g + 3 * k + 2];
+                        const uint32_t o = (tr[0] | tr[1] | tr[2]) | (tr[3] | tr[4] | v[g + 15]);
+                        if (o & HB) {
+#pragma unroll
+                            for (int k = 0; k < 5; k++)
+                                if (tr[k] & HB) {
+#pragma unroll
+                                    for (int u = 0; u < 3; u++) look(g + 3 * k + u);
+                                }
+                            look(g + 15);
+                        }
+                    }
+                } else {
+                    /* L = 16: no spare K byte for the bias; 3-input max tree (VIMNMX3) on the plain match counts */
+#pragma unroll
+                    for (int g = 0; g < ((GKM_MMA_EXP & 1) ? 0 : GKM_MMA_NV); g += 16) {
+                        int mx = 0;
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            const uint32_t x = v[g + u];
+                            mx = max(mx, GKM_MMA_PACK16 ? max((int) (x & 0xFFFFu), (int) (x >> 16)) : (int) x);
+                        }
                         if (mx >= thr) {
 #pragma unroll
                             for (int u = 0; u < 16; u++) {
-                                const int m = (int) v[g + u];
-                                if (m >= thr) {
-                                    const int wgt = WEIGHTED ? wa * (int) sWb[s * GKM_MMA_N + col_half + cc + g + u] : 1;
-                                    atomicAdd(Hq + (L - m), wgt);
-                                }
+                                const uint32_t x = v[g + u];
+                                if (GKM_MMA_PACK16) {
+                                    if ((int) (x & 0xFFFFu) >= thr) hit(2 * (g + u), (int) (x & 0xFFFFu));
+                                    if ((int) (x >> 16) >= thr) hit(2 * (g + u) + 1, (int) (x >> 16));
+                                } else if ((int) x >= thr) hit(g + u, (int) x);
                             }
                         }
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;");
-                __syncwarp();
-                if (lane == 0) gkm_mbar_arrive(&bars->acc_empty[buf]);
             }
         }
     }
@@ -346,11 +416,14 @@ gkm_mma_kernel(const __grid_constant__ gkm_kparams p, const __grid_constant__ gk
         const int q = tid / GKM_MMA_TB, b_l = tid - q * GKM_MMA_TB;
         const int a_g = a0 + q, b_g = col0 + b_l;
         const bool skip = q >= nA || b_l >= nB || (p.mode == GKM_MODE_LOWER && b_g >= a_g);
-        if (!skip) gkm_emit_entry(p, a_g, b_g, sH + (q * GKM_MMA_TB + b_l) * NBN);
+        int32_t *h0 = sH + (q * GKM_MMA_TB + b_l) * NBN;
+        for (int w = 1; w < GKM_MMA_HSETS; w++)
+            for (int m = 0; m < NBN; m++) h0[m] += sH[((w * GKM_MMA_QA + q) * GKM_MMA_TB + b_l) * NBN + m];
+        if (!skip) gkm_emit_entry(p, a_g, b_g, h0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * GKM_MMA_N));
+    if (warp == GKM_MMA_EPI) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "n"(2 * GKM_MMA_N));
 }
 
 #endif /* GKM_MMA_KERNEL_CUH_INCLUDED */

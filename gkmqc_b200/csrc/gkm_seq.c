@@ -490,6 +490,7 @@ int gkm_shape_problem(gkmb200_problem *p)
     for (int i = 0; i < p->n; i++) if (p->len[i] > maxlen) maxlen = p->len[i];
     p->Wmax = (2 * maxlen + 31) / 32;
     p->Wa = (maxlen + 31) / 32;
+    p->maxlen = maxlen;
     p->sqnorm = (double *) calloc((size_t) p->n, sizeof(double));
     if (!p->sqnorm) { gkm_set_error("out of memory"); return 1; }
     p->packed = 1;
