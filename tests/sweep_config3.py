@@ -11,7 +11,7 @@ evaluated in the reference's operation order from the reference's integers and t
 (weight routines of libgkm.c through the probe).  Three triples are additionally checked against the doubles
 the reference itself returns (gkmkernel_kernelfunc_batch_all).  Also times one resident pass per (L, d).
 
-    python tools/sweep_config3.py [n] [rows...]      (writes gpurun_out/sweep_config3.json)
+    python tests/sweep_config3.py [n] [rows...]      (writes gpurun_out/sweep_config3.json)
 """
 import json
 import os
