@@ -28,6 +28,9 @@
 #ifndef GKM_IDX_UNROLL
 #define GKM_IDX_UNROLL 4
 #endif
+#ifndef GKM_IDX_WUNR
+#define GKM_IDX_WUNR 2 /* slot loads in flight per thread of the weighted two-CTA build (A/B: 3, 4) */
+#endif
 #define GKM_IDX_QCAP 64 /* queued overflow walks per warp: < 32 waiting + <= 32 new */
 #define GKM_IDX_LQCAP 32 /* long lists waiting for a whole-warp walk, per warp */
 /* Problems of several column blocks run two CTAs per SM only while both fit the 196 KB step of the L1/shared split
@@ -690,7 +693,7 @@ gkm_index_rows_kernel(const __grid_constant__ gkm_kparams p, const __grid_consta
     if (r.ncold > 0) idx_probe_cold<WEIGHTED, RANGE, FMT>(r, 0, r.ncold, xq, wq, nq, C, ldh, blo, bhi, queue + GKM_IDX_QCAP, lqcnt);
     /* weighted types at two CTAs per SM: two loads in flight per thread instead of four (the same number per SM as one
      * CTA with four) keep the 32-register build nearly spill-free: wgkm at 10k 50.7 -> 47.8 ms (tools/wgkm_ab.py) */
-    constexpr int UNR = (WEIGHTED && MINB == 2) ? 2 : GKM_IDX_UNROLL;
+    constexpr int UNR = (WEIGHTED && MINB == 2) ? GKM_IDX_WUNR : GKM_IDX_UNROLL;
     idx_probe_hot<WEIGHTED, RANGE, FMT, UNR>(r, r.ncold, r.ndelta, xq, wq, nq, H, ncoldb, ldh, blo, bhi, queue);
     __syncthreads();
 
