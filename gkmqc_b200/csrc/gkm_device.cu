@@ -1251,8 +1251,12 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
     pthread_mutex_lock(&g_lock);
     const double t0 = now_ms();
     p->stats.launches = 0;
-    const char *ord = getenv("GKM_CHUNK_ORDER"); /* A/B knob: "asc" = rows in ascending order */
-    const int desc = lower && !(ord && ord[0] == 'a');
+    /* Chunks are issued in ascending row order.  Round 1 issued the widest rows first so that the call ends on the smallest
+     * copy; that saves < 1 ms at 10k and costs the weighted kernel types dearly (wgkm 10k x 300 bp: device span 59.0
+     * against 47.3 ms; gkmQC's default, 600-bp windows: 312 against 237 ms; unit weights: equal) -- tools/order_ab.py.
+     * GKM_CHUNK_ORDER=desc brings the old order back (A/B knob). */
+    const char *ord = getenv("GKM_CHUNK_ORDER");
+    const int desc = lower && ord && ord[0] == 'd';
     int rc = upload_locked(p, 0);
     const double t_up = now_ms();
     if (!rc) rc = choose_variant(p, row0, nrows, col0, ncols, lower);
@@ -1275,8 +1279,6 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
             gkm_job job;
             memset(&job, 0, sizeof(job));
             job.p = p; job.chunks = chunks; job.owned = owned;
-            /* triangle: widest chunks first, so that the call ends on the chunk with the smallest copy and scatter
-             * (the last D2H + scatter cannot overlap anything; rows 0..591 are 2.8 MB, the last 592 rows 47 MB) */
             for (int i = 0; i < nchunks; i++) {
                 const int c = desc ? nchunks - 1 - i : i;
                 if (gkm_chunk_owner(c, nchunks, p->shard_world) == p->shard_rank) owned[job.nowned++] = c;

@@ -783,6 +783,18 @@ int gkm_idx_rows(const gkm_kparams *kp, const gkm_idx_rowargs *ra, int weighted,
     else fn = GKM_IDX_PICK(false, GKM_IDX_FMT_P32);
 #undef GKM_IDX_PICK
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    {   /* Ask for no more shared memory per SM than this launch's CTAs need: what is left is L1, where the in-flight slot
+         * probes live.  Without the hint the split of an earlier, larger launch can stay in force (rows issued widest
+         * first ran the weighted build 25 % slower than ascending: tools/order_ab.py).  GKM_IDX_CARVEOUT=0: no hint. */
+        static int use = -1;
+        if (use < 0) { const char *c = getenv("GKM_IDX_CARVEOUT"); use = !(c && c[0] == '0'); }
+        if (use && e == cudaSuccess) {
+            const unsigned per_sm = (two ? 2u : 1u) * (smem + 1280u);
+            int pct = (int) ((per_sm * 100u + 228u * 1024u - 1u) / (228u * 1024u));
+            if (pct > 100) pct = 100;
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    }
     if (e == cudaSuccess) {
         void *args[] = { (void *) kp, (void *) ra };
         e = cudaLaunchKernel(fn, dim3((unsigned) rows, 1, 1), dim3(GKM_IDX_THREADS, 1, 1), args, smem, st);
