@@ -604,6 +604,17 @@ def main():
         w2 = e2e_of(pos2, neg2, n2, kernel_type=KTYPE, L=L, k=K, d=D)
         sec1 = {"workload": "BASELINE configs[1]: 5k + 5k x 300 bp, type 2, L=11 k=7 d=3", "value": e2 / (float(m2.mean()) * 1e-3),
                 "ms_per_step": float(m2.mean()), "e2e": {"value": e2 / w2, "ms_per_step": 1e3 * w2}, "unit": "entries/s"}
+        # a caller pinned to ONE core (a slurm job that asked for one): the copy-out runs on that core alone
+        try:
+            full_mask = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, {sorted(full_mask)[0]})
+            try:
+                w1 = e2e_of(pos2, neg2, n2, reps=2, kernel_type=KTYPE, L=L, k=K, d=D)
+            finally:
+                os.sched_setaffinity(0, full_mask)
+            sec1["e2e_one_core"] = {"value": e2 / w1, "ms_per_step": 1e3 * w1, "note": "same call with the process's affinity mask cut to one core"}
+        except Exception as e:
+            sec1["e2e_one_core"] = {"error": str(e)}
         with capi.Problem(4, L, K, D, 50, 50.0, 1.0) as P4:
             P4.read(pos2, neg2)
             ms4 = P4.bench_lower_resident(3, 2, flush_l2=True)
