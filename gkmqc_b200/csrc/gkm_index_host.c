@@ -109,7 +109,12 @@ double gkm_idx_cost_ms(int L, int d, int weighted, long long rows, double mean_q
     const double scale = weighted ? 0.86 : 1.0;
     const double probes = (double) rows * mean_query_lmers * nd * col_blocks;
     const double hits = (double) entries * mean_pairs_per_entry * nd / slots; /* random sequences: P(distance <= d) = nd / 4^L */
-    double t = probes / (8.7e11 * scale) + hits / (4.1e11 * scale);
+    /* postings found per probe: with several per probe the lanes of a warp share their shared atomics and overflow walks
+     * (fuller warps), and the hit side runs up to 1.7x faster (round 2: L = 10, d = 4 at 20k, 3.7 hits per probe, 7.4e11
+     * hits/s -- the flat round-1 rate sent that problem to the bit-sliced kernel, 1515 against 1089 ms) */
+    const double hpp = probes > 0.0 ? hits / probes : 0.0;
+    const double hit_rate = 4.1e11 * (hpp <= 1.0 ? 1.0 : hpp >= 3.0 ? 1.7 : 1.0 + 0.35 * (hpp - 1.0));
+    double t = probes / (8.7e11 * scale) + hits / (hit_rate * scale);
     const double floor_t = probes / ((tab_mb <= 64.0 ? 4.0e11 : tab_mb <= 256.0 ? 1.8e11 : 0.9e11) * scale);
     if (t < floor_t) t = floor_t;
     return 1e3 * t + 1.0 * col_blocks + 0.3 + slots * slot_bytes / 3e12 * 1e3;
