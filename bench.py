@@ -268,10 +268,10 @@ def parity_rows(n, blk_cols, nblk, want=96, seed=7):
     return np.array(sorted(rows), np.int32)
 
 
-def check_parity(h, kmat, hist_of_rows, n, layout, threads, owned_only=True):
+def check_parity(h, kmat, hist_of_rows, n, layout, threads, owned_only=True, want=96):
     """rows of the matrix the product returned (and their integer histograms) against the reference's own numbers"""
     nblk, blk_cols = layout[0], layout[1] or n
-    rows = parity_rows(n, blk_cols, nblk)
+    rows = parity_rows(n, blk_cols, nblk, want=want)
     if owned_only:   # a sharded call fills only the rows of this rank's chunks: their unit diagonal tells which
         rows = rows[[kmat[r, r] == 1.0 for r in rows]]
     Kref, Href, t = h.rows_values(rows, threads)
@@ -483,7 +483,7 @@ def main():
             def hist_of_row(r):
                 return P.hist_block(r, 1, 0, r)[0]
             P.set_shard(0, 1)
-            parity, _ = check_parity(href, kmat, hist_of_row, n, layout, threads, owned_only=world > 1)
+            parity, _ = check_parity(href, kmat, hist_of_row, n, layout, threads, owned_only=world > 1, want=min(96 * world, 800))  # ~96 rows land in rank 0's chunks
             parity["checked"] = "the numpy matrix returned by the timed gkm_main_pywrapper call (rank 0's rows)" + \
                                 (" of %d ranks" % world if world > 1 else "")
             # hits per entry of this input, exactly: the histogram of one band of rows, all bins (unit weights: one per L-mer pair within d)
