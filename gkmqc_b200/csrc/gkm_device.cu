@@ -1016,7 +1016,8 @@ static void scatter_chunk(gkm_team *tm, const gkm_job *job, const gkm_chunk *c, 
  * Round 1 hinted the whole matrix and measured no gain: the triangle covers half of it.  The hint is now given per
  * chunk, only to the whole huge pages inside that chunk's own row span, and only where the chunk's entries cover
  * at least `thp_cover` of that span (break-even 0.37 on this host: 400 us per huge page against 512 x 2.1 us).
- * A hint only: it changes no contents and no ownership.  GKM_NO_THP=1 switches it off, GKM_THP_COVER sets the bar. */
+ * A hint only: it changes no contents and no ownership -- but it makes the untouched part of a huge page resident, and it
+ * bought nothing measurable (gkm_dev_compute), so it is off unless GKM_THP_COVER sets a bar. */
 static int advise_chunk(const gkm_job *job, const gkm_chunk *c)
 {
     const int nr = c->row_end - c->row_begin;
@@ -1288,9 +1289,13 @@ extern "C" int gkm_dev_compute(gkmb200_problem *p, int row0, int nrows, int col0
             /* the host threads that scatter finished chunks are shared by the GPUs of the call: each device thread
              * leads a team of its share of them (different chunks, so different 2 MB regions of the destination) */
             job.copy_threads = copy_threads / ds->ndev > 1 ? copy_threads / ds->ndev : 1;
+            /* huge-page hint on the destination: OFF unless asked for (GKM_THP_COVER=<least covered share of a chunk's row
+             * span>, e.g. 0.4).  Round 2 measured no gain at any GPU count (16 threads first-touch 23 GB/s with 2 MB pages
+             * against 19 with 4 KB ones in the probe, 0.427 s per 50k call on 2 GPUs either way) and the hint makes the
+             * caller's untouched upper triangle resident. */
             if ((rows || out) && !hist && !getenv("GKM_NO_THP")) {
                 const char *tc = getenv("GKM_THP_COVER");
-                job.thp_cover = tc ? atof(tc) : 0.4;
+                job.thp_cover = tc ? atof(tc) : 0.0;
             }
             gkm_devthread dts[GKM_MAX_DEV];
             pthread_t th[GKM_MAX_DEV];
