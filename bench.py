@@ -654,6 +654,54 @@ def main():
                                       "lmer_pairs_per_entry": pairs600, "lmer_pairs_per_s": e2 / (float(md.mean()) * 1e-3) * pairs600,
                                       "type4_300bp_L11_lmer_pairs_per_s": sec1["type4"]["value"] * PAIRS_PER_ENTRY}
 
+        # the consumer of the matrix: gkmQC's 5-fold x 10-repeat C-SVC cross-validation on the matrix kept
+        # resident on the device, gkmQC's default kernel; two of the 50 fits against sklearn's SVC on the same splits
+        try:
+            from sklearn.metrics import roc_auc_score
+            from sklearn.model_selection import StratifiedKFold
+            from sklearn.svm import SVC
+            rng = np.random.default_rng(7)
+            arrm = synth(n2)
+            npos_m = n2 // 2
+            motifs = [b"GATAAGGCAT", b"TTGACGTCAA", b"CCCGCCCCTA"]
+            for i in range(npos_m):   # degenerate motifs planted in the positives: a problem an SVM can learn
+                for m in motifs[: 1 + i % 3]:
+                    at = int(rng.integers(0, 290))
+                    mm = bytearray(m)
+                    if rng.random() < 0.5:
+                        mm[int(rng.integers(0, 10))] = b"ACGT"[int(rng.integers(0, 4))]
+                    arrm[i, at:at + 10] = np.frombuffer(bytes(mm), np.uint8)
+            ym = np.concatenate((np.ones(npos_m, int), np.zeros(n2 - npos_m, int)))
+            splits = []
+            for rep in range(10):
+                splits.extend(StratifiedKFold(n_splits=5, shuffle=True, random_state=rep).split(np.zeros(n2), ym))
+            with capi.Problem(4, 10, 6, 3, 50, 50.0, 1.0) as Pm:
+                Pm.add_block(arrm)
+                Pm.upload()
+                t0 = time.perf_counter()
+                scores, fits, _ = capi.svm_cv(ym, splits, problem=Pm, C=1.0, eps=1e-3)
+                t_first = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                scores, fits, _ = capi.svm_cv(ym, splits, problem=Pm, C=1.0, eps=1e-3)
+                t_fits = time.perf_counter() - t0
+                aucs = [roc_auc_score(ym[te], sc) for (_, te), sc in zip(splits, scores)]
+                Km = Pm.kernel_lower()
+                Km = np.maximum(Km, Km.T)
+            t0 = time.perf_counter()
+            worst = 0.0
+            for f_i, (tr, te) in enumerate(splits[:2]):
+                sv = SVC(kernel="precomputed", C=1.0, tol=1e-3, shrinking=False, gamma=1.0, cache_size=1000)
+                ref_s = sv.fit(Km[tr][:, tr], ym[tr]).decision_function(Km[te][:, tr])
+                worst = max(worst, float(np.max(np.abs(ref_s - scores[f_i]))))
+            t_sk = time.perf_counter() - t0
+            del Km
+            secondary["svm_cv"] = {"workload": "50 C-SVC fits (5-fold x 10 repeats, C = 1, tol = 1e-3) on 10k x 300 bp with planted motifs, wgkm L=10 k=6 d=3, matrix resident on the device",
+                                   "fits_s": t_fits, "with_matrix_s": t_first, "auc_mean": float(np.mean(aucs)),
+                                   "iterations_mean": float(np.mean([f["n_iter"] for f in fits])), "n_sv_mean": float(np.mean([f["n_sv"] for f in fits])),
+                                   "sklearn_2_fits_s": t_sk, "max_abs_diff_decision_values_vs_sklearn": worst}
+        except Exception as e:
+            secondary["svm_cv"] = {"error": str(e)}
+
         # genome-like, NON-uniform input (AT-rich background, a repeat family in 20 %, poly-A tracts in 10 %, dinucleotide repeats in 5 %, 5 % duplicates)
         try:
             import importlib.util
