@@ -227,12 +227,11 @@ static char *dup_string(const char *s)
     return r;
 }
 
-/* the arrays of a gkm_data from base codes 0..3 (libgkm.c:864-932): seq, seq_rc (codes 1..4), seq_string, wt, wt_rc
+/* the arrays of a gkm_data from the letters of a sequence (libgkm.c:864-932): seq, seq_rc (codes 1..4), seq_string, wt, wt_rc
  * and the leaf index of every L-mer in the reference's 4-ary tree (libgkm.c:891-908: base-4 digits 0..3).
  * Returns 1 when an allocation failed (the caller deletes the object). */
-static int fill_object(gkm_data *d, const gkm_parameter *pa, const uint8_t *code, int len, const char *text, const char *sid, int seqid)
+static int fill_object(gkm_data *d, const gkm_parameter *pa, const uint8_t *text, int len, const char *sid, int seqid)
 {
-    static const char letters[4] = { 'A', 'C', 'G', 'T' };
     const int nk = len - pa->L + 1;
     d->sid = sid ? dup_string(sid) : NULL;
     d->seqid = seqid;
@@ -249,9 +248,9 @@ static int fill_object(gkm_data *d, const gkm_parameter *pa, const uint8_t *code
         return 1;
     }
     for (int j = 0; j < len; j++) {
-        d->seq[j] = (u_int8_t) (code[j] + 1);
-        d->seq_rc[j] = (u_int8_t) (4 - code[len - 1 - j]);
-        d->seq_string[j] = text ? text[j] : letters[code[j]]; /* the reference keeps the caller's spelling (strcpy) */
+        d->seq[j] = (u_int8_t) (gkm_base_code(text[j]) + 1);
+        d->seq_rc[j] = (u_int8_t) (4 - gkm_base_code(text[len - 1 - j]));
+        d->seq_string[j] = (char) text[j]; /* the reference keeps the spelling it was given (strcpy, libgkm.c:859-860) */
     }
     d->seq_string[len] = '\0';
     gkm_calc_posweights(nk, pa->kernel_type, pa->M, pa->H, d->wt, d->wt_rc);
@@ -286,7 +285,7 @@ gkm_data *gkmkernel_new_object(gkm_kernel *kernel, char *seq, char *sid, int seq
     if (!d) return NULL;
     /* one-sequence problem: coding, and sqnorm = sqrt(Kraw(x,x)) on the device */
     gkmb200_problem *one = gkmb200_problem_new(pa);
-    if (!one || gkmb200_problem_add(one, seq, len) < 0 || fill_object(d, pa, gkm_code(one, 0), len, seq, sid, seqid) || gkm_dev_upload(one)) {
+    if (!one || gkmb200_problem_add(one, seq, len) < 0 || fill_object(d, pa, gkm_letters(one, 0), len, sid, seqid) || gkm_dev_upload(one)) {
         gkmb200_problem_free(one);
         gkmkernel_delete_object(d);
         return NULL;
@@ -419,7 +418,7 @@ int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *p
     for (int i = 0; !bad && i < n; i++) {
         gkm_data *d = (gkm_data *) calloc(1, sizeof(gkm_data));
         prob->x[i] = d;
-        if (!d || fill_object(d, kernel->param, gkm_code(p, i), p->len[i], NULL, p->sid[i] ? p->sid[i] : "", i)) { bad = 1; break; }
+        if (!d || fill_object(d, kernel->param, gkm_letters(p, i), p->len[i], p->sid[i] ? p->sid[i] : "", i)) { bad = 1; break; }
         d->label = (i < npos) ? 1 : -1;
         d->sqnorm = p->sqnorm[i];
         prob->y[i] = d->label;

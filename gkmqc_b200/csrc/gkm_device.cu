@@ -751,7 +751,9 @@ extern "C" void gkm_dev_release(gkmb200_problem *p)
 /* packing on the device: base codes -> the image of 3 */
 /* ------------------------------------------------------------------ */
 /* What gkm_seq.c:pack_worker does on the host (it stays there for the CPU emulators of the test tier), one CTA per
- * sequence, one warp per 32-position word of the circular string: forward strand at [0, len), reverse complement
+ * sequence, one warp per 32-position word of the circular string.  The input is the sequence TEXT, one byte per base as
+ * the FASTA file or the caller spelled it: the letter -> code rule (A,C,G,T in either case -> 0..3, anything else -> A,
+ * libgkm.c:864-875; gkm_base_code) is applied here.  Layout: forward strand at [0, len), reverse complement
  * (3 - code, mirrored: libgkm.c:878-888) at [len, 2 len), zero padding; plane bits by warp ballot; E = positions at
  * which an L-mer of either strand may end; wend[j] = positional weight of the L-mer ending at j, looked up by its
  * distance from the centre L-mer in a table the host computed with the reference's expression (libgkm.c:910-932) --
@@ -770,10 +772,10 @@ gkm_pack_kernel(const uint8_t *__restrict__ codes, const unsigned long long *__r
         uint32_t code = 0;
         int s = -1; /* start index (forward-strand numbering of wt[]) of the L-mer that ends at j, if any */
         if (j < len) {
-            code = c[j];
+            code = gkm_base_code(c[j]);
             if (j >= L - 1) s = j - (L - 1);
         } else if (j < 2 * len) {
-            code = 3u - c[2 * len - 1 - j];
+            code = 3u - gkm_base_code(c[2 * len - 1 - j]);
             const int rel = j - len;
             if (rel >= L - 1) s = nk - 1 - (rel - (L - 1)); /* wt_rc[t] = wt[nk - 1 - t] */
         }

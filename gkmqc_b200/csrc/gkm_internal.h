@@ -38,7 +38,8 @@ struct gkmb200_problem {
     int n, cap;
     int npos;      /* set by read_problem */
     int *len;      /* bases per sequence */
-    uint8_t *arena;/* forward strands of all sequences back to back, base codes 0..3 (A,C,G,T): what goes to the GPU */
+    uint8_t *arena;/* forward strands of all sequences back to back, the LETTERS as they were given (either case, anything
+                    * else than ACGT counts as A: gkm_base_code): what goes to the GPU, which codes and packs them */
     size_t arena_len, arena_cap;
     size_t *off;   /* first base of sequence i in the arena */
     char **sid;    /* FASTA record ids (first token after '>', libgkm.c:1287-1292); NULL for sequences added in memory */
@@ -66,7 +67,18 @@ int gkm_problem_reserve(gkmb200_problem *p, int extra);
 void gkm_problem_shard_from_env(gkmb200_problem *p); /* GKM_SHARD="rank/world": gkm_main_pywrapper only */
 int gkm_shape_problem(gkmb200_problem *p);   /* Wmax, Wa, sqnorm buffer; no image */
 int gkm_pack_problem(gkmb200_problem *p);    /* + the image on the host */
-static inline const uint8_t *gkm_code(const gkmb200_problem *p, int i) { return p->arena + p->off[i]; }
+static inline const uint8_t *gkm_letters(const gkmb200_problem *p, int i) { return p->arena + p->off[i]; }
+/* A,C,G,T (either case) -> 0..3; anything else counts as 'A' (libgkm.c:864-875).  With the case bit cleared the four letters
+ * are 0x41, 0x43, 0x47, 0x54: t = (ch >> 1) & 3 is 0,1,3,2 and t ^ (t >> 1) is 0,1,2,3.  The device packer
+ * (gkm_device.cu: gkm_pack_kernel) applies the same rule. */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint8_t gkm_base_code(unsigned char ch)
+{
+    const unsigned u = ch & 0xDFu, t = (ch >> 1) & 3u;
+    return (u == 'A' || u == 'C' || u == 'G' || u == 'T') ? (uint8_t) (t ^ (t >> 1)) : (uint8_t) 0;
+}
 /* positional weight by distance from the centre L-mer (libgkm.c:910-932): tab[dist], dist = 0..GKM_MAX_BASES */
 void gkm_posweight_table(int kernel_type, int M, double H, uint8_t *tab);
 void gkm_unpack_problem(gkmb200_problem *p);

@@ -98,21 +98,6 @@ static int arena_reserve(gkmb200_problem *p, size_t extra)
     return 0;
 }
 
-/* A,C,G,T (either case) -> 0..3; anything else counts as 'A' (libgkm.c:864-875) and is flagged with 0x80 */
-static uint8_t g_code_tab[256];
-static int g_code_tab_ready = 0;
-
-static void code_tab_init(void)
-{
-    if (g_code_tab_ready) return;
-    for (int i = 0; i < 256; i++) g_code_tab[i] = 0x80;
-    g_code_tab['A'] = g_code_tab['a'] = 0;
-    g_code_tab['C'] = g_code_tab['c'] = 1;
-    g_code_tab['G'] = g_code_tab['g'] = 2;
-    g_code_tab['T'] = g_code_tab['t'] = 3;
-    __atomic_store_n(&g_code_tab_ready, 1, __ATOMIC_RELEASE);
-}
-
 int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
 {
     if (!p || !seq) { gkm_set_error("null argument"); return -1; }
@@ -123,43 +108,36 @@ int gkmb200_problem_add(gkmb200_problem *p, const char *seq, int len)
         return -1;
     }
     if (gkm_problem_reserve(p, 1) || arena_reserve(p, (size_t) len)) { gkm_set_error("out of memory"); return -1; }
+    /* the letters go into the arena as they are (the GPU codes and packs them); the host only looks for letters that are
+     * not nucleotides, sixteen at a time, to name them like the reference does (libgkm.c:864-875) */
     uint8_t *c = p->arena + p->arena_len;
-    code_tab_init();
-    unsigned any_bad = 0;
-    int i = 0;
+    memcpy(c, seq, (size_t) len);
+    int any_bad = 0, i = 0;
 #if defined(__SSE2__)
-    /* sixteen bases per step: with the case bit cleared, t = (ch >> 1) & 3 maps A,C,G,T to 0,1,3,2 and t ^ (t >> 1) to
-     * 0,1,2,3; a byte that is none of the four letters is flagged like the table does (bit 7) */
     {
-        const __m128i up = _mm_set1_epi8((char) 0xDF), m3 = _mm_set1_epi8(3), m1 = _mm_set1_epi8(1), bad7 = _mm_set1_epi8((char) 0x80);
+        const __m128i up = _mm_set1_epi8((char) 0xDF);
         const __m128i cA = _mm_set1_epi8('A'), cC = _mm_set1_epi8('C'), cG = _mm_set1_epi8('G'), cT = _mm_set1_epi8('T');
-        __m128i acc = _mm_setzero_si128();
+        __m128i all_ok = _mm_set1_epi8((char) 0xFF);
         for (; i + 16 <= len; i += 16) {
-            const __m128i ch = _mm_loadu_si128((const __m128i *) (seq + i));
-            const __m128i u = _mm_and_si128(ch, up);
+            const __m128i u = _mm_and_si128(_mm_loadu_si128((const __m128i *) (seq + i)), up);
             const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, cA), _mm_cmpeq_epi8(u, cC)),
                                             _mm_or_si128(_mm_cmpeq_epi8(u, cG), _mm_cmpeq_epi8(u, cT)));
-            const __m128i t = _mm_and_si128(_mm_srli_epi16(ch, 1), m3);
-            const __m128i code = _mm_xor_si128(t, _mm_and_si128(_mm_srli_epi16(t, 1), m1));
-            const __m128i v = _mm_or_si128(_mm_and_si128(ok, code), _mm_andnot_si128(ok, bad7));
-            _mm_storeu_si128((__m128i *) (c + i), v);
-            acc = _mm_or_si128(acc, v);
+            all_ok = _mm_and_si128(all_ok, ok);
         }
-        any_bad |= (unsigned) _mm_movemask_epi8(acc) ? 0x80u : 0u;
+        any_bad |= _mm_movemask_epi8(all_ok) != 0xFFFF;
     }
 #endif
     for (; i < len; i++) {
-        const uint8_t v = g_code_tab[(unsigned char) seq[i]];
-        c[i] = v;
-        any_bad |= v;
+        const unsigned u = (unsigned char) seq[i] & 0xDFu;
+        any_bad |= !(u == 'A' || u == 'C' || u == 'G' || u == 'T');
     }
-    if (any_bad & 0x80) { /* rare: name the offenders like the reference does, then fold them to 'A' */
-        for (int i = 0; i < len; i++) {
-            if (!(c[i] & 0x80)) continue;
+    if (any_bad) { /* rare: name the offenders like the reference does; they count as 'A' wherever codes are made */
+        for (int j = 0; j < len; j++) {
+            const unsigned u = (unsigned char) seq[j] & 0xDFu;
+            if (u == 'A' || u == 'C' || u == 'G' || u == 'T') continue;
             if (p->nonacgt < 10)
-                gkm_log(GKM_LOG_WARN, "'%c' at sequence %d(%d) is not a valid nucleotide. Only ACGT are allowed", seq[i], p->n, i);
+                gkm_log(GKM_LOG_WARN, "'%c' at sequence %d(%d) is not a valid nucleotide. Only ACGT are allowed", seq[j], p->n, j);
             p->nonacgt++;
-            c[i] = 0;
         }
     }
     p->len[p->n] = len;
@@ -343,8 +321,8 @@ int gkmb200_problem_codes(const gkmb200_problem *p, int i, uint8_t *fwd, uint8_t
     if (!p || i < 0 || i >= p->n) return 1;
     const int n = p->len[i];
     for (int j = 0; j < n; j++) {
-        if (fwd) fwd[j] = (uint8_t) (gkm_code(p, i)[j] + 1);
-        if (rc) rc[j] = (uint8_t) (4 - gkm_code(p, i)[n - 1 - j]);
+        if (fwd) fwd[j] = (uint8_t) (gkm_base_code(gkm_letters(p, i)[j]) + 1);
+        if (rc) rc[j] = (uint8_t) (4 - gkm_base_code(gkm_letters(p, i)[n - 1 - j]));
     }
     return 0;
 }
@@ -394,7 +372,9 @@ static void *pack_worker(void *arg)
     int wt_nk = -1; /* positional weights depend on the number of L-mers only: reuse them across equal lengths */
     for (int i = job->i0; i < job->i1; i++) {
         const int n = p->len[i];
-        const uint8_t *c = gkm_code(p, i);
+        uint8_t c[GKM_MAX_BASES + 9]; /* base codes of this sequence (+ slack: the loop below reads eight at a time) */
+        for (int j = 0; j < n; j++) c[j] = gkm_base_code(gkm_letters(p, i)[j]);
+        memset(c + n, 0, 8);
         uint32_t *pl = p->planes + (size_t) i * 3 * (size_t) W;
         /* Forward strand: bit b of the codes, eight bases per multiply (the byte-to-bit gather trick); the reverse
          * complement half is the forward half mirrored and complemented (3 - c = ~c & 3; libgkm.c:878-888), so it

@@ -98,7 +98,7 @@ def test_read_problems_fills_what_the_reference_fills(name, lib):
         assert np.array_equal(np.ctypeslib.as_array(d.kmerids_rc, (nk,)), ids_rc)
         wt, wt_rc = o.poswt(i)
         assert np.array_equal(np.ctypeslib.as_array(d.wt, (nk,)), wt) and np.array_equal(np.ctypeslib.as_array(d.wt_rc, (nk,)), wt_rc)
-        assert len(d.seq_string) == len(seq)
+        assert d.seq_string == bases                      # the file's own spelling (lower case, N ...), like strcpy in libgkm.c:859-860
         assert d.sqnorm == g["sqnorm"][i]
     # build_tree over exactly these objects adopts the image read_problems uploaded: no second upload
     st0 = capi.gkmb200_stats()
