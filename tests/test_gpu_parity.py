@@ -474,3 +474,52 @@ def test_one_core_affinity_still_correct(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     n = len(g["lens"])
     assert np.array_equal(np.load(out)[:n, :n], g["kmat"])
+
+
+@pytest.mark.parametrize("kernel_type", [2, 4])
+def test_two_column_blocks_at_20k_index_against_bitsliced(kernel_type):
+    """20 000 x 300 bp: the index kernel runs two column blocks (rows of the second block probe both); rows on both sides
+    of the block boundary, the first and the last rows: integers and doubles against the bit-sliced kernel"""
+    import bench
+    n = 20000
+    arr = bench.synth(n, seed=77)
+    got = {}
+    for v in ("index", "diag"):
+        capi.set_option("kernel", v)
+        try:
+            with capi.Problem(kernel_type, 11, 7, 3) as P:
+                P.add_block(arr)
+                P.upload()
+                if v == "index":
+                    K0 = P.kernel_block(n - 1, 1, 0, n - 1)     # creates the partition over all columns
+                    nblk, cols, _ = P.index_layout()
+                    assert nblk == 2
+                    rows = sorted({1, 2, cols - 1, cols, cols + 1, cols + 147, cols + 148, n - 149, n - 148, n - 2, n - 1, 12345})
+                got[v] = [(P.hist_block(r, 1, 0, r)[0], P.kernel_block(r, 1, 0, r)[0]) for r in rows]
+                assert P.stats()["kernel_variant"] == {"diag": 2, "index": 4}[v]
+        finally:
+            capi.set_option("kernel", "auto")
+    for r, (hi, ki), (hd, kd) in zip(rows, got["index"], got["diag"]):
+        assert np.array_equal(hi, hd), "histograms of row %d" % r
+        assert np.array_equal(ki, kd), "kernel values of row %d" % r
+
+
+def test_ragged_lengths_at_scale_index_against_bitsliced():
+    """4 000 sequences of 40 .. 1 200 bp (weighted kernel type, gkmQC's default L=10 k=6 d=3): the whole matrix of the index
+    kernel against the bit-sliced kernel's"""
+    rng = np.random.default_rng(21)
+    letters = np.frombuffer(b"ACGT", np.uint8)
+    seqs = [letters[rng.integers(0, 4, int(rng.integers(40, 1201)))].tobytes().decode() for _ in range(4000)]
+    mats = {}
+    for v in ("index", "diag"):
+        capi.set_option("kernel", v)
+        try:
+            with capi.Problem(4, 10, 6, 3, 50, 50.0, 1.0) as P:
+                P.add_many(seqs)
+                mats[v] = P.kernel_lower()
+        finally:
+            capi.set_option("kernel", "auto")
+    assert np.array_equal(mats["index"], mats["diag"])
+    K = mats["index"]
+    low = K[np.tril_indices(4000, -1)]
+    assert np.all(np.diag(K) == 1.0) and low.min() >= 0 and low.max() <= 1.0 and np.count_nonzero(low) > 0.99 * low.size  # 40-bp pairs may share nothing
