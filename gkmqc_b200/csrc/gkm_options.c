@@ -18,7 +18,7 @@
 static int g_loaded = 0;
 static int g_kernel = GKM_KERNEL_AUTO;
 static int g_max_L = 12;
-static int g_chunk_mb = 64;
+static int g_chunk_mb = 128; /* 50k x 50k: 686 ms per pass with 64 MB chunks (one wave of 148 rows each), 671 with 128, 669 with 256 */
 static int g_tile_rows = 0;
 static int g_diag_flavor = -1;
 static int g_index_cols = 0;
