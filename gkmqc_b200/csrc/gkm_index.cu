@@ -40,7 +40,8 @@
 #ifndef GKM_IDX_TWO_SMEM
 #define GKM_IDX_TWO_SMEM (196u * 1024u)
 #endif
-#define GKM_IDX_SKEW_ONE_CTA 16.0 /* sum len^2 / P of the block: 2.4 on uniform 10k x 300 bp, 3 on AT-rich, > 100 with 10 % poly-A */
+#define GKM_IDX_SKEW_ONE_CTA 10.0 /* sum len^2 / P of the block: 2.4 on uniform 10k x 300 bp (L = 11), 3 on AT-rich, 6.5 at L = 10, 12.3 at L = 10 with 600-bp
+                                      * windows (gkmQC's default: one CTA 220.6 ms, two 227.0), > 100 with 10 % poly-A */
 #ifndef GKM_IDX_W20_TWO
 #define GKM_IDX_W20_TWO 1 /* weighted compact slots: two CTAs per SM where the histogram rows fit (A/B: 0) */
 #endif
