@@ -334,6 +334,8 @@ def main():
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
             return
         budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
         h = open_reference(pos, neg)
@@ -361,6 +363,8 @@ def main():
             "config": config, "cpu_baseline": r,
             "e2e": {"value": v, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -471,6 +475,8 @@ def main():
         dist.destroy_process_group()
         dist = None
     if rank != 0:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
         return
 
     # ------------------------------------------------------------------ parity of what the e2e call returned + CPU baseline
