@@ -90,6 +90,7 @@ struct gkm_gpu {
     size_t deltas_bytes;
     int delta_L, delta_d, ndelta, ncold;
     int32_t *d_cold[2];   /* cold-bin scratch of the launches on sc / sc2 */
+    long long nkernels;   /* histogram kernels launched on this GPU so far (the statistics report differences) */
     size_t cold_cap[2];
 };
 
@@ -299,6 +300,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
             ra.cold = g->d_cold[si];
         }
         if (gkm_idx_rows(&kp, &ra, p->weighted, st)) return 1;
+        g->nkernels++;
     }
     return 0;
 }
@@ -390,6 +392,7 @@ static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g
         if (grid.y > 65535u) { gkm_set_error("chunk has too many row tiles"); return 1; }
         void *args[] = { &kp, (void *) &im->mma, (void *) &im->tmap };
         CK(cudaLaunchKernel(fn, grid, dim3(GKM_MMA_THREADS, 1, 1), args, smem, st));
+        g->nkernels++;
         if (variant_out) *variant_out = variant;
         return 0;
     } else {
@@ -412,6 +415,7 @@ static int launch_hist(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *g
     if (grid.y > 65535u) { gkm_set_error("chunk has too many row tiles"); return 1; }
     void *args[] = { &kp };
     CK(cudaLaunchKernel(fn, grid, dim3(256, 1, 1), args, smem, st));
+    g->nkernels++;
     if (variant_out) *variant_out = variant;
     return 0;
 }
@@ -1073,13 +1077,14 @@ static int dev_issue(gkm_devthread *dt, gkm_gpu *g, const gkm_image *im, const g
     cudaStream_t st = (buf & 1) ? g->sc2 : g->sc;
     dt->thp_chunks += advise_chunk(job, c); /* ahead of the kernel: off the critical path of the copy-out */
     CK(cudaEventRecord(g->k0[buf], st));
+    const long long k_before = g->nkernels;
     if (launch_hist(job->p, im, g, kp, st, &dt->variant)) return 1;
+    dt->launches += g->nkernels - k_before; /* kernels, not chunks: the index variant launches one per column block */
     CK(cudaEventRecord(g->k1[buf], st));
     CK(cudaStreamWaitEvent(g->sx, g->k1[buf], 0));
     const size_t bytes = (size_t) (c->row_end - c->row_begin) * (size_t) width * sizeof(double);
     if (bytes) CK(cudaMemcpyAsync(g->h_stage[buf], g->d_band[buf], bytes, cudaMemcpyDeviceToHost, g->sx));
     CK(cudaEventRecord(g->cdone[buf], g->sx));
-    dt->launches++;
     dt->d2h_bytes += (long long) bytes;
     dt->entries += c->entries;
     return 0;
@@ -1571,6 +1576,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
             cudaEventRecord(e0, g->sc);
             cudaStreamWaitEvent(g->sc2, e0, 0);
             launches = 0; entries = 0;
+            int nchunk_issued = 0;
             for (int c = 0; !rc && c < nchunks; c++) {
                 if (gkm_chunk_owner(c, nchunks, p->shard_world) != p->shard_rank) continue;
                 gkm_kparams kp;
@@ -1581,8 +1587,9 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
                 kp.row_base = 0; kp.col_base = 0;
                 kp.out = im->full; kp.ld = (long long) im->full_ld;
                 im->full_sym = 0;
-                rc = launch_hist(p, im, g, kp, (launches & 1) ? g->sc2 : g->sc, &variant);
-                launches++;
+                const long long k_before = g->nkernels;
+                rc = launch_hist(p, im, g, kp, (nchunk_issued++ & 1) ? g->sc2 : g->sc, &variant);
+                launches += g->nkernels - k_before; /* kernels of this pass (one per chunk and column block) */
                 entries += chunks[c].entries;
             }
             cudaEventRecord(g->join, g->sc2);
