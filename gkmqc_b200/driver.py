@@ -58,3 +58,31 @@ def crossValidate(args_svm, _kmat, n_pseqs, n_nseqs, problem=None):
         logging.info("SVC training and validation; nu = %.3f, AUC = %.3f", f["nu"], aucs[-1])
     logging.info("done cross-validation.")
     return np.mean(aucs), np.std(aucs)
+
+
+def init(pos_fa, neg_fa, args, resident=False):
+    """gkmsvm.init (gkmsvm.py:182-222): one bin of gkmQC's `evaluate` -- kernel matrix, cross-validation, one line appended to
+    `<args.name>.gkmqc.eval.out` (pos_fa, neg_fa, n_pseqs, mean AUC, std AUC; tab-separated).  `args` carries the attributes the
+    reference's argparse namespace has (gkmsvm.py:236-300, bin/gkmqc.py:150-215).
+    resident=True keeps the matrix on the device between the two steps (gkmb200_svm_cv with kmat = NULL): same numbers, no
+    15000 x 15000 host matrix."""
+    args_gkm = [args.kernel_type, args.full_word_length, args.non_gap_length, args.max_num_gaps, args.init_decay,
+                args.half_life_decay, args.rbf_gamma, pos_fa, neg_fa, args.n_processes, args.verbosity]
+    args_svm = [args.regularization, args.precision, args.shrinking, args.cache_size, args.ncv, args.repeats,
+                args.fast_estimation, args.random_seeds, args.n_processes]
+    logging.info("%s: building up kernel matrix", pos_fa)
+    if resident:
+        with capi.Problem(args.kernel_type, args.full_word_length, args.non_gap_length, args.max_num_gaps,
+                          args.init_decay, args.half_life_decay, args.rbf_gamma) as P:
+            n_pseqs = P.read(pos_fa, neg_fa)
+            n_nseqs = P.n - n_pseqs
+            logging.info("%s: svm training", pos_fa)
+            auc_score, auc_std = crossValidate(args_svm, None, n_pseqs, n_nseqs, problem=P)
+    else:
+        kmat, n_pseqs, n_nseqs = computeGkmKernel(args_gkm)
+        logging.info("%s: svm training", pos_fa)
+        auc_score, auc_std = crossValidate(args_svm, kmat, n_pseqs, n_nseqs)
+    logging.info("%s: writing result to output file", pos_fa)
+    with open(args.name + ".gkmqc.eval.out", "a") as fa:
+        fa.write("\t".join(map(str, [pos_fa, neg_fa, n_pseqs, auc_score, auc_std])) + "\n")
+    return auc_score, auc_std

@@ -110,3 +110,41 @@ def test_bad_arguments(problem):
         capi.svm_cv(y, [(np.arange(10), np.arange(10, 20))], kmat=K)   # one class only
     with pytest.raises(capi.GkmError):
         capi.svm_cv(y, [(np.arange(len(y)), np.arange(5))], kmat=K, C=-1.0)
+
+
+def test_init_mirrors_one_bin_of_evaluate(tmp_path):
+    """driver.init = gkmsvm.init (gkmsvm.py:182-222): kernel matrix + 2 x 3 cross-validation + the line in <name>.gkmqc.eval.out;
+    the AUCs are those of sklearn's SVC on the same splits (what the reference's pool computes), host matrix or resident"""
+    import types
+    from sklearn.metrics import roc_auc_score
+    from sklearn.model_selection import StratifiedKFold
+    from sklearn.svm import SVC
+    from gkmqc_b200 import driver
+    rng = np.random.default_rng(11)
+    n, npos = 240, 120
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    arr = acgt[rng.integers(0, 4, (n, 200))]
+    for i in range(npos):   # a motif the positives share
+        at = int(rng.integers(0, 190))
+        arr[i, at:at + 10] = np.frombuffer(b"GATAAGGCAT", np.uint8)
+    pos, neg = tmp_path / "p.fa", tmp_path / "n.fa"
+    pos.write_text("".join(">p%d\n%s\n" % (i, arr[i].tobytes().decode()) for i in range(npos)))
+    neg.write_text("".join(">n%d\n%s\n" % (i, arr[i].tobytes().decode()) for i in range(npos, n)))
+    args = types.SimpleNamespace(kernel_type=4, full_word_length=10, non_gap_length=6, max_num_gaps=3, init_decay=50, half_life_decay=50.0,
+                                 rbf_gamma=1.0, n_processes=1, verbosity=0, regularization=1.0, precision=1e-3, shrinking=0, cache_size=100,
+                                 ncv=3, repeats=2, fast_estimation=0, random_seeds=5, name=str(tmp_path / "bin0"))
+    auc, std = driver.init(str(pos), str(neg), args)
+    auc_r, std_r = driver.init(str(pos), str(neg), args, resident=True)
+    assert abs(auc - auc_r) < 1e-12 and abs(std - std_r) < 1e-12
+    lines = open(args.name + ".gkmqc.eval.out").read().splitlines()
+    assert len(lines) == 2 and lines[0].split("\t")[:3] == [str(pos), str(neg), str(npos)]
+    assert abs(float(lines[0].split("\t")[3]) - auc) < 1e-15
+    # the reference's own flow on the same matrix and splits (gkmsvm.py:104-160)
+    kmat, _, _ = driver.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, str(pos), str(neg), 1, 0], max_seqs=n)
+    y = np.concatenate((np.repeat(1, npos), np.repeat(0, n - npos)))
+    aucs = []
+    for _ in range(2):
+        for tr, te in StratifiedKFold(n_splits=3, shuffle=True, random_state=5).split(np.zeros(n), y):
+            sv = SVC(kernel="precomputed", C=1.0, tol=1e-3, shrinking=False, gamma=1.0, cache_size=100)
+            aucs.append(roc_auc_score(y[te], sv.fit(kmat[tr][:, tr], y[tr]).decision_function(kmat[te][:, tr])))
+    assert abs(np.mean(aucs) - auc) < 1e-9 and abs(np.std(aucs) - std) < 1e-9 and auc > 0.7
