@@ -86,3 +86,43 @@ def init(pos_fa, neg_fa, args, resident=False):
     with open(args.name + ".gkmqc.eval.out", "a") as fa:
         fa.write("\t".join(map(str, [pos_fa, neg_fa, n_pseqs, auc_score, auc_std])) + "\n")
     return auc_score, auc_std
+
+
+def main(argv=None):
+    """`python -m gkmqc_b200.driver -p pos.fa -n neg.fa -w name ...`: the command line of scripts/gkmsvm.py (gkmsvm.py:224-324:
+    same options, same defaults, same output file) on the engine.  --resident (not in the reference) keeps the matrix on the
+    device between the kernel and the cross-validation."""
+    import argparse
+    ap = argparse.ArgumentParser(description="gkm-SVM evaluation of one bin on B200 (option set of gkmQC's scripts/gkmsvm.py)",
+                                 formatter_class=argparse.RawTextHelpFormatter)
+    ap.add_argument("-p", "--pos-fa", type=str, required=True, help="positive fa file. REQUIRED")
+    ap.add_argument("-n", "--neg-fa", type=str, required=True, help="negative fa file. REQUIRED")
+    ap.add_argument("-w", "--name", type=str, required=True, help="prefix of output file to write AUC score. REQUIRED")
+    ap.add_argument("-s", "--random-seeds", type=int, default=-1, help="random seed number (default: no seed)")
+    ap.add_argument("-@", "--n-processes", type=int, default=1, help="number of processes (default: 1)")
+    ap.add_argument("-v", "--verbosity", type=int, default=1, help="verbosity (default: 1), 0: silent")
+    g = ap.add_argument_group("gkm-kernel")
+    g.add_argument("-t", "--kernel-type", type=int, default=4, help="0 gkm, 1 full filter, 2 truncated filter, 3 gkmrbf, 4 wgkm (default), 5 wgkmrbf")
+    g.add_argument("-L", "--full-word-length", type=int, default=10, help="full word length including gaps (default: 10)")
+    g.add_argument("-k", "--non-gap-length", type=int, default=6, help="number of non-gap positions (default: 6)")
+    g.add_argument("-d", "--max-num-gaps", type=int, default=3, help="maximum number of gaps allowed (default: 3)")
+    g.add_argument("-M", "--init-decay", type=int, default=50, help="initial value M of the decay function, -t 4 or 5 (default: 50)")
+    g.add_argument("-H", "--half-life-decay", type=int, default=50, help="half-life H of the decay function, -t 4 or 5 (default: 50)")
+    g.add_argument("-G", "--rbf-gamma", type=float, default=1.0, help="gamma for RBF kernel, -t 3 or 5 (default: 1.0)")
+    s = ap.add_argument_group("SVM training")
+    s.add_argument("-C", "--regularization", type=float, default=1.0, help="regularization parameter C (default: 1.0)")
+    s.add_argument("-e", "--precision", type=float, default=0.001, help="precision parameter epsilon (default: 0.001)")
+    s.add_argument("-u", "--shrinking", type=int, default=0, help="accepted for compatibility; the GPU solver does not shrink (default: 0)")
+    s.add_argument("-c", "--cache-size", type=int, default=512, help="accepted for compatibility (the matrix is resident)")
+    s.add_argument("-x", "--ncv", type=int, default=5, help="x-fold cross validation (default: 5)")
+    s.add_argument("-r", "--repeats", type=int, default=1, help="number of repeats of CV training (default: 1)")
+    s.add_argument("-f", "--fast-estimation", type=int, default=0, help="not available (commented out in the reference as well)")
+    ap.add_argument("--resident", action="store_true", help="keep the kernel matrix on the device (no host matrix)")
+    args = ap.parse_args(argv)
+    return init(args.pos_fa, args.neg_fa, args, resident=args.resident)
+
+
+if __name__ == "__main__":
+    logging.basicConfig(stream=sys.stdout, format="%(levelname)s %(asctime)s: %(message)s", datefmt="%Y-%m-%d %H:%M:%S",
+                        level=logging.INFO)  # formatting compatible with clog (gkmsvm.py:326-333)
+    main()

@@ -148,3 +148,28 @@ def test_init_mirrors_one_bin_of_evaluate(tmp_path):
             sv = SVC(kernel="precomputed", C=1.0, tol=1e-3, shrinking=False, gamma=1.0, cache_size=100)
             aucs.append(roc_auc_score(y[te], sv.fit(kmat[tr][:, tr], y[tr]).decision_function(kmat[te][:, tr])))
     assert abs(np.mean(aucs) - auc) < 1e-9 and abs(np.std(aucs) - std) < 1e-9 and auc > 0.7
+
+
+def test_command_line_of_gkmsvm_on_the_engine(tmp_path):
+    """python -m gkmqc_b200.driver: the option set and defaults of scripts/gkmsvm.py (gkmsvm.py:236-320) -- wgkm L=10 k=6 d=3 M=50
+    H=50, C=1, eps=1e-3, 5-fold x 1 repeat -- and its output line"""
+    from gkmqc_b200 import driver
+    rng = np.random.default_rng(2)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    arr = acgt[rng.integers(0, 4, (160, 150))]
+    for i in range(80):
+        at = int(rng.integers(0, 140))
+        arr[i, at:at + 10] = np.frombuffer(b"TTGACGTCAA", np.uint8)
+    pos, neg = tmp_path / "p.fa", tmp_path / "n.fa"
+    pos.write_text("".join(">p%d\n%s\n" % (i, arr[i].tobytes().decode()) for i in range(80)))
+    neg.write_text("".join(">n%d\n%s\n" % (i, arr[i].tobytes().decode()) for i in range(80, 160)))
+    name = str(tmp_path / "run")
+    auc, std = driver.main(["-p", str(pos), "-n", str(neg), "-w", name, "-s", "3", "-v", "0"])
+    auc2, std2 = driver.main(["-p", str(pos), "-n", str(neg), "-w", name, "-s", "3", "-v", "0", "--resident"])
+    assert auc == auc2 and std == std2 and 0.5 < auc <= 1.0
+    lines = [l.split("\t") for l in open(name + ".gkmqc.eval.out").read().splitlines()]
+    assert len(lines) == 2 and lines[0][2] == "80" and float(lines[1][3]) == auc
+    # the defaults are gkmQC's: the same call spelled out
+    auc3, _ = driver.main(["-p", str(pos), "-n", str(neg), "-w", name, "-s", "3", "-v", "0", "-t", "4", "-L", "10", "-k", "6", "-d", "3",
+                           "-M", "50", "-H", "50", "-C", "1.0", "-e", "0.001", "-x", "5", "-r", "1"])
+    assert auc3 == auc
