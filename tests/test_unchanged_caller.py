@@ -59,3 +59,44 @@ def test_unchanged_gkmsvm_end_to_end_with_fork_after_cuda():
     # the parent's CUDA context is still usable after the pool's fork + join
     kmat2, _, _ = mod.computeGkmKernel([4, 10, 6, 3, 50, 50.0, 1.0, pos, neg, 1, 0])
     assert np.array_equal(kmat2, kmat)
+
+
+def test_command_line_mirror_has_the_reference_options_and_defaults():
+    """gkmqc_b200.driver.main mirrors the argparse of scripts/gkmsvm.py (gkmsvm.py:236-320): every option of the reference,
+    with its short flag, type and default, read out of the reference's source text"""
+    import argparse
+    import re
+    if not os.path.exists(REF_SCRIPT):
+        pytest.skip("no reference tree on this box")
+    text = open(REF_SCRIPT).read()
+    ref = {}
+    for m in re.finditer(r'add_argument\("(-[\w@])",\s*"--([\w-]+)",\s*type=(\w+),\s*(?:required=True|default=([^,]+)),', text):
+        ref[m.group(2)] = (m.group(1), m.group(3), m.group(4))
+    assert len(ref) >= 20 and "full-word-length" in ref and "pos-fa" in ref
+    from gkmqc_b200 import driver
+    captured = {}
+    real = argparse.ArgumentParser.parse_args
+
+    def spy(self, argv=None):
+        captured["parser"] = self
+        raise SystemExit(0)
+    argparse.ArgumentParser.parse_args = spy
+    try:
+        with pytest.raises(SystemExit):
+            driver.main([])
+    finally:
+        argparse.ArgumentParser.parse_args = real
+    ours = {}
+    for a in captured["parser"]._actions:
+        longs = [o[2:] for o in a.option_strings if o.startswith("--")]
+        shorts = [o for o in a.option_strings if not o.startswith("--")]
+        if longs and shorts:
+            ours[longs[0]] = (shorts[0], a.type.__name__ if a.type else None, a.default, a.required)
+    for name, (short, typ, default) in ref.items():
+        assert name in ours, "option --%s of the reference is missing" % name
+        o_short, o_type, o_default, o_req = ours[name]
+        assert o_short == short and o_type == typ, name
+        if default is None:
+            assert o_req, name
+        else:
+            assert o_default == eval(default), (name, o_default, default)
