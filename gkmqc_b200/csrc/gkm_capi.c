@@ -350,6 +350,14 @@ void gkmkernel_build_tree(gkm_kernel *kernel, gkm_data **x, int n)
     kernel->prob_svm_data = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
     kernel->prob_gkmkernel_index = (int *) malloc(sizeof(int) * (size_t) (n ? n : 1));
     kernel->prob_libsvm_index = (int *) malloc(sizeof(int) * (size_t) (n ? n : 1));
+    if (!kernel->prob_svm_data || !kernel->prob_gkmkernel_index || !kernel->prob_libsvm_index) {
+        free(kernel->prob_svm_data); free(kernel->prob_gkmkernel_index); free(kernel->prob_libsvm_index);
+        kernel->prob_svm_data = NULL; kernel->prob_gkmkernel_index = NULL; kernel->prob_libsvm_index = NULL;
+        kernel->prob_num = 0;
+        gkm_set_error("out of memory");
+        gkm_log(GKM_LOG_ERROR, "gkmkernel_build_tree: out of memory");
+        return;
+    }
     memcpy(kernel->prob_svm_data, x, sizeof(gkm_data *) * (size_t) n);
     kernel->prob_num = n;
     for (int i = 0; i < n; i++) { kernel->prob_gkmkernel_index[i] = i; kernel->prob_libsvm_index[i] = i; }
@@ -447,6 +455,7 @@ int gkmkernel_read_problems(gkm_kernel *kernel, svm_problem *prob, const char *p
 
 void gkmkernel_swap_index(gkm_kernel *kernel, int i, int j)
 {
+    if (!kernel || !kernel->prob_gkmkernel_index || i < 0 || j < 0 || i >= kernel->prob_num || j >= kernel->prob_num) return;
     int *gi = kernel->prob_gkmkernel_index, *li = kernel->prob_libsvm_index;
     int t = li[gi[i]]; li[gi[i]] = li[gi[j]]; li[gi[j]] = t;
     t = gi[i]; gi[i] = gi[j]; gi[j] = t;
@@ -456,8 +465,10 @@ void gkmkernel_swap_index(gkm_kernel *kernel, int i, int j)
  * libsvm calls i; the device image is rebuilt in the new order on next use */
 void gkmkernel_update_index(gkm_kernel *kernel)
 {
+    if (!kernel || !kernel->prob_svm_data) return;
     const int n = kernel->prob_num;
     gkm_data **fresh = (gkm_data **) malloc(sizeof(gkm_data *) * (size_t) (n ? n : 1));
+    if (!fresh) { gkm_set_error("out of memory"); gkm_log(GKM_LOG_ERROR, "gkmkernel_update_index: out of memory"); return; }
     for (int i = 0; i < n; i++) fresh[i] = kernel->prob_svm_data[kernel->prob_gkmkernel_index[i]];
     free(kernel->prob_svm_data);
     kernel->prob_svm_data = fresh;

@@ -306,6 +306,7 @@ static int launch_index(const gkmb200_problem *p, const gkm_image *im, gkm_gpu *
 }
 
 static int pool_alloc(gkm_gpu *g, void **out, size_t *got, size_t bytes);
+static void pool_free(gkm_gpu *g, void *ptr, size_t bytes);
 
 /* "mma" variant: the 16-byte-pitched copy of the plane image and the TMA descriptor over it, made on first use */
 typedef CUresult (*gkm_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -337,14 +338,24 @@ static int ensure_mma(const gkmb200_problem *p, gkm_image *im, gkm_gpu *g, cudaS
     const int maxnk = p->maxlen - p->param.L + 1;
     im->mma.QA = GKM_MMA_ROWS_CAP / (maxnk > 0 ? maxnk : 1);
     if (im->mma.QA > GKM_MMA_QA) im->mma.QA = GKM_MMA_QA;
-    if (im->mma.QA < 1) { gkm_set_error("sequence too long for the mma kernel"); return 1; }
+    if (im->mma.QA < 1) {
+        cudaStreamSynchronize(st);
+        pool_free(g, im->pimg, im->pimg_bytes); im->pimg = NULL; /* no half-made image: the next call starts over */
+        gkm_set_error("sequence too long for the mma kernel");
+        return 1;
+    }
     const cuuint64_t gdim[2] = { (cuuint64_t) P, (cuuint64_t) n };
     const cuuint64_t gstr[1] = { (cuuint64_t) P * 4 };
     const cuuint32_t box[2] = { (cuuint32_t) im->mma.box, 1 };
     const cuuint32_t estr[2] = { 1, 1 };
     const CUresult r = encode(&im->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, im->pimg, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { gkm_set_error("mma variant: cuTensorMapEncodeTiled failed (%d)", (int) r); return 1; }
+    if (r != CUDA_SUCCESS) {
+        cudaStreamSynchronize(st); /* the copy into the block must not outlive its owner */
+        pool_free(g, im->pimg, im->pimg_bytes); im->pimg = NULL;
+        gkm_set_error("mma variant: cuTensorMapEncodeTiled failed (%d)", (int) r);
+        return 1;
+    }
     return 0;
 }
 
@@ -1110,7 +1121,7 @@ static int dev_thread_run(gkm_devthread *dt, gkm_team *team_p)
     if (job->hist) {
         CK(dev_malloc(g, (void **) &d_hist, maxhist ? maxhist : 4));
         h_hist = (int32_t *) malloc(maxhist ? maxhist : 4);
-        if (!h_hist) { gkm_set_error("out of memory"); return 1; }
+        if (!h_hist) { cudaFree(d_hist); gkm_set_error("out of memory"); return 1; }
     }
     /* up to `depth` chunks are in flight: slot s holds chunk inslot[s]; the oldest is retired (D2H done ->
      * scattered into the caller's rows) while the GPU works on the younger ones.  Histogram dumps (tests)
@@ -1470,7 +1481,7 @@ static int resident_symmetric(gkmb200_problem *p)
     const int maxc = n / 16 + 2;
     gkm_chunk *chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
     const int nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, 1),
-                                                      by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
+                                                      by_rows ? 4 * 148 : 65520 /* grid.y */, chunks, maxc) : -1;
     if (nchunks < 0) { free(chunks); gkm_set_error("chunk planning failed"); return 1; }
     int rc = 0, launches = 0;
     for (int c = 0; !rc && c < nchunks; c++) {
@@ -1564,7 +1575,7 @@ extern "C" int gkm_dev_bench_lower(gkmb200_problem *p, int steps, int warmup, in
             const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
             chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
             nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, 1),
-                                                    by_rows ? 4 * 148 : 0, chunks, maxc) : -1;
+                                                    by_rows ? 4 * 148 : 65520 /* grid.y */, chunks, maxc) : -1;
             if (nchunks < 0) { gkm_set_error("chunk planning failed"); rc = 1; }
         }
         cudaEvent_t e0 = NULL, e1 = NULL;
