@@ -129,7 +129,10 @@ int gkmb200_get_stats(const gkmb200_problem *p, gkmb200_stats *out);
 /* `steps` timed passes over the full lower triangle with inputs and outputs resident in HBM;
  * ms_each[steps] = CUDA-event time of each pass; flush_l2 != 0 rewrites a >L2-sized buffer between passes */
 int gkmb200_bench_lower_resident(gkmb200_problem *p, int steps, int warmup, int flush_l2, double *ms_each);
-/* issue-rate micro-benchmarks: what = "lop3" | "shf" | "popc" | "iadd3" | "imad"; result = 1e9 lane-ops per second */
+/* micro-benchmarks behind the roofline denominators (bench.py), on the first selected GPU:
+ *   "lop3" | "shf" | "popc" | "iadd3" | "imad" | "imadhi" | "lop3+imad" | "lop3+popc" | "lop3+imad+popc": 1e9 lane-ops per second;
+ *   "gather16": 1e9 random 16-byte gathers per second from a 64 MB (L2-resident) table;
+ *   "atoms7" | "atoms14" | "atoms32": 1e9 shared-memory atomic adds per second with ~7 / 14 / 32 of 32 lanes on per instruction */
 int gkmb200_microbench(const char *what, double *result);
 
 #ifdef __cplusplus
