@@ -116,6 +116,7 @@ struct gkm_image {
     /* "index" variant: one inverted index per block of blk_cols columns, built on first use */
     gkm_idx_block *blk;
     int nblk, blk_cols;
+    int blk_greedy;       /* the blocks were cut full-size first (index_split) */
     int part_lo, part_hi; /* the column range the blocks partition (that of the call that created them) */
 };
 
@@ -488,13 +489,15 @@ static void pool_free(gkm_gpu *g, void *ptr, size_t bytes)
 static int index_block_cap(const gkmb200_problem *p)
 {
     int cap = gkm_idx_max_cols(p->nbins, 32 * p->Wa, p->weighted);
-    /* beyond ~16k columns the posting lists grow past the four inline postings of a slot often enough that the
-     * overflow walks cost more than probing a second block does (measured: 6.0 us per row at 14k columns in one
-     * block, 10.9 us at 20k in one block against 7.5 us in two) */
-    if (cap > 16384) cap = 16384;
     if (p->weighted && cap > GKM_IDX_W20_MAX_COLS) cap = GKM_IDX_W20_MAX_COLS; /* 14-bit columns of the compact weighted slots */
+    if (!p->weighted && cap > (GKM_IDX_C16_MAX_COLS & ~31)) cap = GKM_IDX_C16_MAX_COLS & ~31; /* 15-bit columns of the compact slots */
     const int opt = gkm_opt_index_cols();
-    if (opt > 0 && opt < cap) cap = opt;
+    /* Default width of a full block: wider blocks mean fewer probes per row, denser slots (longer posting lists: more
+     * overflow walks) and less L1 next to the histogram rows.  50k x 300 bp, L = 11, full blocks first: 12 512 columns
+     * 672 ms, 16 384 609, 18 432 592, 20 480 586, 22 528 577, 25 024 633 (tools/split_ab2.py).  The option replaces this
+     * default, not the limits of the formats. */
+    const int lim = opt > 0 ? opt : 22528;
+    if (lim < cap) cap = lim;
     return cap;
 }
 
@@ -527,13 +530,13 @@ static int ensure_deltas(gkm_gpu *g, int L, int d)
 }
 
 /* build the indexes of the column blocks that intersect [col_begin, col_end); queued on g->sc */
-static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_begin, int col_end)
+static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_begin, int col_end, int greedy, int strict)
 {
     const int L = p->param.L;
     if (ensure_deltas(g, L, p->param.d)) return 1;
     /* The blocks partition the column range of the call that created them (the SVs of a scoring problem, all
      * sequences of a kernel matrix); a later call for columns outside that range starts over. */
-    if (im->blk && (col_begin < im->part_lo || col_end > im->part_hi)) {
+    if (im->blk && (col_begin < im->part_lo || col_end > im->part_hi || (strict && im->blk_greedy != greedy))) { /* strict: the option names a split */
         cudaStreamSynchronize(g->sc); cudaStreamSynchronize(g->sc2);
         release_index(g, im);
     }
@@ -542,8 +545,11 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
         if (cap <= 0) { gkm_set_error("index variant: sequences too long for shared memory"); return 1; }
         const int span = col_end - col_begin;
         const int nblk = (span + cap - 1) / cap;
+        /* equal shares, or -- greedy -- full blocks first and the rest in the last one: in a lower triangle row a probes
+         * only the blocks that start below it, so the earlier a block ends the fewer rows pay for the next one */
         int cols = (((span + nblk - 1) / nblk) + 31) & ~31;
-        if (cols > cap) cols = cap;
+        if (cols > cap || greedy) cols = cap & ~31;
+        im->blk_greedy = greedy;
         im->blk = (gkm_idx_block *) calloc((size_t) nblk, sizeof(gkm_idx_block));
         if (!im->blk) { gkm_set_error("out of memory"); return 1; }
         im->nblk = nblk;
@@ -568,7 +574,7 @@ static int ensure_index(gkmb200_problem *p, gkm_gpu *g, gkm_image *im, int col_b
         const size_t sbytes = gkm_idx_scratch_bytes(P, L, &cub_bytes);
         void *scratch = NULL, *d_offs = NULL;
         size_t scratch_got = 0, offs_got = 0;
-        /* unit-weight kernel types get the compact 16-bit slots (a block never holds more than 16384 columns) */
+        /* unit-weight kernel types get the compact slots with 15-bit columns (index_block_cap keeps the blocks below that) */
         b->fmt = GKM_IDX_FMT_P32;
         if (!gkm_opt_index_wide()) {
             if (!p->weighted && nc <= GKM_IDX_C16_MAX_COLS) b->fmt = GKM_IDX_FMT_C16;
@@ -616,6 +622,13 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     const int opt = gkm_opt_kernel();
     int v = base_variant(p);
     double ci = 0.0, cd = 0.0; /* estimates of kernel = auto */
+    /* How the columns are cut into index blocks (index_split).  In a lower triangle row a probes only the blocks that start
+     * below it: full blocks first, the rest last (50k: 16 384 + 16 384 + 16 384 + 848 columns = 2.03 n row-block probes
+     * against 2.5 n for four equal blocks).  Measured (tools/split_ab.py, profiles/r2_index_split_ab.txt): 50k x 50k 672 ->
+     * 609 ms with blocks of 16 384, 577 ms with blocks of 22 528; 20k wgkm 244 -> 225 ms.  A rectangle probes every block
+     * from every row: equal shares there. */
+    const int gopt = gkm_opt_index_greedy();
+    const int greedy = gopt >= 0 ? gopt : (lower != 0);
     if ((opt == GKM_KERNEL_AUTO || opt == GKM_KERNEL_INDEX) && nrows > 0 && ncols > 0 &&
         gkm_idx_supported(p->param.L, p->param.d, p->nbins)) {
         const int cap = index_block_cap(p);
@@ -632,7 +645,13 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             const double nq = sum / (double) p->n;
             const long long entries = (long long) nrows * (long long) ncols / (lower ? 2 : 1);
             /* lower: row a probes only the blocks that start below it */
-            const double eff_blocks = lower ? 0.5 * (double) (blocks + 1) : (double) blocks;
+            double eff_blocks = lower ? 0.5 * (double) (blocks + 1) : (double) blocks;
+            if (greedy) { /* rows of block k probe k + 1 blocks; all blocks but the last hold cap columns */
+                const int capc = cap & ~31;
+                double s = 0.0;
+                for (int k = 0; k < blocks; k++) s += (double) (k + 1) * (double) ((k + 1) * capc <= ncols ? capc : ncols - k * capc);
+                eff_blocks = s / (double) ncols;
+            }
             ci = gkm_idx_cost_ms(p->param.L, p->param.d, p->weighted, nrows, nq, eff_blocks, entries, 2.0 * nq * nq);
             cd = gkm_diag_cost_ms(p->param.d, p->weighted, entries, 2.0 * nq * nq);
             ok = ci < cd;
@@ -643,7 +662,7 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
     if (v == GKM_KERNEL_INDEX) {
         /* every GPU builds its own copy of the (cheap) index: side by side, one host thread per GPU -- in turn the
          * builds of an 8-GPU call at 50k (4 column blocks each, a stream sync per block) were ~25 ms of host time */
-        struct idx_job { gkmb200_problem *p; int slot, col0, col1, rc; char err[256]; };
+        struct idx_job { gkmb200_problem *p; int slot, col0, col1, greedy, strict, rc; char err[256]; };
         idx_job jobs[GKM_MAX_DEV];
         pthread_t th[GKM_MAX_DEV];
         int started[GKM_MAX_DEV];
@@ -653,13 +672,13 @@ static int choose_variant(gkmb200_problem *p, int row0, int nrows, int col0, int
             gkm_gpu *g = &g_gpu[d->dev[j->slot]];
             j->rc = 1;
             if (cudaSetDevice(d->dev[j->slot]) != cudaSuccess) { gkm_set_error("CUDA: cannot select device %d", d->dev[j->slot]); }
-            else if (!ensure_index(j->p, g, &d->img[j->slot], j->col0, j->col1) &&
+            else if (!ensure_index(j->p, g, &d->img[j->slot], j->col0, j->col1, j->greedy, j->strict) &&
                      cudaEventRecord(g->join, g->sc) == cudaSuccess && cudaStreamWaitEvent(g->sc2, g->join, 0) == cudaSuccess) j->rc = 0;
             if (j->rc) snprintf(j->err, sizeof(j->err), "%s", gkmb200_last_error());
             return NULL;
         };
         for (int i = 0; i < ds->ndev; i++) {
-            jobs[i].p = p; jobs[i].slot = i; jobs[i].col0 = col0; jobs[i].col1 = col0 + ncols; jobs[i].rc = 0; jobs[i].err[0] = 0;
+            jobs[i].p = p; jobs[i].slot = i; jobs[i].col0 = col0; jobs[i].col1 = col0 + ncols; jobs[i].greedy = greedy; jobs[i].strict = gopt >= 0; jobs[i].rc = 0; jobs[i].err[0] = 0;
             started[i] = (i > 0) && pthread_create(&th[i], NULL, body, &jobs[i]) == 0;
         }
         body(&jobs[0]);

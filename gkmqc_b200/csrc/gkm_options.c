@@ -6,6 +6,7 @@
  *   GKM_MAX_L    = 12 | 16                 ceiling of the parameter gate in gkm_main_pywrapper
  *   GKM_CHUNK_MB = n                       upper bound of one chunk's dense output
  *   GKM_INDEX_COLS = n                     upper bound of the columns of one index block (tests: forces several blocks)
+ *   GKM_INDEX_SPLIT = equal | greedy       how a column range is cut into index blocks: equal shares, or full blocks first
  *   GKM_PACK     = device | host           who builds the 2-bit plane image from the base codes (default: the GPU)
  *   GKM_DEVICES  = "0,1,.."                GPUs to use (gkm_device.cu)
  */
@@ -24,6 +25,7 @@ static int g_diag_flavor = -1;
 static int g_index_cols = 0;
 static int g_index_wide = 0;
 static int g_pack_host = 0;
+static int g_index_greedy = -1; /* -1: the library decides per call */
 
 static int parse_kernel(const char *v, int *out)
 {
@@ -48,6 +50,7 @@ static void load_env(void)
     if ((v = getenv("GKM_INDEX_COLS")) != NULL) { int x = atoi(v); if (x >= 32) g_index_cols = x & ~31; }
     if ((v = getenv("GKM_INDEX_WIDE")) != NULL) g_index_wide = atoi(v) != 0;
     if ((v = getenv("GKM_PACK")) != NULL) g_pack_host = !strcmp(v, "host");
+    if ((v = getenv("GKM_INDEX_SPLIT")) != NULL) g_index_greedy = !strcmp(v, "greedy") ? 1 : !strcmp(v, "equal") ? 0 : -1;
     if ((v = getenv("GKM_TILE_ROWS")) != NULL) { int x = atoi(v); if (x >= 1 && x <= 16) g_tile_rows = x; }
 }
 
@@ -59,6 +62,7 @@ int gkm_opt_diag_flavor(void) { load_env(); return g_diag_flavor; }
 int gkm_opt_index_cols(void) { load_env(); return g_index_cols; }
 int gkm_opt_index_wide(void) { load_env(); return g_index_wide; }
 int gkm_opt_pack_host(void) { load_env(); return g_pack_host; }
+int gkm_opt_index_greedy(void) { load_env(); return g_index_greedy; }
 
 int gkmb200_set_option(const char *key, const char *value)
 {
@@ -96,6 +100,11 @@ int gkmb200_set_option(const char *key, const char *value)
     if (!strcmp(key, "pack")) { /* device (default): the GPU packs the bit planes from one byte per base; host: gkm_seq.c does (A/B, tests) */
         if (strcmp(value, "host") && strcmp(value, "device")) { gkm_set_error("pack must be host or device"); return 1; }
         g_pack_host = !strcmp(value, "host");
+        return 0;
+    }
+    if (!strcmp(key, "index_split")) { /* equal: blocks of equal size; greedy: full blocks first, the rest last; auto: per call */
+        if (strcmp(value, "equal") && strcmp(value, "greedy") && strcmp(value, "auto")) { gkm_set_error("index_split must be equal, greedy or auto"); return 1; }
+        g_index_greedy = !strcmp(value, "greedy") ? 1 : !strcmp(value, "equal") ? 0 : -1;
         return 0;
     }
     if (!strcmp(key, "tile_rows")) {

@@ -476,16 +476,51 @@ def test_one_core_affinity_still_correct(tmp_path):
     assert np.array_equal(np.load(out)[:n, :n], g["kmat"])
 
 
-@pytest.mark.parametrize("kernel_type", [2, 4])
-def test_two_column_blocks_at_20k_index_against_bitsliced(kernel_type):
-    """20 000 x 300 bp: the index kernel runs two column blocks (rows of the second block probe both); rows on both sides
-    of the block boundary, the first and the last rows: integers and doubles against the bit-sliced kernel"""
+@pytest.mark.parametrize("kernel_type,L,k,d", [(2, 11, 7, 3), (4, 10, 6, 3), (2, 6, 4, 2)])
+def test_index_split_layouts(kernel_type, L, k, d):
+    """the two ways of cutting a lower triangle's columns into index blocks (option index_split: equal shares / full blocks
+    first, which is what a lower triangle gets by default) give the oracle's integers and doubles, from different layouts"""
+    n = 150
+    seqs = random_seqs(n, 120, seed=5 * L + d + kernel_type, ragged=True)
+    seqs = [s if len(s) >= L else s + "ACGT" * 4 for s in seqs]
+    seqs[127] = seqs[2]
+    seqs[128] = seqs[3]
+    o = pyoracle.Oracle(kernel_type, L, k, d, 50, 50.0, 0.7)
+    for s in seqs:
+        o.add(s)
+    Ko, Ho = o.matrix_lower()
+    capi.set_option("kernel", "index")
+    capi.set_option("index_cols", "128")
+    layouts = {}
+    try:
+        for split in ("equal", "greedy", "auto"):
+            capi.set_option("index_split", split)
+            with capi.Problem(kernel_type, L, k, d, 50, 50.0, 0.7) as P:
+                P.add_many(seqs)
+                assert np.array_equal(P.hist_block(0, n, 0, n, lower=True), Ho), split
+                layouts[split] = P.index_layout()
+                check_kmat(P.kernel_lower(), Ko, kernel_type)
+                assert P.stats()["kernel_variant"] == 4
+    finally:
+        capi.set_option("index_cols", "0")
+        capi.set_option("index_split", "auto")
+        capi.set_option("kernel", "auto")
+    assert layouts["equal"][:2] == (2, 96) and layouts["greedy"][:2] == (2, 128) and layouts["auto"] == layouts["greedy"]
+
+
+@pytest.mark.parametrize("kernel_type,split", [(2, "equal"), (4, "equal"), (2, "greedy"), (4, "greedy")])
+def test_two_column_blocks_at_20k_index_against_bitsliced(kernel_type, split):
+    """20 000 x 300 bp with at most 16 384 columns per index block: two column blocks, cut into equal shares or full block
+    first (rows of the second block probe both); rows on both sides of the block boundary, the first and the last rows:
+    integers and doubles against the bit-sliced kernel"""
     import bench
     n = 20000
     arr = bench.synth(n, seed=77)
     got = {}
     for v in ("index", "diag"):
         capi.set_option("kernel", v)
+        capi.set_option("index_cols", "16384")
+        capi.set_option("index_split", split)
         try:
             with capi.Problem(kernel_type, 11, 7, 3) as P:
                 P.add_block(arr)
@@ -494,11 +529,14 @@ def test_two_column_blocks_at_20k_index_against_bitsliced(kernel_type):
                     K0 = P.kernel_block(n - 1, 1, 0, n - 1)     # creates the partition over all columns
                     nblk, cols, _ = P.index_layout()
                     assert nblk == 2
+                    assert cols == (10016 if split == "equal" else 16384 if kernel_type == 2 else 16352)
                     rows = sorted({1, 2, cols - 1, cols, cols + 1, cols + 147, cols + 148, n - 149, n - 148, n - 2, n - 1, 12345})
                 got[v] = [(P.hist_block(r, 1, 0, r)[0], P.kernel_block(r, 1, 0, r)[0]) for r in rows]
                 assert P.stats()["kernel_variant"] == {"diag": 2, "index": 4}[v]
         finally:
             capi.set_option("kernel", "auto")
+            capi.set_option("index_cols", "0")
+            capi.set_option("index_split", "auto")
     for r, (hi, ki), (hd, kd) in zip(rows, got["index"], got["diag"]):
         assert np.array_equal(hi, hd), "histograms of row %d" % r
         assert np.array_equal(ki, kd), "kernel values of row %d" % r
