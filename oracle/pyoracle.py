@@ -208,6 +208,10 @@ class RefHook:
         lib.gkmref_sqnorm.restype = ctypes.c_double
         lib.gkmref_sqnorm.argtypes = [ctypes.c_int]
         lib.gkmref_seqlen.argtypes = [ctypes.c_int]
+        for f in ("gkmref_sid", "gkmref_seq_string"):   # absent from a hook built before these were added
+            if hasattr(lib, f):
+                getattr(lib, f).restype = ctypes.c_char_p
+                getattr(lib, f).argtypes = [ctypes.c_int]
         lib.gkmref_poswt.argtypes = [ctypes.c_int, c_u8_p, c_u8_p]
         lib.gkmref_codes.argtypes = [ctypes.c_int, c_u8_p, c_u8_p]
         lib.gkmref_mmprofile.argtypes = [ctypes.c_int, ctypes.c_int, c_int_p]
@@ -238,6 +242,12 @@ class RefHook:
 
     def seqlen(self, i):
         return self.lib.gkmref_seqlen(i)
+
+    def sid(self, i):
+        return self.lib.gkmref_sid(i)
+
+    def seq_string(self, i):
+        return self.lib.gkmref_seq_string(i)
 
     def poswt(self, i):
         nk = self.seqlen(i) - self.L + 1

@@ -77,6 +77,9 @@ void gkmref_weights_only(int kernel_type, int L, int k, double *out, int n)
 
 double gkmref_sqnorm(int i) { return g_prob.x[i]->sqnorm; }
 int gkmref_seqlen(int i) { return g_prob.x[i]->seqlen; }
+/* record id and spelling as the reference's reader stored them (libgkm.c:849-860,1287-1292) */
+const char *gkmref_sid(int i) { return g_prob.x[i]->sid; }
+const char *gkmref_seq_string(int i) { return g_prob.x[i]->seq_string; }
 
 void gkmref_poswt(int i, unsigned char *wt, unsigned char *wt_rc)
 {

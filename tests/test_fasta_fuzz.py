@@ -1,0 +1,139 @@
+"""CPU tier: the product's FASTA reader against the UNMODIFIED reference's reader on generated files.
+
+The reference ships no reader tests; tests/golden holds two hand-made fixtures.  Here hypothesis writes
+FASTA files inside the input space on which the reference's reader is well defined and both readers must agree on
+every record: count, order (positives first, libgkm.c:1316-1333), id (first token behind '>', libgkm.c:1287-1292),
+length after the 2047-base cut (libgkm.c:1294-1299), spelling (seq_string) and base codes of both strands
+(libgkm.c:864-888).
+
+Kept out of the generator, because the reference itself is undefined there (not because the product is):
+  * lines of 1023 bytes or more: readline() reallocs a by-value buffer, the caller keeps the stale pointer
+    (libgkm.c:1207-1225)
+  * a last line without a newline: the same buffer is freed twice (libgkm.c:1312)
+  * text before the first '>': strcat() onto an uninitialised array (libgkm.c:1263,1301)
+  * files without records (y[-1] is written, libgkm.c:1307) and records shorter than L (malloc of a negative size,
+    libgkm.c:891-893) -- the product rejects both with an error (test_host_logic.py::test_fasta_quirks)
+  * NUL bytes (fgets/strlen disagree about where such a line ends)
+"""
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle
+from gkmqc_b200 import capi
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref (the compiled reference) is not here")
+
+L = 5  # a small tree: the reference allocates 4^L leaves per open problem
+EOLS = ("\n", "\r\n")
+BASES = "ACGTacgt"
+NOISE = "Nn-*xXRYKM.0 \t"        # counted as 'A' by both sides (libgkm.c:871-874), blanks included
+ID_CHARS = "abcXYZ019:_-|.>"
+
+
+def _line(draw, max_len):
+    n = draw(st.integers(0, max_len))
+    noisy = draw(st.integers(0, 9)) == 0
+    alphabet = BASES + (NOISE if noisy else "")
+    body = "".join(draw(st.lists(st.sampled_from(alphabet), min_size=n, max_size=n)))
+    if body.startswith(">"):
+        body = "A" + body[1:]
+    # a CR inside a line ends it there for both readers (libgkm.c:1222); what follows up to the LF is dropped
+    if draw(st.integers(0, 19)) == 0 and len(body) > 2:
+        cut = draw(st.integers(1, len(body) - 1))
+        body = body[:cut] + "\r" + body[cut:]
+    return body + draw(st.sampled_from(EOLS))
+
+
+@st.composite
+def fasta_text(draw):
+    nrec = draw(st.integers(1, 6))
+    out = []
+    for _ in range(nrec):
+        sid = "".join(draw(st.lists(st.sampled_from(ID_CHARS), min_size=0, max_size=12)))
+        desc = draw(st.sampled_from(["", " description here", "\tlen=300", "  two  blanks", " >not a record"]))
+        out.append(">" + sid + desc + draw(st.sampled_from(EOLS)))
+        shape = draw(st.sampled_from(["short", "short", "multi", "long"]))
+        if shape == "short":
+            lines, max_len = draw(st.integers(0, 3)), 40
+        elif shape == "multi":
+            lines, max_len = draw(st.integers(2, 8)), 120
+        else:                     # crosses the 2047-base cut, at a line boundary or inside a line
+            lines, max_len = draw(st.integers(3, 5)), 1000
+        for _ in range(lines):
+            out.append(_line(draw, max_len))
+            if draw(st.integers(0, 7)) == 0:
+                out.append(draw(st.sampled_from(EOLS)))      # blank line inside a record
+        # no record may end up shorter than L (see the module docstring)
+        out.append("".join(draw(st.lists(st.sampled_from("ACGT"), min_size=L, max_size=L + 3))) + draw(st.sampled_from(EOLS)))
+    return "".join(out)
+
+
+def _records(P):
+    rec = []
+    for i in range(P.n):
+        f, r = P.codes(i)
+        rec.append((P.seqlen(i), P.sid(i), f.tobytes(), r.tobytes()))
+    return rec
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(pos=fasta_text(), neg=fasta_text())
+def test_reader_agrees_with_the_reference_reader(tmp_path, pos, neg):
+    lib = capi.load()
+    pf, nf = tmp_path / "pos.fa", tmp_path / "neg.fa"
+    pf.write_bytes(pos.encode("ascii"))
+    nf.write_bytes(neg.encode("ascii"))
+    lib.gkmb200_set_verbosity(0)      # both sides warn about every noise letter; not the point here
+    ref = pyoracle.RefHook(str(pf), str(nf), kernel_type=4, L=L, k=3, d=2)
+    try:
+        if not hasattr(ref.lib, "gkmref_sid"):
+            pytest.skip("oracle/_ref was built before the hook exported sid / seq_string")
+        with capi.Problem(4, L, 3, 2) as P:
+            assert P.read(str(pf), str(nf)) == ref.npos
+            assert P.n == ref.n
+            ours = _records(P)
+        for i, (ln, sid, fwd, rc) in enumerate(ours):
+            assert ln == ref.seqlen(i), i
+            assert ln <= 2047
+            assert sid == ref.sid(i), i
+            rf, rr = ref.codes(i)
+            assert fwd == rf.tobytes() and rc == rr.tobytes(), i
+    finally:
+        ref.close()
+        lib.gkmb200_set_verbosity(2)
+
+
+def test_cut_at_2047_bases_in_every_position_of_a_line(tmp_path):
+    """the cut (libgkm.c:1294-1299) falls at a line boundary, one base before it, one behind it, and in the middle"""
+    lib = capi.load()
+    lib.gkmb200_set_verbosity(0)
+    rng = np.random.default_rng(7)
+    recs = []
+    for first in (2046, 2047, 2048, 1500):
+        seq = "".join(rng.choice(list("ACGT"), first + 700))
+        lines = [seq[i:i + 500] for i in range(0, first, 500)]
+        lines[-1] = seq[(len(lines) - 1) * 500:first]
+        lines.append(seq[first:])
+        recs.append(">r%d\n" % first + "\n".join(lines) + "\n")
+    pf, nf = tmp_path / "p.fa", tmp_path / "n.fa"
+    pf.write_text("".join(recs))
+    nf.write_text(">n\nACGTACGTAC\n")
+    ref = pyoracle.RefHook(str(pf), str(nf), kernel_type=2, L=L, k=3, d=2)
+    try:
+        with capi.Problem(2, L, 3, 2) as P:
+            assert P.read(str(pf), str(nf)) == 4 == ref.npos
+            for i in range(P.n):
+                assert P.seqlen(i) == ref.seqlen(i)
+                f, r = P.codes(i)
+                rf, rr = ref.codes(i)
+                assert np.array_equal(f, rf) and np.array_equal(r, rr)
+            assert [P.seqlen(i) for i in range(4)] == [2047] * 4
+    finally:
+        ref.close()
+        lib.gkmb200_set_verbosity(2)
