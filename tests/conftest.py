@@ -56,7 +56,8 @@ def emu_lib():
     import ctypes
     import __graft_entry__ as ge
     from gkmqc_b200 import capi
-    lib = ctypes.CDLL(ge.build_emulator())
+    # GKM_EMU_LIB: another build of the emulator library (tools/asan_host.sh: the host C under ASan + UBSan)
+    lib = ctypes.CDLL(os.environ.get("GKM_EMU_LIB") or ge.build_emulator())
     capi._declare(lib)
     lib.gkm_emu_hist_lower.argtypes = [ctypes.c_void_p, capi.c_i32_p]
     lib.gkm_emu_hist.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, capi.c_i32_p]
