@@ -1,8 +1,9 @@
 #!/bin/sh
 # The host C of the library (FASTA reader, coding, host packer, weights, chunk planner, index cost model) and the CPU
 # emulator of the index variant under AddressSanitizer + UndefinedBehaviorSanitizer, driven by the CPU test tier.
-# The CUDA objects cannot be sanitised this way (nvcc, static cudart); compute-sanitizer covers them on the GPU box
-# (tools/sanitize_target.py).  The bit-sliced emulator is compiled plain: its templates take minutes under ASan.
+# The CUDA objects cannot be sanitised this way (nvcc, static cudart), and compute-sanitizer is closed on this GPU pool
+# (tools/sanitize_target.py is the command it would run): the device code's addressing rules are checked on the CPU by the
+# emulators this script runs.  The bit-sliced emulator is compiled plain: its templates take minutes under ASan.
 set -e
 cd "$(dirname "$0")/.."
 B=build/asan
