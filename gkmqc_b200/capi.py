@@ -119,6 +119,7 @@ def _declare(lib):
         ("gkmb200_get_stats", [P, ctypes.POINTER(gkmb200_stats)]),
         ("gkmb200_problem_index_layout", [P, c_int_p]),
         ("gkmb200_problem_image", [P, ctypes.c_void_p, ctypes.c_void_p, c_int_p]),
+        ("gkmb200_resident_rows", [P, I, I, c_dbl_p, ctypes.c_long]),
         ("gkmb200_trim", []),
         ("gkmb200_bench_lower_resident", [P, I, I, I, c_dbl_p]),
         ("gkmb200_microbench", [ctypes.c_char_p, c_dbl_p]),
@@ -322,6 +323,14 @@ class Problem:
         wend = np.zeros((n, 32 * W), np.uint8) if self.kernel_type in (4, 5) else None
         _check(self.lib.gkmb200_problem_image(self.h, planes.ctypes.data, wend.ctypes.data if wend is not None else None, shape), self.lib)
         return planes, wend
+
+    def resident_matrix(self, row0=0, nrows=None):
+        """rows of the symmetric kernel matrix kept on the device (computed on first use; what svm_cv(problem=...) consumes);
+        nrows = 0 only makes it resident"""
+        nrows = self.n - row0 if nrows is None else nrows
+        out = np.zeros((max(nrows, 1), self.n))
+        _check(self.lib.gkmb200_resident_rows(self.h, row0, nrows, out.ctypes.data_as(c_dbl_p), self.n), self.lib)
+        return out[:nrows]
 
     def index_layout(self):
         """(column blocks, columns per block, first column) of the index variant's last call; (0, 0, 0) otherwise"""

@@ -1483,7 +1483,40 @@ extern "C" int gkm_dev_decision(gkmb200_problem *p, int row0, int nrows, int col
 /* ------------------------------------------------------------------ */
 /* the consumer: cross-validated C-SVC on the resident matrix (8f/f4)   */
 /* ------------------------------------------------------------------ */
-/* one pass of the lower triangle into im->full on GPU 0, then mirrored: the matrix never leaves the device */
+/* GPUs of the call that compute chunks of the resident matrix.  The matrix lives on the first selected GPU; the others
+ * may help only if they can store into its memory -- peer access over NVLink / NVSwitch, enabled once per process and
+ * pair.  All of them or one: GKM_RESIDENT_GPUS=1 keeps the whole pass on the owner (A/B, and boxes whose GPUs are
+ * not peers do so by themselves).  Leaves another device current. */
+static int resident_sharers(const gkm_devstate *ds)
+{
+    static signed char peer_ok[GKM_MAX_DEV][GKM_MAX_DEV]; /* [writer][owner]: 0 not asked yet, 1 yes, -1 no */
+    const char *e = getenv("GKM_RESIDENT_GPUS");
+    if (ds->ndev < 2 || (e && atoi(e) == 1)) return 1;
+    const int owner = ds->dev[0];
+    for (int i = 1; i < ds->ndev; i++) {
+        const int d = ds->dev[i];
+        if (d == owner) return 1;
+        if (peer_ok[d][owner] == 0) {
+            int can = 0;
+            peer_ok[d][owner] = -1;
+            if (cudaDeviceCanAccessPeer(&can, d, owner) == cudaSuccess && can && cudaSetDevice(d) == cudaSuccess) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(owner, 0);
+                if (pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled) peer_ok[d][owner] = 1;
+            }
+            cudaGetLastError();
+            gkm_log(GKM_LOG_DEBUG, "GPU %d %s store into the memory of GPU %d", d, peer_ok[d][owner] > 0 ? "may" : "cannot", owner);
+        }
+        if (peer_ok[d][owner] < 0) return 1;
+    }
+    return ds->ndev;
+}
+
+/* One pass of the lower triangle into im->full on the first selected GPU, then mirrored there: the matrix never leaves
+ * the devices.  With several GPUs in the call (one process, GKM_DEVICES) the chunks go round-robin over all of them
+ * and every GPU writes its entries straight into the owner's matrix -- the epilogue's streaming stores travel over
+ * NVLink while the next rows are being counted, so there is no gather step and no staging copy (SURVEY.md 8f/f4:
+ * "NVSwitch allgather of tiles if sharded"; here the tiles are never anywhere else).  Each GPU reads its own replica
+ * of the sequence image, the sqnorms and -- index variant -- its own slot tables (choose_variant built them). */
 static int resident_symmetric(gkmb200_problem *p)
 {
     gkm_devstate *ds = p->dev;
@@ -1491,6 +1524,7 @@ static int resident_symmetric(gkmb200_problem *p)
     gkm_image *im = &ds->img[0];
     const int n = p->n;
     if (im->full && im->full_sym) return 0;
+    const int nshare = resident_sharers(ds);
     CK(cudaSetDevice(ds->dev[0]));
     if (!im->full) {
         im->full_ld = ((size_t) n + 15) & ~(size_t) 15;
@@ -1499,28 +1533,74 @@ static int resident_symmetric(gkmb200_problem *p)
     const int by_rows = (ds->variant == GKM_KERNEL_INDEX);
     const int maxc = n / 16 + 2;
     gkm_chunk *chunks = (gkm_chunk *) malloc(sizeof(gkm_chunk) * (size_t) maxc);
-    const int nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, 1),
+    const int nchunks = chunks ? gkm_plan_chunks_rows(0, n, 0, n, 1, by_rows ? 148 : 16, plan_budget(p, (long long) n * n / 2, nshare),
                                                       by_rows ? 4 * 148 : 65520 /* grid.y */, chunks, maxc) : -1;
     if (nchunks < 0) { free(chunks); gkm_set_error("chunk planning failed"); return 1; }
-    int rc = 0, launches = 0;
+    int rc = 0, issued[GKM_MAX_DEV];
+    long long kernels = 0;
+    for (int s = 0; s < GKM_MAX_DEV; s++) issued[s] = 0;
     for (int c = 0; !rc && c < nchunks; c++) {
+        const int s = c % nshare;
+        gkm_gpu *gs = &g_gpu[ds->dev[s]];
+        if (nshare > 1 && cudaSetDevice(ds->dev[s]) != cudaSuccess) { gkm_set_error("CUDA: cannot select device %d", ds->dev[s]); rc = 1; break; }
         gkm_kparams kp;
-        fill_kparams(p, im, &kp);
+        fill_kparams(p, &ds->img[s], &kp);
         kp.mode = GKM_MODE_LOWER;
         kp.row_begin = chunks[c].row_begin; kp.row_end = chunks[c].row_end;
         kp.col_begin = chunks[c].col_begin; kp.col_end = chunks[c].col_end;
         kp.row_base = 0; kp.col_base = 0;
-        kp.out = im->full; kp.ld = (long long) im->full_ld;
-        rc = launch_hist(p, im, g, kp, (launches++ & 1) ? g->sc2 : g->sc, NULL);
+        kp.out = im->full; kp.ld = (long long) im->full_ld; /* the owner's block, whichever GPU runs the chunk */
+        const long long k_before = gs->nkernels;
+        rc = launch_hist(p, &ds->img[s], gs, kp, (issued[s]++ & 1) ? gs->sc2 : gs->sc, NULL);
+        kernels += gs->nkernels - k_before;
     }
     free(chunks);
+    /* the stores of the other GPUs have landed once their streams have drained; the owner mirrors the triangle after that */
+    for (int s = 1; s < nshare; s++) {
+        gkm_gpu *gs = &g_gpu[ds->dev[s]];
+        if (cudaSetDevice(ds->dev[s]) != cudaSuccess || cudaStreamSynchronize(gs->sc) != cudaSuccess || cudaStreamSynchronize(gs->sc2) != cudaSuccess) {
+            if (!rc) gkm_set_error("CUDA: resident matrix, GPU %d: %s", ds->dev[s], cudaGetErrorString(cudaGetLastError()));
+            rc = 1;
+        }
+    }
+    CK(cudaSetDevice(ds->dev[0]));
     if (rc) return 1;
     CK(cudaEventRecord(g->join, g->sc2));
     CK(cudaStreamWaitEvent(g->sc, g->join, 0));
     if (gkm_svm_symmetrize(im->full, (long long) im->full_ld, n, g->sc)) { gkm_set_error("CUDA: symmetrize kernel failed"); return 1; }
     im->full_sym = 1;
-    p->stats.launches += launches + 1;
+    p->stats.launches += kernels + 1;
+    p->stats.devices = nshare;
     return 0;
+}
+
+/* rows [row0, row0 + nrows) of the resident symmetric matrix, computed on first use: out[(r - row0) * ld + c] = K(r, c)
+ * for every c < n, unit diagonal.  nrows = 0 only makes the matrix resident (and waits for it). */
+extern "C" int gkmb200_resident_rows(gkmb200_problem *p, int row0, int nrows, double *out, long ld)
+{
+    if (!p) { gkm_set_error("null problem"); return 1; }
+    if (row0 < 0 || nrows < 0 || row0 + nrows > p->n || (nrows > 0 && (!out || ld < p->n))) { gkm_set_error("rows [%d,+%d) outside the matrix (n=%d) or ld < n", row0, nrows, p->n); return 1; }
+    pthread_mutex_lock(&g_lock);
+    const double t0 = now_ms();
+    p->stats.launches = 0;
+    int rc = upload_locked(p, 0);
+    if (!rc) rc = choose_variant(p, 0, p->n, 0, p->n, 1);
+    if (!rc) rc = resident_symmetric(p);
+    if (!rc) {
+        gkm_devstate *ds = p->dev;
+        gkm_gpu *g = &g_gpu[ds->dev[0]];
+        const gkm_image *im = &ds->img[0];
+        cudaError_t e = cudaSetDevice(ds->dev[0]);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc);
+        if (e == cudaSuccess && nrows > 0)
+            e = cudaMemcpy2D(out, (size_t) ld * sizeof(double), im->full + (size_t) row0 * im->full_ld, im->full_ld * sizeof(double),
+                             (size_t) p->n * sizeof(double), (size_t) nrows, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { gkm_set_error("CUDA: resident matrix read-back: %s", cudaGetErrorString(e)); rc = 1; }
+        p->stats.kernel_variant = ds->variant;
+        p->stats.wall_ms = now_ms() - t0;
+    }
+    pthread_mutex_unlock(&g_lock);
+    return rc;
 }
 
 extern "C" int gkm_dev_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int ntasks, const gkmb200_svm_task *tasks,

@@ -118,6 +118,11 @@ int gkmb200_svm_cv(gkmb200_problem *p, const double *kmat, long ld, int n, int n
                    const int *train_idx, const signed char *train_y, const int *test_idx,
                    double C, double eps, int max_iter, double *scores, gkmb200_svm_fit *fits, double *alpha);
 
+/* rows [row0, row0 + nrows) of the resident symmetric matrix of p (all n columns, unit diagonal; ld >= n doubles per row),
+ * computed on first use and kept on the device for gkmb200_svm_cv; nrows = 0 only makes it resident.  With several
+ * GPUs in one process every GPU writes its chunks straight into the first GPU's matrix (peer stores over NVLink). */
+int gkmb200_resident_rows(gkmb200_problem *p, int row0, int nrows, double *out, long ld);
+
 /* the packed image as it lies on GPU 0: planes[n][3][W] (code bit 0, code bit 1, window-end plane E; both strands in one
  * circular string) and, weighted kernel types only, wend[n][32 W]; either may be NULL; out_shape = {n, W} */
 int gkmb200_problem_image(gkmb200_problem *p, uint32_t *planes, uint8_t *wend, int *out_shape);

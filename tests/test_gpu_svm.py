@@ -173,3 +173,59 @@ def test_command_line_of_gkmsvm_on_the_engine(tmp_path):
     auc3, _ = driver.main(["-p", str(pos), "-n", str(neg), "-w", name, "-s", "3", "-v", "0", "-t", "4", "-L", "10", "-k", "6", "-d", "3",
                            "-M", "50", "-H", "50", "-C", "1.0", "-e", "0.001", "-x", "5", "-r", "1"])
     assert auc3 == auc
+
+
+def _resident_against_host_matrix(ids):
+    """the matrix kept on the device (gkmb200_resident_rows) = the caller-side matrix of the same problem, symmetrised like
+    gkmsvm.py:96-97 -- on the GPUs `ids` of this process: with several, every GPU stores its chunks into the first one's
+    memory (peer access), so the comparison covers rows written by each of them"""
+    lib = capi.load()
+    arr = (capi.ctypes.c_int * len(ids))(*ids)
+    assert lib.gkmb200_set_devices(arr, len(ids)) == 0, capi.last_error()
+    seqs = random_seqs(1300, 260, seed=41, ragged=True)
+    try:
+        for variant, kt, L, k, d in (("diag", 2, 11, 7, 3), ("index", 2, 11, 7, 3), ("index", 4, 10, 6, 3), ("mma", 4, 10, 6, 3)):
+            capi.set_option("kernel", variant)
+            with capi.Problem(kt, L, k, d, 50, 50.0, 1.0) as P:
+                P.add_many(seqs)
+                R = P.resident_matrix()
+                st = P.stats()
+                assert st["devices"] == len(ids), (variant, st)
+                low = np.tril(P.kernel_lower(), -1)
+                K = low + low.T + np.eye(P.n)
+                assert np.array_equal(R, K), (variant, kt, len(ids))
+                assert np.array_equal(P.resident_matrix(5, 7), K[5:12])          # a band of the matrix that is already there
+                with pytest.raises(capi.GkmError):
+                    P.resident_matrix(P.n - 3, 4)
+            if variant == "index":
+                assert st["kernel_variant"] == 4
+    finally:
+        capi.set_option("kernel", "auto")
+
+
+def test_resident_matrix_read_back():
+    _resident_against_host_matrix([0])
+
+
+def test_resident_matrix_shared_by_the_gpus_of_one_process_if_available(problem):
+    ndev = capi.device_count()
+    if ndev < 2:
+        pytest.skip("single GPU box")
+    try:
+        _resident_against_host_matrix(list(range(ndev)))
+        # the consumer on a matrix every GPU wrote a share of: the same fits, bit for bit, as on the host matrix
+        P0, K, y = problem
+        splits = list(StratifiedKFold(n_splits=4, shuffle=True, random_state=11).split(np.zeros(len(y)), y))
+        s_host, f_host, _ = capi.svm_cv(y, splits, kmat=K, C=1.0, eps=1e-3)
+        with capi.Problem(4, 10, 6, 3, 50, 50.0, 1.0) as P:
+            for i in range(P0.n):
+                f, _ = P0.codes(i)
+                P.add(bytes(b"ACGT"[c - 1] for c in f))
+            s_dev, f_dev, _ = capi.svm_cv(y, splits, problem=P, C=1.0, eps=1e-3)
+            assert P.stats()["devices"] == ndev
+        for a, b in zip(s_host, s_dev):
+            assert np.array_equal(a, b)
+        assert [f["n_iter"] for f in f_host] == [f["n_iter"] for f in f_dev]
+    finally:
+        ids = (capi.ctypes.c_int * 1)(0)
+        capi.load().gkmb200_set_devices(ids, 1)
