@@ -1,0 +1,127 @@
+"""CPU tier: the libgkm.h entry points of the product (gkm_capi.c, on the host stand-in of the device layer -- see
+tests/test_abi_on_emulator.py) against THE SAME entry points of the unmodified reference (oracle/_ref/gkmref_hook.so is
+libgkm.c compiled as it is, so it exports gkmkernel_init / new_object / build_tree / kernelfunc_batch_all unmangled), on
+generated parameter sets and sequences: a caller of the C ABI must see the same structs and the same doubles.
+
+Compared per call sequence  init -> new_object x n -> build_tree -> kernelfunc_batch_all(a, 0, a) for every a:
+  gkm_kernel.weights[0..d]; every field of every gkm_data (sid, seqid, seqlen, seq, seq_rc, wt, wt_rc, kmerids, kmerids_rc,
+  seq_string, sqnorm); every kernel row.  Doubles bit for bit -- on the CPU both sides end in the same libm exp(), so
+  the RBF types are included."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import pyoracle
+import test_gpu_abi as T
+from gkmqc_b200 import capi
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref (the compiled reference) is not here")
+
+G = ctypes.POINTER(T.gkm_data)
+
+
+def declare(lib):
+    P = ctypes.c_void_p
+    lib.gkmkernel_init.restype = P
+    lib.gkmkernel_init.argtypes = [ctypes.POINTER(capi.gkm_parameter)]
+    lib.gkmkernel_build_tree.restype = None
+    lib.gkmkernel_build_tree.argtypes = [P, ctypes.POINTER(G), ctypes.c_int]
+    lib.gkmkernel_kernelfunc_batch_all.restype = capi.c_dbl_p
+    lib.gkmkernel_kernelfunc_batch_all.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, capi.c_dbl_p]
+    lib.gkmkernel_delete_object.restype = None
+    lib.gkmkernel_delete_object.argtypes = [G]
+    lib.gkmkernel_destroy.restype = None
+    lib.gkmkernel_destroy.argtypes = [P]
+    lib.gkmkernel_new_object.restype = G
+    lib.gkmkernel_new_object.argtypes = [P, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def libs(tmp_path_factory):
+    import __graft_entry__ as ge
+    ours = ctypes.CDLL(os.environ.get("GKM_ABI_EMU_LIB") or ge.build_abi_emulator())
+    capi._declare(ours)
+    ours.gkmb200_set_verbosity(0)
+    # the reference logs through a process-global logger that its pywrapper / the hook's open sets up (gkmkern_pylib.c:118-138)
+    d = tmp_path_factory.mktemp("ref")
+    fa = d / "x.fa"
+    fa.write_text(">a\nACGTACGTACGT\n")
+    h = pyoracle.RefHook(str(fa), str(fa), 2, 4, 2, 1)
+    h.close()
+    return declare(ours), declare(h.lib if h.lib is not None else ctypes.CDLL(os.path.join(pyoracle.REF_DIR, "gkmref_hook.so")))
+
+
+def run(lib, param, seqs):
+    """the call sequence on one library; everything read out before the objects are deleted"""
+    par = capi.gkm_parameter(*param)            # the kernel keeps a pointer to it
+    kern = lib.gkmkernel_init(ctypes.byref(par))
+    assert kern
+    d, L = param[3], param[1]
+    out = {"weights": np.array((ctypes.c_double * (d + 1)).from_address(kern + 8))}   # gkm_kernel.weights @8
+    objs = [lib.gkmkernel_new_object(kern, s, b"id%d" % i, 100 + i) for i, s in enumerate(seqs)]
+    assert all(objs)
+    recs = []
+    for o, s in zip(objs, seqs):
+        c = o.contents
+        n, nk = c.seqlen, c.seqlen - L + 1
+        arr = lambda p, k: np.ctypeslib.as_array(p, (k,)).copy()
+        recs.append((c.sid, c.seqid, n, arr(c.seq, n).tobytes(), arr(c.seq_rc, n).tobytes(), arr(c.wt, nk).tobytes(), arr(c.wt_rc, nk).tobytes(),
+                     arr(c.kmerids, nk).tobytes(), arr(c.kmerids_rc, nk).tobytes(), c.seq_string, c.sqnorm))
+    out["objects"] = recs
+    arrp = (G * len(objs))(*objs)
+    lib.gkmkernel_build_tree(kern, arrp, len(objs))
+    rows = []
+    for a in range(1, len(objs)):
+        res = np.zeros(a)
+        lib.gkmkernel_kernelfunc_batch_all(kern, a, 0, a, res.ctypes.data_as(capi.c_dbl_p))
+        rows.append(res)
+    out["rows"] = rows
+    for o in objs:
+        lib.gkmkernel_delete_object(o)
+    lib.gkmkernel_destroy(kern)
+    return out
+
+
+@st.composite
+def problems(draw):
+    L = draw(st.integers(3, 8))
+    k = draw(st.integers(1, L))
+    d = draw(st.integers(0, min(L - k, 4)))
+    kt = draw(st.integers(0, 5))
+    M = draw(st.sampled_from([1, 7, 50, 63, 64, 200, 255]))
+    H = draw(st.sampled_from([0.7, 3.0, 50.0, 400.0]))
+    gamma = draw(st.sampled_from([0.5, 1.0, 2.0]))
+    n = draw(st.integers(2, 6))
+    seqs = []
+    for _ in range(n):
+        ln = draw(st.integers(L, 90))
+        alphabet = "ACGT" if draw(st.integers(0, 3)) else "ACGTacgtNnRY-"
+        s = "".join(draw(st.lists(st.sampled_from(alphabet), min_size=ln, max_size=ln)))
+        if draw(st.integers(0, 5)) == 0:
+            s = (draw(st.sampled_from(["A", "AC", "ACGT"])) * ln)[:ln]              # low complexity: long posting lists, big counts
+        seqs.append(s.encode("ascii"))
+    if draw(st.booleans()):
+        seqs[-1] = seqs[0]                                                        # a duplicate: K = 1 off the diagonal
+    return (kt, L, k, d, M, H, gamma, 1), seqs
+
+
+@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(pb=problems())
+def test_same_structs_and_doubles_as_the_reference(libs, pb):
+    ours, ref = libs
+    param, seqs = pb
+    a, b = run(ours, param, seqs), run(ref, param, seqs)
+    assert np.array_equal(a["weights"], b["weights"]), (param, a["weights"], b["weights"])
+    names = ("sid", "seqid", "seqlen", "seq", "seq_rc", "wt", "wt_rc", "kmerids", "kmerids_rc", "seq_string", "sqnorm")
+    for i, (x, y) in enumerate(zip(a["objects"], b["objects"])):
+        for nm, u, v in zip(names, x, y):
+            assert u == v, (param, i, nm)
+    for i, (x, y) in enumerate(zip(a["rows"], b["rows"])):
+        assert x.tobytes() == y.tobytes(), (param, i + 1, x, y)   # bit patterns: 0 / 0 (a sequence whose only L-mer weighs 0 at M = 255) is the same NaN on both sides
