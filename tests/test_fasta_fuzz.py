@@ -51,7 +51,7 @@ def _line(draw, max_len):
 
 
 @st.composite
-def fasta_text(draw):
+def fasta_text(draw, min_len=L):
     nrec = draw(st.integers(1, 6))
     out = []
     for _ in range(nrec):
@@ -70,7 +70,7 @@ def fasta_text(draw):
             if draw(st.integers(0, 7)) == 0:
                 out.append(draw(st.sampled_from(EOLS)))      # blank line inside a record
         # no record may end up shorter than L (see the module docstring)
-        out.append("".join(draw(st.lists(st.sampled_from("ACGT"), min_size=L, max_size=L + 3))) + draw(st.sampled_from(EOLS)))
+        out.append("".join(draw(st.lists(st.sampled_from("ACGT"), min_size=min_len, max_size=min_len + 3))) + draw(st.sampled_from(EOLS)))
     return "".join(out)
 
 

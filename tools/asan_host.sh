@@ -24,7 +24,7 @@ LIB=$PWD/$B/libgkm_emu_asan.so
 # leaks are not checked: the interpreter itself never frees most of what it allocates
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
 GKM_PYLIB=$LIB GKM_EMU_LIB=$LIB GKM_ABI_EMU_LIB=$PWD/$B/libgkm_abi_emu_asan.so python -m pytest -q -x -m "not gpu" \
-    tests/test_abi_on_emulator.py tests/test_fasta_fuzz.py tests/test_sched_properties.py tests/test_posweights_properties.py \
+    tests/test_abi_on_emulator.py tests/test_abi_vs_reference.py tests/test_pywrapper_vs_reference.py tests/test_fasta_fuzz.py tests/test_sched_properties.py tests/test_posweights_properties.py \
     tests/test_host_logic.py tests/test_index_host.py tests/test_emu_bitslice.py \
     --deselect tests/test_host_logic.py::test_library_exports_every_declared_symbol \
     --deselect tests/test_host_logic.py::test_copy_threads_policy \
