@@ -21,6 +21,9 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 
+# derandomize: every run draws the same fixed sequence of examples (a test tier must not be a lottery); the wider sweeps
+# named in DESIGN.md were run once by raising max_examples.
+
 pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref (the compiled reference) is not here")
 
 G = ctypes.POINTER(T.gkm_data)
@@ -112,7 +115,7 @@ def problems(draw):
     return (kt, L, k, d, M, H, gamma, 1), seqs
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(derandomize=True, max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(pb=problems())
 def test_same_structs_and_doubles_as_the_reference(libs, pb):
     ours, ref = libs

@@ -27,6 +27,9 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 
+# derandomize: every run draws the same fixed sequence of examples (a test tier must not be a lottery); the wider sweeps
+# named in DESIGN.md were run once by raising max_examples.
+
 pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref (the compiled reference) is not here")
 
 L = 5  # a small tree: the reference allocates 4^L leaves per open problem
@@ -82,7 +85,7 @@ def _records(P):
     return rec
 
 
-@settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(derandomize=True, max_examples=120, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(pos=fasta_text(), neg=fasta_text())
 def test_reader_agrees_with_the_reference_reader(tmp_path, pos, neg):
     lib = capi.load()

@@ -13,6 +13,9 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 
+# derandomize: every run draws the same fixed sequence of examples (a test tier must not be a lottery); the wider sweeps
+# named in DESIGN.md were run once by raising max_examples.
+
 MAX_BASES = 2047
 
 
@@ -25,7 +28,7 @@ def table(kernel_type, M, H):
     return tab
 
 
-@settings(max_examples=150, deadline=None)
+@settings(derandomize=True, max_examples=150, deadline=None)
 @given(M=st.integers(1, 255), H=st.one_of(st.floats(0.3, 3000.0, allow_nan=False), st.sampled_from([1.0, 50.0, 20.0, 0.5])),
        nk=st.integers(1, MAX_BASES - 1), kernel_type=st.sampled_from([4, 5]))
 def test_three_routes_to_the_same_bytes(M, H, nk, kernel_type):

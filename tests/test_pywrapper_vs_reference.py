@@ -19,6 +19,9 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import HealthCheck, given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 
+# derandomize: every run draws the same fixed sequence of examples (a test tier must not be a lottery); the wider sweeps
+# named in DESIGN.md were run once by raising max_examples.
+
 pytestmark = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref (the compiled reference) is not here")
 
 NMAX = 16      # rows and columns of the caller's matrix: more than any generated problem holds
@@ -61,7 +64,7 @@ def gate(o):
     return 0 <= o["kernel_type"] <= 5 and 2 <= o["L"] <= 12 and o["k"] <= o["L"] and o["d"] <= o["L"] - o["k"]
 
 
-@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@settings(derandomize=True, max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
 @given(opt=options(), pos=fasta_text(min_len=8), neg=fasta_text(min_len=8), nthreads=st.integers(1, 3))
 def test_same_return_code_matrix_and_sizes(libs, tmp_path, opt, pos, neg, nthreads):
     ours, ref = libs

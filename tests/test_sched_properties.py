@@ -13,6 +13,9 @@ hypothesis = pytest.importorskip("hypothesis")
 from hypothesis import given, settings  # noqa: E402
 from hypothesis import strategies as st  # noqa: E402
 
+# derandomize: every run draws the same fixed sequence of examples (a test tier must not be a lottery); the wider sweeps
+# named in DESIGN.md were run once by raising max_examples.
+
 
 class Chunk(ctypes.Structure):
     _fields_ = [("row_begin", ctypes.c_int), ("row_end", ctypes.c_int), ("col_begin", ctypes.c_int),
@@ -35,7 +38,7 @@ def entries_of(rb, re_, col0, cend, lower):
     return tot
 
 
-@settings(max_examples=300, deadline=None)
+@settings(derandomize=True, max_examples=300, deadline=None)
 @given(row0=st.integers(0, 5000), nrows=st.integers(0, 3000), col0=st.integers(0, 5000), ncols=st.integers(0, 3000),
        lower=st.booleans(), tile_rows=st.sampled_from([1, 2, 16, 148]), budget=st.sampled_from([8, 4096, 1 << 20, 1 << 27]),
        max_rows=st.sampled_from([0, 148, 592, 65520]))
@@ -59,7 +62,7 @@ def test_chunks_tile_any_block(row0, nrows, col0, ncols, lower, tile_rows, budge
     assert sum(c[4] for c in chunks) == entries_of(row0, row0 + nrows, col0, col0 + ncols, lower)
 
 
-@settings(max_examples=60, deadline=None)
+@settings(derandomize=True, max_examples=60, deadline=None)
 @given(n=st.integers(2000, 60000), world=st.sampled_from([1, 2, 3, 4, 8]), index=st.booleans())
 def test_round_robin_ownership_is_balanced(n, world, index):
     """the plan gkm_dev_compute makes for a lower triangle (tile 148 rows and at most 592 per chunk for the index variant,
