@@ -128,3 +128,62 @@ def test_same_structs_and_doubles_as_the_reference(libs, pb):
             assert u == v, (param, i, nm)
     for i, (x, y) in enumerate(zip(a["rows"], b["rows"])):
         assert x.tobytes() == y.tobytes(), (param, i + 1, x, y)   # bit patterns: 0 / 0 (a sequence whose only L-mer weighs 0 at M = 255) is the same NaN on both sides
+
+
+def rows_with_permutation(lib, param, seqs, queries, swaps, queries_after):
+    """init -> new_object x n -> build_tree -> batch_all(a, start, end) for the queries -> swap_index x m -> update_index ->
+    batch_all(a, start, n) for the later queries (after the update the reference's tree keeps stale pruning keys, so
+    only full-width rows are defined there: libgkm.c:1084-1109 renumbers the leaves, not the inner nodes)"""
+    par = capi.gkm_parameter(*param)
+    kern = lib.gkmkernel_init(ctypes.byref(par))
+    objs = [lib.gkmkernel_new_object(kern, s, None, i) for i, s in enumerate(seqs)]
+    assert kern and all(objs)
+    n = len(objs)
+    arrp = (G * n)(*objs)
+    lib.gkmkernel_build_tree(kern, arrp, n)
+    out = []
+    for a, s, e in queries:
+        res = np.full(max(e - s, 1), -1.5)
+        lib.gkmkernel_kernelfunc_batch_all(kern, a, s, e, res.ctypes.data_as(capi.c_dbl_p))
+        out.append(res.tobytes())
+    for i, j in swaps:
+        lib.gkmkernel_swap_index(kern, i, j)
+    lib.gkmkernel_update_index(kern)
+    for a, s in queries_after:
+        res = np.full(n - s, -1.5)
+        lib.gkmkernel_kernelfunc_batch_all(kern, a, s, n, res.ctypes.data_as(capi.c_dbl_p))
+        out.append(res.tobytes())
+    for o in objs:
+        lib.gkmkernel_delete_object(o)
+    lib.gkmkernel_destroy(kern)
+    return out
+
+
+@st.composite
+def permuted(draw):
+    param, seqs = draw(problems())
+    n = len(seqs)
+    idx = st.integers(0, n - 1)
+    queries = []
+    for _ in range(draw(st.integers(1, 4))):
+        s = draw(st.integers(0, n))
+        queries.append((draw(idx), s, draw(st.integers(s, n))))
+    swaps = draw(st.lists(st.tuples(idx, idx), min_size=0, max_size=6))
+    after = [(draw(idx), draw(st.integers(0, n - 1))) for _ in range(draw(st.integers(1, 3)))]
+    return param, seqs, queries, swaps, after
+
+
+@settings(derandomize=True, max_examples=100, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(case=permuted())
+def test_rows_ranges_and_index_permutation_like_the_reference(libs, case):
+    """gkmkernel_kernelfunc_batch_all for any (a, start, end) -- the diagonal and the columns behind it included -- and
+    gkmkernel_swap_index / gkmkernel_update_index (libgkm.c:1071-1109): the same doubles as the reference, bit for bit"""
+    ours, ref = libs
+    for lib in (ours, ref):
+        lib.gkmkernel_swap_index.restype = None
+        lib.gkmkernel_swap_index.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        lib.gkmkernel_update_index.restype = None
+        lib.gkmkernel_update_index.argtypes = [ctypes.c_void_p]
+    a, b = rows_with_permutation(ours, *case), rows_with_permutation(ref, *case)
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x == y, (case[0], i, np.frombuffer(x), np.frombuffer(y))
