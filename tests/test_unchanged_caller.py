@@ -100,3 +100,42 @@ def test_command_line_mirror_has_the_reference_options_and_defaults():
             assert o_req, name
         else:
             assert o_default == eval(default), (name, o_default, default)
+
+
+@pytest.mark.timeout(300)
+def test_unchanged_gkmsvm_sees_no_difference_between_the_two_libraries(tmp_path):
+    """CPU tier: scripts/gkmsvm.py, unchanged, run twice -- once on the reference's own gkmkern_pylib.so (oracle/_ref), once on
+    the product's HOST code (gkm_capi.c: option handling, FASTA reading, the writes into the caller's rows) over the host
+    stand-in of the device layer (test infrastructure, tests/emu/dev_stub.cc; the shipped library has no CPU path).
+    computeGkmKernel must return the same matrix and sizes, crossValidate the same AUC."""
+    import shutil
+    import pyoracle
+    import __graft_entry__ as ge
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref (the compiled reference) is not here")
+    mod = load_reference_caller()
+    emu_dir = tmp_path / "bin"
+    emu_dir.mkdir()
+    shutil.copy(ge.build_abi_emulator(), emu_dir / "gkmkern_pylib.so")     # the artefact name gkmsvm.py:85 loads
+    pos, neg = tmp_path / "pos.fa", tmp_path / "neg.fa"
+    rng = np.random.default_rng(12)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    arr = acgt[rng.integers(0, 4, (40, 120))]
+    for i in range(20):     # a motif the positives share, so that the cross-validation has something to find
+        at = int(rng.integers(0, 110))
+        arr[i, at:at + 10] = np.frombuffer(b"GATAAGGCAT", np.uint8)
+    pos.write_text("".join(">p%d desc\n%s\n" % (i, arr[i].tobytes().decode()) for i in range(20)))
+    neg.write_text("".join(">n%d\r\n%s\r\n" % (i, arr[i].tobytes().decode().lower()) for i in range(20, 40)))
+    results = []
+    try:
+        for bin_dir in (pyoracle.REF_DIR, str(emu_dir)):
+            mod.bin_dir = bin_dir
+            kmat, npos, nneg = mod.computeGkmKernel([4, 8, 5, 3, 50, 50.0, 1.0, str(pos), str(neg), 2, 0])
+            auc, std = mod.crossValidate([1.0, 1e-3, 0, 100, 4, 2, 0, 3, 2], kmat, npos, nneg)
+            results.append((kmat, npos, nneg, auc, std))
+    finally:
+        mod.bin_dir = capi.BIN_DIR
+    (k0, p0, n0, a0, s0), (k1, p1, n1, a1, s1) = results
+    assert (p0, n0) == (p1, n1) == (20, 20) and k0.shape == k1.shape == (40, 40)
+    assert np.array_equal(k0, k1)
+    assert a0 == a1 and s0 == s1 and a0 > 0.6
