@@ -139,3 +139,14 @@ def test_unchanged_gkmsvm_sees_no_difference_between_the_two_libraries(tmp_path)
     assert (p0, n0) == (p1, n1) == (20, 20) and k0.shape == k1.shape == (40, 40)
     assert np.array_equal(k0, k1)
     assert a0 == a1 and s0 == s1 and a0 > 0.6
+    # gkmqc_b200/driver.py, the mirror the GPU box uses in place of this script: the same triple from the same library
+    import ctypes
+    from gkmqc_b200 import driver
+    saved = capi._lib
+    capi._lib = ctypes.CDLL(str(emu_dir / "gkmkern_pylib.so"))
+    capi._declare(capi._lib)
+    try:
+        k2, p2, n2 = driver.computeGkmKernel([4, 8, 5, 3, 50, 50.0, 1.0, str(pos), str(neg), 2, 0], max_seqs=64)
+    finally:
+        capi._lib = saved
+    assert (p2, n2) == (20, 20) and np.array_equal(k2, k0)
